@@ -1,0 +1,68 @@
+"""The CPU oracle (oracle/plan_oracle.py) against golden vectors minted from the
+reference's own unmodified `_plan` (oracle/make_golden.py).  CPU only."""
+import pytest
+import torch
+
+from oracle.plan_oracle import draw_noise, plan_oracle
+from helpers import load_golden, stable_positions, boundary_separated
+
+CASES = ["tiny", "tiny_mt", "c1_dog5m",
+         pytest.param("c3_humanoid48m_e1", marks=pytest.mark.slow),
+         pytest.param("c4_mt80_317m_e1", marks=pytest.mark.slow)]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_golden(name):
+    cfg, sd, calls = load_golden(name)
+    from oracle.plan_oracle import OracleModel
+    model = OracleModel(cfg, sd)
+    for c in calls:
+        noise = draw_noise(cfg, c["seed"], 1, eval_mode=c["eval_mode"])
+        tr = plan_oracle(cfg, model, c["obs"][None], task=None if c["task"] is None else [c["task"]],
+                         t0=[c["t0"]], prev_mean=c["prev_mean"][None], noise=noise, eval_mode=c["eval_mode"])
+        # fp32: the oracle re-uses torch's own kernels, only the Q-ensemble goes through
+        # per-head F.linear instead of vmap/bmm -> a few ulp.  Tolerance 2e-5 abs on
+        # trajectory values (|v| ~ 1), 1e-5 on actions/means.
+        assert torch.allclose(tr.values[0], c["values"], atol=2e-5, rtol=0)
+        # observed |dv| <= 7e-7, so positions separated by > 5e-6 must agree bit-exactly
+        stable = stable_positions(c["values"], cfg.num_elites, 5e-6)
+        assert stable.float().mean() > 0.9
+        assert torch.equal(tr.elite_idx[0][stable], c["elite_idx"][stable])      # bit-exact top-k indices
+        if boundary_separated(c["values"], cfg.num_elites, 5e-6).all() and stable.all():
+            assert torch.allclose(tr.action[0], c["action"], atol=1e-5, rtol=0)
+            assert torch.allclose(tr.mean[0], c["mean"], atol=1e-5, rtol=0)
+
+
+def test_noise_stream_is_the_reference_stream():
+    """draw_noise(seed) reproduces torch.manual_seed(seed) + the reference's draw order."""
+    cfg, _, _ = load_golden("tiny")
+    n = draw_noise(cfg, 5, 1)
+    torch.manual_seed(5)
+    H, N, P, A = cfg.horizon, cfg.num_samples, cfg.num_pi_trajs, cfg.action_dim
+    for t in range(H):
+        assert torch.equal(torch.randn(P, A), n.prior[0, t])
+    for it in range(cfg.iterations):
+        assert torch.equal(torch.randn(H, N - P, A), n.r[0, it])
+        assert torch.equal(torch.randn_like(torch.empty(N, A)), n.pi[0, it])
+        assert torch.equal(torch.randperm(cfg.num_q)[:2], n.qidx[0, it])
+    assert torch.equal(torch.empty(cfg.num_elites).exponential_(), n.expo[0])
+    assert torch.equal(torch.randn(A), n.final[0])
+
+
+def test_batched_oracle_is_independent_envs():
+    cfg, sd, calls = load_golden("tiny_mt")
+    E = 3
+    g = torch.Generator().manual_seed(0)
+    obs = torch.randn(E, cfg.obs_shape["state"][0], generator=g)
+    pm = torch.randn(E, cfg.horizon, cfg.action_dim, generator=g) * 0.2
+    task, t0 = [0, 3, 1], [False, True, False]
+    noise = draw_noise(cfg, 77, E)
+    tr = plan_oracle(cfg, sd, obs, task=task, t0=t0, prev_mean=pm, noise=noise)
+    for e in range(E):
+        one = plan_oracle(cfg, sd, obs[e:e + 1], task=[task[e]], t0=[t0[e]], prev_mean=pm[e:e + 1],
+                          noise=draw_noise(cfg, 77 + e, 1))
+        assert torch.equal(one.action[0], tr.action[e])
+    # masked action dims are exactly zero (world_model.py:158-162, tdmpc2.py:180-181,195-197)
+    for e in range(E):
+        a = cfg.action_dims[task[e]]
+        assert torch.all(tr.action[e, a:] == 0) and torch.all(tr.mean[e, :, a:] == 0)
