@@ -1,0 +1,183 @@
+/*
+ * tdmpc2_b200.h -- C ABI of the B200-native TD-MPC2 planning hot path.
+ *
+ * The reference (nicklashansen/tdmpc2) has no FFI / plugin API: its planner is
+ * the Python method TDMPC2._plan (tdmpc2/tdmpc2.py:138-206) calling
+ * WorldModel.{encode,next,reward,pi,Q} (tdmpc2/common/world_model.py:103-216).
+ * This header is the boundary a binding would target instead: plain pointers
+ * and sizes, no torch types.  Each entry point names the reference code it
+ * replaces.  INTEGRATION.md shows the ctypes stub (tdmpc2_b200/_cabi.py is it).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative tdmpc2_status; the
+ *     message is available from tdmpc2_last_error() (thread-local);
+ *   - all device memory is CALLER-OWNED (torch tensors in the Python host):
+ *     contiguous, 256-byte aligned; the library never allocates device memory;
+ *   - all work is enqueued on the caller's `stream` (a cudaStream_t passed as
+ *     void*); no host synchronisation, except in create/bind/pack which are
+ *     set-up calls;
+ *   - fp32 tensors, int32 task / q-head indices, uint8 flags, int64 elite
+ *     indices (torch.topk's dtype);
+ *   - there is NO CPU fallback: every call fails with TDMPC2_ERR_NO_DEVICE
+ *     unless the current device is sm_100 (B200).
+ *
+ * Batched semantics (new in this build): a leading environment axis E.  Each
+ * environment is one independent reference _plan call (own obs, task, t0,
+ * _prev_mean, noise); E == 1 is exactly the reference.
+ */
+#ifndef TDMPC2_B200_H_
+#define TDMPC2_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDMPC2_B200_ABI_VERSION 1
+#define TDMPC2_MAX_ENC_LAYERS 8
+
+typedef enum tdmpc2_status {
+  TDMPC2_OK = 0,
+  TDMPC2_ERR_INVALID = -1,     /* bad dims / null pointer / unsupported config */
+  TDMPC2_ERR_NO_DEVICE = -2,   /* no CUDA device, or device is not sm_100      */
+  TDMPC2_ERR_CUDA = -3,        /* a CUDA runtime / driver call failed          */
+  TDMPC2_ERR_STATE = -4,       /* call order violated (e.g. plan before bind)  */
+  TDMPC2_ERR_UNSUPPORTED = -5  /* valid reference config this build lacks (episodic) */
+} tdmpc2_status;
+
+/* GEMM engine used by the fused MLP kernels. */
+typedef enum tdmpc2_engine {
+  TDMPC2_ENGINE_TCGEN05 = 0,   /* TMA + tcgen05.mma (3x fp16-split, fp32 TMEM accumulate): the product path */
+  TDMPC2_ENGINE_SIMT = 1       /* CUDA-core fp32 FFMA over the same packed operands: bring-up / diagnostics  */
+} tdmpc2_engine;
+
+/* Planner + model dimensions.  Mirrors the keys the reference reads from cfg:
+ * planning block config.yaml:33-42, architecture config.yaml:54-64, MODEL_SIZE
+ * common/__init__.py:1-24, env dims envs/__init__.py:76-82. */
+typedef struct tdmpc2_dims {
+  int32_t num_envs;        /* E  (this rank's shard)                                   */
+  int32_t num_samples;     /* N  cfg.num_samples                                        */
+  int32_t num_pi_trajs;    /* P  cfg.num_pi_trajs                                       */
+  int32_t num_elites;      /* K  cfg.num_elites                                         */
+  int32_t horizon;         /* H  cfg.horizon                                            */
+  int32_t iterations;      /* I  effective loop count (after tdmpc2.py:34's += 2)       */
+  int32_t obs_dim;         /* cfg.obs_shape['state'][0]                                 */
+  int32_t action_dim;      /* A                                                          */
+  int32_t latent_dim;      /* L                                                          */
+  int32_t mlp_dim;         /* M                                                          */
+  int32_t enc_dim;
+  int32_t num_enc_layers;  /* cfg.num_enc_layers: encoder has max(n-1,1)+1 Linear layers */
+  int32_t task_dim;        /* T, 0 for single-task                                       */
+  int32_t num_tasks;       /* len(cfg.tasks); 1 for single-task                          */
+  int32_t num_q;
+  int32_t num_bins;        /* B (two-hot regression bins; must be > 1)                   */
+  int32_t simnorm_dim;     /* 8                                                          */
+  int32_t episodic;        /* must be 0 (termination head: SURVEY.md section 8(f))       */
+  float temperature;       /* cfg.temperature                                            */
+  float min_std, max_std;
+  float log_std_min, log_std_dif;   /* WorldModel buffers, world_model.py:34-35          */
+} tdmpc2_dims;
+
+/* One Linear (+ optional LayerNorm) of the reference state dict
+ * (layers.NormedLinear, layers.py:94-111).  Device pointers, fp32, row-major
+ * `weight[out, in]` exactly as nn.Linear stores it; ln_* NULL for plain Linear. */
+typedef struct tdmpc2_linear {
+  const float* weight;
+  const float* bias;
+  const float* ln_weight;
+  const float* ln_bias;
+} tdmpc2_linear;
+
+/* Device pointers into WorldModel.state_dict() tensors. */
+typedef struct tdmpc2_weights {
+  int32_t num_enc;                              /* number of encoder Linear layers          */
+  tdmpc2_linear enc[TDMPC2_MAX_ENC_LAYERS];     /* _encoder.state.{i}.*                     */
+  tdmpc2_linear dynamics[3];                    /* _dynamics.{0,1,2}.*                      */
+  tdmpc2_linear reward[3];                      /* _reward.{0,1,2}.*   (layer 2: no LN)     */
+  tdmpc2_linear pi[3];                          /* _pi.{0,1,2}.*       (layer 2: no LN)     */
+  tdmpc2_linear qs[3];                          /* _Qs.params.{0,1,2}.* leading [num_q] dim */
+  const float* task_emb;                        /* _task_emb.weight [num_tasks, T] or NULL  */
+  const float* action_masks;                    /* _action_masks [num_tasks, A] or NULL     */
+  const float* discount_pow;                    /* [num_tasks, H+1]: gamma_task^t, computed by
+                                                   the host the way tdmpc2.py:125-132 does  */
+  const float* bins;                            /* torch.linspace(vmin, vmax, B), math.py:80 */
+} tdmpc2_weights;
+
+typedef struct tdmpc2_planner tdmpc2_planner;    /* opaque host-side context */
+
+/* ---- set-up ------------------------------------------------------------- */
+int tdmpc2_abi_version(void);
+const char* tdmpc2_last_error(void);
+
+/* Validates dims, lays out the packed-weight blob and the workspace.  Needs a
+ * current sm_100 device (queries SM count).  No device memory is allocated. */
+int tdmpc2_planner_create(const tdmpc2_dims* dims, tdmpc2_planner** out);
+void tdmpc2_planner_destroy(tdmpc2_planner* p);
+int tdmpc2_planner_packed_bytes(const tdmpc2_planner* p, size_t* out);
+int tdmpc2_planner_workspace_bytes(const tdmpc2_planner* p, size_t* out);
+/* Attach caller-owned device buffers (sizes from the two calls above), zero the
+ * workspace and encode the TMA descriptors.  Synchronous. */
+int tdmpc2_planner_bind(tdmpc2_planner* p, void* packed, void* workspace);
+int tdmpc2_planner_set_engine(tdmpc2_planner* p, int engine);
+/* Replaces: agent.load()/WorldModel.to(device) weight placement (tdmpc2.py:81-95).
+ * Packs the state-dict tensors into the kernel layout: per Linear two fp16
+ * planes (hi, lo) of weight * 2^k, K-major, zero-padded; applies the
+ * nn.Embedding(max_norm=1) renormalisation (world_model.py:21). */
+int tdmpc2_pack_weights(tdmpc2_planner* p, const tdmpc2_weights* w, void* stream);
+
+/* ---- the hot path -------------------------------------------------------- */
+/* Replaces tdmpc2.py:153-170: z = encode(obs, task); the P policy-prior
+ * trajectories; mean/std initialisation incl. the warm start from _prev_mean.
+ *   obs [E, obs_dim]; task [E] int32 or NULL (single-task); t0 [E] uint8;
+ *   prev_mean [E, H, A]; noise_prior [E, H, P, A] (draw 1 of SURVEY 8(a)). */
+int tdmpc2_plan_prologue(tdmpc2_planner* p, const float* obs, const int32_t* task,
+                         const uint8_t* t0, const float* prev_mean,
+                         const float* noise_prior, void* stream);
+
+/* Replaces ONE pass of the loop tdmpc2.py:173-197 (sample, _estimate_value
+ * :122-136, topk, MPPI weights, refit) for all E environments.
+ *   noise_r  [E, H, N-P, A]  (tdmpc2.py:176)
+ *   noise_pi [E, N, A]       (terminal pi(), world_model.py:156)
+ *   qidx     [E, 2] int32    (randperm(num_q)[:2], world_model.py:212)
+ * Optional outputs (NULL to skip): values [E, N] (after nan_to_num),
+ * elite_idx [E, K] int64 sorted by value desc (ties: lower index first). */
+int tdmpc2_plan_iter(tdmpc2_planner* p, const float* noise_r, const float* noise_pi,
+                     const int32_t* qidx, float* values_out, int64_t* elite_idx_out,
+                     void* stream);
+
+/* Replaces tdmpc2.py:199-206: gumbel pick (math.py:86-94, `expo` [E, K] are the
+ * exponential_() draws), optional exploration noise (`noise_final` [E, A], NULL
+ * == eval_mode), clamp, and the _prev_mean update.
+ *   action_out [E, A]; prev_mean_out [E, H, A]; pick_out [E] int32 or NULL. */
+int tdmpc2_plan_epilogue(tdmpc2_planner* p, const float* expo, const float* noise_final,
+                         float* action_out, float* prev_mean_out, int32_t* pick_out,
+                         void* stream);
+
+/* Current CEM state (after prologue / any iteration): mean, std [E, H, A];
+ * z [E, L]; pi_actions [E, H, P, A]; score [E, K].  NULL to skip an output. */
+int tdmpc2_plan_get_state(tdmpc2_planner* p, float* mean, float* std, float* z,
+                          float* pi_actions, float* score, void* stream);
+
+/* Replaces TDMPC2._estimate_value (tdmpc2.py:122-136) as a stand-alone call:
+ *   z [E, N, L], actions [E, H, N, A], noise_pi [E, N, A], qidx [E, 2] -> value [E, N]
+ * (no nan_to_num; E == 1 is the reference's signature). */
+int tdmpc2_estimate_value(tdmpc2_planner* p, const float* z, const float* actions,
+                          const int32_t* task, const float* noise_pi, const int32_t* qidx,
+                          float* value_out, void* stream);
+
+/* Diagnostics: y[rows, out] = act(LN(x W^T + b)) for ONE packed layer, through
+ * the same fused kernels (rows <= 128).  layer index: 0.. = enc, then dynamics
+ * 0-2, reward 0-2, pi 0-2, then q-head h layer l = base + 3*h + l.
+ * mode: 0 = raw linear output, 1 = LN+Mish, 2 = LN+SimNorm. */
+int tdmpc2_debug_layer(tdmpc2_planner* p, int layer, int mode, const float* x, int rows,
+                       float* y, void* stream);
+int tdmpc2_planner_layer_count(const tdmpc2_planner* p);
+/* Number of kernel launches this planner has enqueued so far. */
+int64_t tdmpc2_planner_launch_count(const tdmpc2_planner* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDMPC2_B200_H_ */

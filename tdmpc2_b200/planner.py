@@ -1,0 +1,266 @@
+"""Python host of the fused B200 planner: owns the device buffers (torch tensors)
+and drives the C ABI (include/tdmpc2_b200.h).  torch is plumbing here -- device
+memory, streams, RNG -- the planning math runs in the sm_100a kernels.
+
+Call sequence of one `plan()` (reference tdmpc2.py:138-206):
+    prologue  -> encode, policy-prior trajectories, mean/std init
+    I x iter  -> sample, H-step latent rollout, value, top-k, MPPI refit
+    epilogue  -> gumbel pick, exploration noise, clamp, _prev_mean update
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+
+from . import _cabi
+from .config import Config, get_discount
+
+
+@dataclass
+class Noise:
+    """All random numbers of one batched plan() in reference draw order
+    (SURVEY.md section 8(a)).  Shapes: prior [E,H,P,A], r [E,I,H,N-P,A],
+    pi [E,I,N,A], qidx [E,I,2] int32, expo [E,K], final [E,A] or None (eval_mode)."""
+    prior: torch.Tensor
+    r: torch.Tensor
+    pi: torch.Tensor
+    qidx: torch.Tensor
+    expo: torch.Tensor
+    final: Optional[torch.Tensor]
+
+
+def draw_noise(cfg: Config, num_envs: int, device, eval_mode: bool = False,
+               generator: Optional[torch.Generator] = None, reference_order: Optional[bool] = None) -> Noise:
+    """Draw the planner's noise with torch's generator on `device`.
+
+    reference_order (default: num_envs == 1): issue the draws one by one in the
+    order and shapes of the reference's `_plan` (H x randn[P,A]; per iteration
+    randn[H,N-P,A], randn[N,A], randperm(num_q); exponential_[K]; randn[A]) so a
+    single-env agent consumes the generator exactly like the reference does.
+    Otherwise each kind of draw is one batched call over all environments.
+    """
+    H, N, P, A, I, K = (cfg.horizon, cfg.num_samples, cfg.num_pi_trajs, cfg.action_dim,
+                        cfg.iterations, cfg.num_elites)
+    E, g = num_envs, generator
+    kw = dict(device=device, dtype=torch.float32, generator=g)
+    if reference_order is None:
+        reference_order = (E == 1)
+    if reference_order and E == 1:
+        prior = torch.zeros(1, H, max(P, 0), A, device=device)
+        for t in range(H if P > 0 else 0):
+            prior[0, t] = torch.randn(P, A, **kw)
+        r = torch.empty(1, I, H, N - P, A, device=device)
+        pi = torch.empty(1, I, N, A, device=device)
+        qidx = torch.empty(1, I, 2, device=device, dtype=torch.int32)
+        for it in range(I):
+            r[0, it] = torch.randn(H, N - P, A, **kw)
+            pi[0, it] = torch.randn(N, A, **kw)
+            qidx[0, it] = torch.randperm(cfg.num_q, device=device, generator=g)[:2].to(torch.int32)
+        expo = torch.empty(1, K, device=device).exponential_(generator=g)
+        final = None if eval_mode else torch.randn(A, **kw).view(1, A)
+        return Noise(prior, r, pi, qidx, expo, final)
+    prior = torch.randn(E, H, P, A, **kw)
+    r = torch.randn(E, I, H, N - P, A, **kw)
+    pi = torch.randn(E, I, N, A, **kw)
+    # randperm(num_q)[:2] per (env, iteration): the two smallest of num_q iid uniforms
+    qidx = torch.rand(E, I, cfg.num_q, **kw).argsort(dim=-1)[..., :2].to(torch.int32).contiguous()
+    expo = torch.empty(E, K, device=device).exponential_(generator=g)
+    final = None if eval_mode else torch.randn(E, A, **kw)
+    return Noise(prior, r, pi, qidx, expo, final)
+
+
+def discount_table(cfg: Config, device) -> torch.Tensor:
+    """[num_tasks, H+1] fp32: the running `discount` of tdmpc2.py:125-132 after t steps.
+    Single-task: a Python float product (double) cast to fp32 when it multiplies
+    the fp32 reward tensor; multi-task: an fp32 tensor product."""
+    H = cfg.horizon
+    if cfg.multitask:
+        g = torch.tensor([get_discount(cfg, ep) for ep in cfg.episode_lengths], dtype=torch.float32)
+        cols, d = [torch.ones_like(g)], torch.ones_like(g)
+        for _ in range(H):
+            d = d * g
+            cols.append(d)
+        return torch.stack(cols, dim=1).contiguous().to(device)
+    g, d, vals = get_discount(cfg, cfg.episode_length), 1, [1.0]
+    for _ in range(H):
+        d = d * g
+        vals.append(d)
+    return torch.tensor([vals], dtype=torch.float32, device=device)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class Planner:
+    """Owns one tdmpc2_planner handle plus its packed weights and workspace."""
+
+    def __init__(self, cfg: Config, num_envs: int, device, engine: str = "tcgen05"):
+        self.lib = _cabi.load()                         # raises if the .so is missing
+        self.cfg, self.E = cfg, int(num_envs)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _cabi.CabiError("the B200 planner needs a CUDA device; there is no CPU fallback")
+        d = _cabi.Dims(
+            num_envs=self.E, num_samples=cfg.num_samples, num_pi_trajs=cfg.num_pi_trajs, num_elites=cfg.num_elites,
+            horizon=cfg.horizon, iterations=cfg.iterations, obs_dim=cfg.obs_shape["state"][0],
+            action_dim=cfg.action_dim, latent_dim=cfg.latent_dim, mlp_dim=cfg.mlp_dim, enc_dim=cfg.enc_dim,
+            num_enc_layers=cfg.num_enc_layers, task_dim=cfg.task_dim if cfg.multitask else 0,
+            num_tasks=len(cfg.tasks) if cfg.multitask else 1, num_q=cfg.num_q, num_bins=cfg.num_bins,
+            simnorm_dim=cfg.simnorm_dim, episodic=int(bool(cfg.episodic)), temperature=cfg.temperature,
+            min_std=cfg.min_std, max_std=cfg.max_std, log_std_min=float(cfg.log_std_min),
+            log_std_dif=float(cfg.log_std_max) - float(cfg.log_std_min))
+        self._dims = d
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.tdmpc2_planner_create(C.byref(d), C.byref(h)))
+            self.h = h
+            nb = C.c_size_t()
+            _cabi.check(self.lib.tdmpc2_planner_packed_bytes(h, C.byref(nb)))
+            self.packed = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
+            _cabi.check(self.lib.tdmpc2_planner_workspace_bytes(h, C.byref(nb)))
+            self.workspace = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
+            _cabi.check(self.lib.tdmpc2_planner_bind(h, self.packed.data_ptr(), self.workspace.data_ptr()))
+        self.set_engine(engine)
+        self._keep = []       # tensors referenced by in-flight async calls
+        self.weights_version = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.tdmpc2_planner_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def set_engine(self, engine: str) -> None:
+        code = {"tcgen05": _cabi.ENGINE_TCGEN05, "simt": _cabi.ENGINE_SIMT}[engine]
+        _cabi.check(self.lib.tdmpc2_planner_set_engine(self.h, code))
+        self.engine = engine
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.tdmpc2_planner_launch_count(self.h))
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # ------------------------------------------------------------------ weights
+    def pack(self, sd: Dict[str, torch.Tensor]) -> None:
+        """Pack a reference-layout state dict (tensors on any device) for the kernels."""
+        cfg = self.cfg
+        f = lambda k: sd[k].detach().to(self.device, torch.float32).contiguous()
+        keep = []
+
+        def lin(prefix):
+            w, b = f(prefix + ".weight"), f(prefix + ".bias")
+            keep.extend([w, b])
+            g = beta = None
+            if prefix + ".ln.weight" in sd:
+                g, beta = f(prefix + ".ln.weight"), f(prefix + ".ln.bias")
+                keep.extend([g, beta])
+            return _cabi.Linear(_ptr(w), _ptr(b), _ptr(g), _ptr(beta))
+
+        W = _cabi.Weights()
+        n = 0
+        while f"_encoder.state.{n}.weight" in sd:
+            W.enc[n] = lin(f"_encoder.state.{n}")
+            n += 1
+        W.num_enc = n
+        for i in range(3):
+            W.dynamics[i] = lin(f"_dynamics.{i}")
+            W.reward[i] = lin(f"_reward.{i}")
+            W.pi[i] = lin(f"_pi.{i}")
+            W.qs[i] = lin(f"_Qs.params.{i}")
+        if cfg.multitask:
+            emb, masks = f("_task_emb.weight"), f("_action_masks")
+            keep.extend([emb, masks])
+            W.task_emb, W.action_masks = _ptr(emb), _ptr(masks)
+        disc = discount_table(cfg, self.device)
+        bins = torch.linspace(cfg.vmin, cfg.vmax, cfg.num_bins, device=self.device, dtype=torch.float32)  # math.py:80
+        keep.extend([disc, bins])
+        W.discount_pow, W.bins = _ptr(disc), _ptr(bins)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.tdmpc2_pack_weights(self.h, C.byref(W), self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()   # `keep` tensors may be freed afterwards
+
+    # ------------------------------------------------------------------ hot path
+    def prologue(self, obs, task, t0, prev_mean, noise_prior) -> None:
+        self._keep = [obs, task, t0, prev_mean, noise_prior]
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.tdmpc2_plan_prologue(self.h, _ptr(obs), _ptr(task), _ptr(t0), _ptr(prev_mean),
+                                                      _ptr(noise_prior), self._stream()))
+
+    def iterate(self, noise_r, noise_pi, qidx, values_out=None, elite_idx_out=None) -> None:
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.tdmpc2_plan_iter(self.h, _ptr(noise_r), _ptr(noise_pi), _ptr(qidx),
+                                                  _ptr(values_out), _ptr(elite_idx_out), self._stream()))
+
+    def epilogue(self, expo, noise_final, action_out, prev_mean_out, pick_out=None) -> None:
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.tdmpc2_plan_epilogue(self.h, _ptr(expo), _ptr(noise_final), _ptr(action_out),
+                                                      _ptr(prev_mean_out), _ptr(pick_out), self._stream()))
+
+    def get_state(self) -> Dict[str, torch.Tensor]:
+        cfg, E = self.cfg, self.E
+        kw = dict(device=self.device, dtype=torch.float32)
+        out = dict(mean=torch.empty(E, cfg.horizon, cfg.action_dim, **kw),
+                   std=torch.empty(E, cfg.horizon, cfg.action_dim, **kw),
+                   z=torch.empty(E, cfg.latent_dim, **kw),
+                   pi_actions=torch.zeros(E, cfg.horizon, cfg.num_pi_trajs, cfg.action_dim, **kw),
+                   score=torch.empty(E, cfg.num_elites, **kw))
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.tdmpc2_plan_get_state(self.h, _ptr(out["mean"]), _ptr(out["std"]), _ptr(out["z"]),
+                                                       _ptr(out["pi_actions"]), _ptr(out["score"]), self._stream()))
+        return out
+
+    def plan(self, obs, task, t0, prev_mean, noise: Noise, trace: bool = False):
+        """One batched plan().  obs [E,obs_dim] f32, task [E] int32 | None, t0 [E] uint8,
+        prev_mean [E,H,A] f32 (all on self.device, contiguous).  Returns (action [E,A],
+        new prev_mean [E,H,A], trace dict | None)."""
+        cfg, E, dev = self.cfg, self.E, self.device
+        action = torch.empty(E, cfg.action_dim, device=dev, dtype=torch.float32)
+        new_mean = torch.empty(E, cfg.horizon, cfg.action_dim, device=dev, dtype=torch.float32)
+        tr = None
+        if trace:
+            tr = dict(values=torch.empty(E, cfg.iterations, cfg.num_samples, device=dev),
+                      elite_idx=torch.empty(E, cfg.iterations, cfg.num_elites, device=dev, dtype=torch.int64),
+                      iter_mean=[], iter_std=[], pick=torch.empty(E, device=dev, dtype=torch.int32))
+        self.prologue(obs, task, t0, prev_mean, noise.prior)
+        if trace:
+            st = self.get_state()
+            tr["z"], tr["pi_actions"] = st["z"], st["pi_actions"]
+        for it in range(cfg.iterations):
+            nr, npi, qi = noise.r[:, it].contiguous(), noise.pi[:, it].contiguous(), noise.qidx[:, it].contiguous()
+            self._keep.extend([nr, npi, qi])
+            if trace:
+                v, ei = torch.empty(E, cfg.num_samples, device=dev), torch.empty(E, cfg.num_elites, device=dev, dtype=torch.int64)
+                self.iterate(nr, npi, qi, v, ei)
+                tr["values"][:, it], tr["elite_idx"][:, it] = v, ei
+                st = self.get_state()
+                tr["iter_mean"].append(st["mean"]); tr["iter_std"].append(st["std"])
+            else:
+                self.iterate(nr, npi, qi)
+        if trace:
+            tr["score"] = self.get_state()["score"]
+            tr["iter_mean"], tr["iter_std"] = torch.stack(tr["iter_mean"], 1), torch.stack(tr["iter_std"], 1)
+        self.epilogue(noise.expo, noise.final, action, new_mean, tr["pick"] if trace else None)
+        return action, new_mean, tr
+
+    def estimate_value(self, z, actions, task, noise_pi, qidx):
+        """z [E,N,L], actions [E,H,N,A], noise_pi [E,N,A], qidx [E,2] int32 -> [E,N]."""
+        out = torch.empty(self.E, self.cfg.num_samples, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.tdmpc2_estimate_value(self.h, _ptr(z), _ptr(actions), _ptr(task), _ptr(noise_pi),
+                                                       _ptr(qidx), _ptr(out), self._stream()))
+        return out
+
+    def debug_layer(self, layer: int, mode: int, x: torch.Tensor, out_features: int) -> torch.Tensor:
+        y = torch.empty(x.shape[0], out_features, device=self.device, dtype=torch.float32)
+        x = x.contiguous()
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.tdmpc2_debug_layer(self.h, layer, mode, _ptr(x), x.shape[0], _ptr(y), self._stream()))
+        return y

@@ -1,0 +1,152 @@
+"""TDMPC2 agent with the reference's inference surface, planning on the B200 kernels.
+
+Drop-in for the inference half of the reference class `TDMPC2`
+(tdmpc2/tdmpc2.py:10-206): `TDMPC2(cfg)`, `.model`, `.cfg`, `.device`,
+`._prev_mean`, `.discount`, `.load()`, `.save()`, `.act()`, `.plan`, `._plan()`,
+`._estimate_value()` keep their names, argument meaning and return shapes, so
+`evaluate.py:57-80` of the reference runs unchanged on it.
+Training (`update`, optimisers, RunningScale) is out of scope (SURVEY.md 2.1 #1b).
+
+New: an environments axis.  `obs [E, obs_dim]`, `t0 [E]`, `task [E]` plan E
+independent environments in one call; E == 1 (1-D obs) is the reference API.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Union
+
+import torch
+
+from .config import Config, get_discount
+from .planner import Noise, Planner, draw_noise
+from .world_model import WorldModel, convert_legacy_checkpoint
+
+
+class TDMPC2(torch.nn.Module):
+    def __init__(self, cfg: Config, device: Union[str, torch.device, None] = None, engine: str = "tcgen05"):
+        super().__init__()
+        self.cfg = cfg
+        self.device = torch.device("cuda:0" if device is None else device)      # tdmpc2.py:20
+        self.model = WorldModel(cfg).to(self.device)
+        self.model.eval()                                                        # tdmpc2.py:32
+        if not cfg.get("iterations_effective", False):
+            self.cfg.iterations += 2 * int(cfg.action_dim >= 20)                # tdmpc2.py:34
+            self.cfg.iterations_effective = True
+        self.discount = torch.tensor(
+            [get_discount(cfg, ep) for ep in cfg.episode_lengths], device=self.device
+        ) if cfg.multitask else get_discount(cfg, cfg.episode_length)           # tdmpc2.py:35-37
+        self.num_envs = int(cfg.get("num_envs", 1) or 1)
+        shape = (cfg.horizon, cfg.action_dim) if self.num_envs == 1 else (self.num_envs, cfg.horizon, cfg.action_dim)
+        self._prev_mean = torch.nn.Buffer(torch.zeros(*shape, device=self.device))   # tdmpc2.py:40
+        self._engine = engine
+        self._planner: Optional[Planner] = None
+        self._weights_dirty = True
+        self.generator: Optional[torch.Generator] = None     # None -> torch's default CUDA generator, like the reference
+
+    # ------------------------------------------------------------------ planner plumbing
+    @property
+    def planner(self) -> Planner:
+        if self._planner is None:
+            self._planner = Planner(self.cfg, self.num_envs, self.device, engine=self._engine)
+            self._weights_dirty = True
+        if self._weights_dirty:
+            self._planner.pack(self.model.state_dict())
+            self._weights_dirty = False
+        return self._planner
+
+    def sync_weights(self) -> None:
+        """Call after modifying `self.model`'s parameters in place."""
+        self._weights_dirty = True
+
+    @property
+    def plan(self):
+        # The reference wraps _plan in torch.compile(mode="reduce-overhead") (tdmpc2.py:45-55);
+        # here the fused kernels are the compiled artefact, so `plan` is `_plan`.
+        return self._plan
+
+    def save(self, fp):
+        torch.save({"model": self.model.state_dict()}, fp)                       # tdmpc2.py:72-79
+
+    def load(self, fp):
+        """tdmpc2.py:81-95: path or dict, optional {"model": ...} wrapper, legacy-key conversion."""
+        if isinstance(fp, dict):
+            state_dict = fp
+        else:
+            state_dict = torch.load(fp, map_location=self.device, weights_only=False)
+        state_dict = state_dict["model"] if "model" in state_dict else state_dict
+        state_dict = convert_legacy_checkpoint(self.model.state_dict(), dict(state_dict))
+        self.model.load_state_dict(state_dict)
+        self._weights_dirty = True
+
+    # ------------------------------------------------------------------ inference API
+    @torch.no_grad()
+    def act(self, obs, t0=False, eval_mode=False, task=None):
+        """tdmpc2.py:97-120.  obs [obs_dim] (CPU) -> action [A] (CPU); or batched
+        obs [E, obs_dim], t0 bool | [E], task int | [E] -> [E, A]."""
+        obs = obs.to(self.device, non_blocking=True)
+        batched = obs.ndim == 2
+        if not batched:
+            obs = obs.unsqueeze(0)
+        if task is not None and not torch.is_tensor(task):
+            task = torch.tensor([task] if isinstance(task, int) else list(task), device=self.device)
+        if self.cfg.mpc:
+            out = self._plan(obs, t0=t0, eval_mode=eval_mode, task=task)
+            return out.cpu()
+        z = self.model.encode(obs, task)
+        action, info = self.model.pi(z, task)
+        if eval_mode:
+            action = info["mean"]
+        return (action if batched else action[0]).cpu()
+
+    @torch.no_grad()
+    def _plan(self, obs, t0=False, eval_mode=False, task=None, noise: Optional[Noise] = None, return_trace=False):
+        """tdmpc2.py:138-206 on the fused kernels.  obs [1|E, obs_dim] on self.device.
+        Returns action [A] when planning a single environment (reference shape),
+        else [E, A]."""
+        cfg, E, dev = self.cfg, self.num_envs, self.device
+        obs = obs.to(dev, torch.float32)
+        if obs.ndim == 1:
+            obs = obs.unsqueeze(0)
+        if obs.shape[0] != E:
+            raise ValueError(f"obs has {obs.shape[0]} environments, agent was built for cfg.num_envs={E}")
+        obs = obs.contiguous()
+        if torch.is_tensor(t0):
+            t0v = t0.to(dev).reshape(-1).to(torch.uint8)
+            t0v = t0v.expand(E).contiguous() if t0v.numel() == 1 else t0v.contiguous()
+        else:
+            t0v = torch.full((E,), int(bool(t0)), dtype=torch.uint8, device=dev) if not isinstance(t0, (list, tuple)) \
+                else torch.tensor([int(bool(x)) for x in t0], dtype=torch.uint8, device=dev)
+        taskv = None
+        if cfg.multitask:
+            if task is None:
+                raise ValueError("multi-task model needs `task`")
+            taskv = torch.as_tensor(task, device=dev).reshape(-1).to(torch.int32)
+            taskv = taskv.expand(E).contiguous() if taskv.numel() == 1 else taskv.contiguous()
+        if noise is None:
+            noise = draw_noise(cfg, E, dev, eval_mode=eval_mode, generator=self.generator)
+        elif eval_mode:
+            noise = Noise(noise.prior, noise.r, noise.pi, noise.qidx, noise.expo, None)
+        prev = self._prev_mean.reshape(E, cfg.horizon, cfg.action_dim).contiguous()
+        action, new_mean, trace = self.planner.plan(obs, taskv, t0v, prev, noise, trace=return_trace)
+        self._prev_mean.copy_(new_mean.reshape(self._prev_mean.shape))           # tdmpc2.py:205
+        out = action[0] if E == 1 else action
+        return (out, trace) if return_trace else out
+
+    @torch.no_grad()
+    def _estimate_value(self, z, actions, task, eps_pi=None, qidx=None):
+        """tdmpc2.py:122-136.  z [N, L], actions [H, N, A] -> [N, 1]  (E == 1), or
+        z [E, N, L], actions [E, H, N, A] -> [E, N, 1]."""
+        cfg, E, dev = self.cfg, self.num_envs, self.device
+        single = z.ndim == 2
+        zb = (z.unsqueeze(0) if single else z).to(dev, torch.float32).contiguous()
+        ab = (actions.unsqueeze(0) if single else actions).to(dev, torch.float32).contiguous()
+        if eps_pi is None:
+            eps_pi = torch.randn(E, cfg.num_samples, cfg.action_dim, device=dev, generator=self.generator)
+        if qidx is None:
+            qidx = torch.rand(E, cfg.num_q, device=dev, generator=self.generator).argsort(-1)[:, :2]
+        taskv = None
+        if cfg.multitask:
+            taskv = torch.as_tensor(task, device=dev).reshape(-1).to(torch.int32)
+            taskv = taskv.expand(E).contiguous() if taskv.numel() == 1 else taskv.contiguous()
+        v = self.planner.estimate_value(zb, ab, taskv, eps_pi.reshape(E, cfg.num_samples, cfg.action_dim).contiguous(),
+                                        qidx.reshape(E, 2).to(torch.int32).contiguous())
+        return v[0].unsqueeze(-1) if single else v.unsqueeze(-1)

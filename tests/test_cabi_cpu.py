@@ -1,0 +1,119 @@
+"""CPU-side checks of the boundary: the C-ABI library loads, exports every symbol the
+header declares, and refuses to run without a B200 (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from tdmpc2_b200 import build, _cabi
+    build.build()
+    return _cabi.load()
+
+
+def test_library_exports_every_header_symbol(lib):
+    from tdmpc2_b200 import _cabi
+    hdr = open(os.path.join(ROOT, "include", "tdmpc2_b200.h")).read()
+    declared = set(re.findall(r"\b(tdmpc2_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"tdmpc2_planner"}
+    assert declared == set(_cabi.SYMBOLS), declared ^ set(_cabi.SYMBOLS)
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert lib.tdmpc2_abi_version() == 1
+
+
+def test_struct_layout_matches_header():
+    from tdmpc2_b200 import _cabi
+    assert C.sizeof(_cabi.Dims) == 18 * 4 + 5 * 4
+    assert C.sizeof(_cabi.Linear) == 4 * 8
+    assert C.sizeof(_cabi.Weights) == 8 + (_cabi.MAX_ENC_LAYERS + 12) * 32 + 4 * 8
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback(lib):
+    from tdmpc2_b200 import _cabi
+    from tdmpc2_b200.config import workload
+    from tdmpc2_b200.planner import Planner
+    with pytest.raises(_cabi.CabiError):
+        Planner(workload("tiny"), 1, "cpu")
+    d = _cabi.Dims(num_envs=1, num_samples=128, num_pi_trajs=8, num_elites=16, horizon=3, iterations=2, obs_dim=8,
+                   action_dim=4, latent_dim=64, mlp_dim=64, enc_dim=64, num_enc_layers=2, task_dim=0, num_tasks=1,
+                   num_q=2, num_bins=101, simnorm_dim=8, episodic=0, temperature=0.5, min_std=0.05, max_std=2.0,
+                   log_std_min=-10.0, log_std_dif=12.0)
+    h = C.c_void_p()
+    rc = lib.tdmpc2_planner_create(C.byref(d), C.byref(h))
+    assert rc == -2 and b"no CUDA device" in lib.tdmpc2_last_error()       # TDMPC2_ERR_NO_DEVICE
+    d.episodic = 1
+    assert lib.tdmpc2_planner_create(C.byref(d), C.byref(h)) == -5          # TDMPC2_ERR_UNSUPPORTED
+
+
+def test_world_model_state_dict_layout():
+    """WorldModel.state_dict() has exactly the reference's keys."""
+    from tdmpc2_b200.config import workload
+    from tdmpc2_b200.synth import synth_state_dict
+    from tdmpc2_b200.world_model import WorldModel, convert_legacy_checkpoint
+    for wl in ("tiny", "tiny-mt"):
+        cfg = workload(wl)
+        m = WorldModel(cfg)
+        sd = m.state_dict()
+        want = synth_state_dict(cfg, seed=3, perturb=True)
+        meta = {k for k in sd if k.endswith(("__batch_size", "__device"))}
+        assert meta == {p + s for p in ("_Qs.params.", "_detach_Qs_params.", "_target_Qs_params.")
+                        for s in ("__batch_size", "__device")}
+        assert set(sd) - meta == set(want)
+        assert sd["_Qs.params.__batch_size"] == torch.Size([cfg.num_q])
+        for k in want:
+            assert tuple(sd[k].shape) == tuple(want[k].shape), k
+        m.load_state_dict(want)
+        got = m.state_dict()
+        for k in want:
+            assert torch.equal(got[k], want[k]), k
+        # zero-init of the reward / Q output layers (world_model.py:32)
+        fresh = WorldModel(cfg).state_dict()
+        assert fresh["_reward.2.weight"].abs().sum() == 0 and fresh["_Qs.params.2.weight"].abs().sum() == 0
+        assert fresh["_detach_Qs_params.0.weight"].data_ptr() == fresh["_Qs.params.0.weight"].data_ptr()
+        # legacy (pre-compile API) checkpoints: _Qs.params.<n>, _target_Qs.params.<n>
+        legacy = {k: v for k, v in want.items() if "Qs" not in k}
+        names = ["weight", "bias", "ln.weight", "ln.bias"]
+        for layer in range(3):
+            for j, nm in enumerate(names):
+                key = f"{layer}.{nm}"
+                if "_Qs.params." + key in want:
+                    legacy[f"_Qs.params.{4 * layer + j}"] = want["_Qs.params." + key]
+                    legacy[f"_target_Qs.params.{4 * layer + j}"] = want["_target_Qs_params." + key]
+        conv = convert_legacy_checkpoint(m.state_dict(), legacy)
+        m2 = WorldModel(cfg)
+        m2.load_state_dict(conv)
+        for k in want:
+            assert torch.equal(m2.state_dict()[k], want[k]), k
+
+
+def test_world_model_forward_matches_oracle_model():
+    from oracle.plan_oracle import OracleModel
+    from tdmpc2_b200.config import workload
+    from tdmpc2_b200.synth import synth_state_dict
+    from tdmpc2_b200.world_model import WorldModel
+    cfg = workload("tiny-mt")
+    sd = synth_state_dict(cfg, seed=4, perturb=True, emb_scale=60.0)
+    m = WorldModel(cfg).eval()
+    m.load_state_dict(sd)
+    om = OracleModel(cfg, sd)
+    g = torch.Generator().manual_seed(0)
+    obs = torch.randn(5, cfg.obs_shape["state"][0], generator=g)
+    a = torch.rand(5, cfg.action_dim, generator=g)
+    eps = torch.randn(5, cfg.action_dim, generator=g)
+    task = torch.tensor([2])
+    with torch.no_grad():
+        z = m.encode(obs, task)
+        assert torch.allclose(z, om.encode(obs, 2), atol=1e-6)
+        assert torch.allclose(m.next(z, a, task), om.next(z, a, 2), atol=1e-6)
+        assert torch.allclose(m.reward(z, a, task), om.reward(z, a, 2), atol=1e-5)
+        assert torch.allclose(m.pi(z, task, eps=eps)[0], om.pi(z, 2, eps), atol=1e-6)
+        q = m.Q(z, a, task, return_type="avg", qidx=torch.tensor([3, 1]))
+        assert torch.allclose(q, om.Q_avg(z, a, 2, [3, 1]), atol=1e-5)
