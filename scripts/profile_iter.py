@@ -1,0 +1,24 @@
+"""One-wave slice of the c2 workload for ncu: prologue + a few CEM-iteration launches."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from tdmpc2_b200.config import workload
+from tdmpc2_b200.synth import synth_state_dict
+from tdmpc2_b200.planner import Planner, draw_noise
+
+wl = sys.argv[1] if len(sys.argv) > 1 else "c2"
+E = int(sys.argv[2]) if len(sys.argv) > 2 else 37
+iters = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+cfg = workload(wl, num_envs=E)
+pl = Planner(cfg, E, "cuda:0")
+pl.pack(synth_state_dict(cfg, seed=1))
+dev = torch.device("cuda:0")
+n = draw_noise(cfg, E, dev)
+obs = torch.randn(E, cfg.obs_shape["state"][0], device=dev)
+task = (torch.arange(E) % len(cfg.tasks)).to(torch.int32).to(dev) if cfg.multitask else None
+pl.prologue(obs, task, torch.ones(E, dtype=torch.uint8, device=dev), torch.zeros(E, cfg.horizon, cfg.action_dim, device=dev), n.prior)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for i in range(iters):
+    a = (n.r[:, i].contiguous(), n.pi[:, i].contiguous(), n.qidx[:, i].contiguous())
+    e0.record(); pl.iterate(*a); e1.record(); torch.cuda.synchronize()
+    print(f"iter {i}: {e0.elapsed_time(e1):.3f} ms (E={E}, tiles={E * ((cfg.num_samples + 127) // 128)})")
