@@ -18,7 +18,7 @@ SYMBOLS = [
     "tdmpc2_planner_packed_bytes", "tdmpc2_planner_workspace_bytes", "tdmpc2_planner_bind",
     "tdmpc2_planner_set_engine", "tdmpc2_pack_weights", "tdmpc2_plan_prologue", "tdmpc2_plan_iter",
     "tdmpc2_plan_epilogue", "tdmpc2_plan_get_state", "tdmpc2_estimate_value", "tdmpc2_debug_layer",
-    "tdmpc2_planner_layer_count", "tdmpc2_planner_launch_count",
+    "tdmpc2_planner_layer_count", "tdmpc2_planner_launch_count", "tdmpc2_planner_set_profile",
 ]
 
 
@@ -79,6 +79,7 @@ def load():
     lib.tdmpc2_estimate_value.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     lib.tdmpc2_debug_layer.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp]
     lib.tdmpc2_planner_layer_count.argtypes = [vp]
+    lib.tdmpc2_planner_set_profile.argtypes = [vp, vp]
     lib.tdmpc2_planner_launch_count.argtypes = [vp]
     lib.tdmpc2_planner_launch_count.restype = i64
     for s in SYMBOLS:

@@ -50,8 +50,16 @@ __global__ void absmax_kernel(const float* __restrict__ w, size_t n, unsigned* s
 
 // W[N, K] fp32 row-major -> two fp16 planes [Npad, Kpad] of W * 2^k, zero padded.
 // 2^k puts max|W| in [128, 256): fp16 hi keeps 11 bits, lo the next 11, both in the normal range.
+// Output row n takes source row n (n < split_at) or split_at + (n - split_to) (n >= split_to): the pi head's
+// log_std rows are moved to a 32-aligned column so the fused epilogue reads them with aligned tcgen05.ld.
+__device__ __forceinline__ int src_index(int n, int src_n, int split_at, int split_to) {
+  if (n < split_at) return n;
+  if (n >= split_to && n - split_to + split_at < src_n) return n - split_to + split_at;
+  return -1;
+}
 __global__ void split_weight_kernel(const float* __restrict__ w, int N, int K, int Npad, int Kpad, __half* hi,
-                                    __half* lo, const unsigned* absmax_slot, LayerDev* entry) {
+                                    __half* lo, const unsigned* absmax_slot, LayerDev* entry, int src_n, int split_at,
+                                    int split_to) {
   const float amax = __uint_as_float(*absmax_slot);
   int ex = 0;
   float scale = 1.f;
@@ -65,16 +73,20 @@ __global__ void split_weight_kernel(const float* __restrict__ w, int N, int K, i
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int n = static_cast<int>(i / Kpad), k = static_cast<int>(i % Kpad);
     float x = 0.f;
-    if (n < N && k < K) x = w[static_cast<size_t>(n) * K + k] * scale;
+    const int sn = src_index(n, src_n, split_at, split_to);
+    if (n < N && k < K && sn >= 0) x = w[static_cast<size_t>(sn) * K + k] * scale;
     const __half h = __float2half_rn(x);
     hi[i] = h;
     lo[i] = __float2half_rn(x - __half2float(h));
   }
 }
 
-__global__ void pad_vector_kernel(const float* __restrict__ src, int n, int npad, float* dst, float fill) {
+__global__ void pad_vector_kernel(const float* __restrict__ src, int n, int npad, float* dst, float fill, int src_n,
+                                  int split_at, int split_to) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < npad) dst[i] = (i < n && src) ? src[i] : fill;
+  if (i >= npad) return;
+  const int si = src_index(i, src_n, split_at, split_to);
+  dst[i] = (i < n && src && si >= 0) ? src[si] : fill;
 }
 
 // nn.Embedding(max_norm=1) (world_model.py:21): rows with ||w|| > 1 are scaled by 1/(||w|| + 1e-7) at lookup.
@@ -91,6 +103,7 @@ __global__ void emb_renorm_kernel(const float* __restrict__ emb, int T, float* o
 // ------------------------------------------------------------------------------------ planner
 struct LayerHost {
   int K, Kpad, N, Npad, wmap, wrow, has_ln;
+  int src_n, split_at, split_to;                   // source rows and the optional row remap (pi head)
   size_t off_hi, off_lo, off_bias, off_g, off_b;   // byte offsets into the packed blob
 };
 
@@ -116,11 +129,13 @@ struct tdmpc2_planner {
   bool bound = false, weights_ok = false, smem_attr_set[2] = {false, false};
   int64_t launches = 0;
   const int32_t* cur_task = nullptr;
+  long long* prof = nullptr;
 };
 
 static int add_layer(tdmpc2_planner* p, int K, int N, bool has_ln) {
   LayerHost l{};
   l.K = K; l.Kpad = pad_to(K, kKch); l.N = N; l.Npad = pad_to(N, 128); l.has_ln = has_ln ? 1 : 0;
+  l.src_n = N; l.split_at = N; l.split_to = N;
   int m = -1;
   for (int i = 0; i < p->nmaps; ++i) if (p->map_kpad[i] == l.Kpad) m = i;
   if (m < 0) {
@@ -168,8 +183,8 @@ extern "C" int tdmpc2_planner_create(const tdmpc2_dims* dims, tdmpc2_planner** o
     return fail(TDMPC2_ERR_INVALID, "num_pi_trajs must be in [0, min(128, num_samples)]");
   if (d.num_samples > 4096) return fail(TDMPC2_ERR_INVALID, "num_samples > 4096 unsupported");
   if (d.num_elites > 1024) return fail(TDMPC2_ERR_INVALID, "num_elites > 1024 unsupported");
-  if (2 * d.action_dim > kMaxHeadCols || d.num_bins > kMaxHeadCols)
-    return fail(TDMPC2_ERR_INVALID, "2*action_dim and num_bins must be <= %d", kMaxHeadCols);
+  if (pad_to(d.action_dim, 32) + d.action_dim > kMaxHeadCols || d.num_bins > kMaxHeadCols)
+    return fail(TDMPC2_ERR_INVALID, "pad32(action_dim)+action_dim and num_bins must be <= %d", kMaxHeadCols);
   if (d.simnorm_dim != 8 || d.latent_dim % 8 != 0)
     return fail(TDMPC2_ERR_INVALID, "simnorm_dim must be 8 and divide latent_dim");
   const int n_hidden = d.num_enc_layers - 1 > 1 ? d.num_enc_layers - 1 : 1;   // layers.py:157
@@ -192,7 +207,13 @@ extern "C" int tdmpc2_planner_create(const tdmpc2_dims* dims, tdmpc2_planner** o
   { int k = d.obs_dim + T; for (int i = 0; i < n_hidden; ++i) { add(k, d.enc_dim, true); k = d.enc_dim; } add(k, L, true); }
   p->li_dyn = static_cast<int>(p->layers.size()); add(D, M, true); add(M, M, true); add(M, L, true);
   p->li_rew = static_cast<int>(p->layers.size()); add(D, M, true); add(M, M, true); add(M, B, false);
-  p->li_pi = static_cast<int>(p->layers.size()); add(L + T, M, true); add(M, M, true); add(M, 2 * A, false);
+  p->li_pi = static_cast<int>(p->layers.size()); add(L + T, M, true); add(M, M, true);
+  {
+    // pi head: rows [0, A) = mean logits, rows [A, 2A) = log_std logits, the latter moved to column pad32(A)
+    const int Apad = pad_to(A, 32);
+    const int i = add(M, Apad + A, false);
+    if (i >= 0) { p->layers[i].src_n = 2 * A; p->layers[i].split_at = A; p->layers[i].split_to = Apad; }
+  }
   p->li_q = static_cast<int>(p->layers.size());
   for (int h = 0; h < d.num_q; ++h) { add(D, M, true); add(M, M, true); add(M, B, false); }
   if (!ok) { delete p; return fail(TDMPC2_ERR_INVALID, "more than %d distinct padded input widths", kMaxWMaps); }
@@ -261,6 +282,11 @@ extern "C" int tdmpc2_planner_workspace_bytes(const tdmpc2_planner* p, size_t* o
 }
 extern "C" int tdmpc2_planner_layer_count(const tdmpc2_planner* p) { return p ? static_cast<int>(p->layers.size()) : -1; }
 extern "C" int64_t tdmpc2_planner_launch_count(const tdmpc2_planner* p) { return p ? p->launches : -1; }
+extern "C" int tdmpc2_planner_set_profile(tdmpc2_planner* p, long long* device_buf) {
+  if (!p) return fail(TDMPC2_ERR_INVALID, "null planner");
+  p->prof = device_buf;
+  return 0;
+}
 extern "C" int tdmpc2_planner_set_engine(tdmpc2_planner* p, int engine) {
   if (!p || (engine != TDMPC2_ENGINE_TCGEN05 && engine != TDMPC2_ENGINE_SIMT)) return fail(TDMPC2_ERR_INVALID, "bad engine");
   p->engine = engine;
@@ -322,7 +348,7 @@ extern "C" int tdmpc2_planner_bind(tdmpc2_planner* p, void* packed, void* worksp
 
   B.layers = reinterpret_cast<const LayerDev*>(p->packed + p->off_table);
   B.E = d.num_envs; B.N = d.num_samples; B.P = d.num_pi_trajs; B.Ppad = p->Ppad; B.K = d.num_elites; B.H = d.horizon;
-  B.obs_dim = d.obs_dim; B.A = d.action_dim; B.L = d.latent_dim; B.M = d.mlp_dim; B.T = d.task_dim; B.B = d.num_bins;
+  B.obs_dim = d.obs_dim; B.A = d.action_dim; B.Apad = pad_to(d.action_dim, 32); B.L = d.latent_dim; B.M = d.mlp_dim; B.T = d.task_dim; B.B = d.num_bins;
   B.num_q = d.num_q; B.simnorm = d.simnorm_dim; B.num_enc = p->num_enc;
   B.tiles_per_env = p->tiles_per_env; B.KpadX = p->KpadX; B.KpadH = p->KpadH; B.NpadMax = p->NpadMax;
   B.li_enc = p->li_enc; B.li_dyn = p->li_dyn; B.li_rew = p->li_rew; B.li_pi = p->li_pi; B.li_q = p->li_q;
@@ -364,20 +390,21 @@ extern "C" int tdmpc2_pack_weights(tdmpc2_planner* p, const tdmpc2_weights* w, v
     const LayerHost& l = p->layers[li];
     if (!lin.weight || !lin.bias) return fail(TDMPC2_ERR_INVALID, "layer %d: null weight/bias", li);
     if (l.has_ln && (!lin.ln_weight || !lin.ln_bias)) return fail(TDMPC2_ERR_INVALID, "layer %d: missing LayerNorm tensors", li);
-    const float* W = lin.weight + head * static_cast<size_t>(l.N) * l.K;
-    const size_t n = static_cast<size_t>(l.N) * l.K;
+    const float* W = lin.weight + head * static_cast<size_t>(l.src_n) * l.K;
+    const size_t n = static_cast<size_t>(l.src_n) * l.K;
     const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 1024));
     absmax_kernel<<<blocks, 256, 0, st>>>(W, n, absmax + li);
     const size_t tot = static_cast<size_t>(l.Npad) * l.Kpad;
     split_weight_kernel<<<static_cast<int>(std::min<size_t>((tot + 255) / 256, 2048)), 256, 0, st>>>(
         W, l.N, l.K, l.Npad, l.Kpad, reinterpret_cast<__half*>(p->packed + l.off_hi),
-        reinterpret_cast<__half*>(p->packed + l.off_lo), absmax + li, table + li);
+        reinterpret_cast<__half*>(p->packed + l.off_lo), absmax + li, table + li, l.src_n, l.split_at, l.split_to);
     const int vb = (l.Npad + 255) / 256;
-    pad_vector_kernel<<<vb, 256, 0, st>>>(lin.bias + head * l.N, l.N, l.Npad, reinterpret_cast<float*>(p->packed + l.off_bias), 0.f);
-    pad_vector_kernel<<<vb, 256, 0, st>>>(l.has_ln ? lin.ln_weight + head * l.N : nullptr, l.N, l.Npad,
-                                          reinterpret_cast<float*>(p->packed + l.off_g), 1.f);
-    pad_vector_kernel<<<vb, 256, 0, st>>>(l.has_ln ? lin.ln_bias + head * l.N : nullptr, l.N, l.Npad,
-                                          reinterpret_cast<float*>(p->packed + l.off_b), 0.f);
+    pad_vector_kernel<<<vb, 256, 0, st>>>(lin.bias + head * l.src_n, l.N, l.Npad, reinterpret_cast<float*>(p->packed + l.off_bias),
+                                          0.f, l.src_n, l.split_at, l.split_to);
+    pad_vector_kernel<<<vb, 256, 0, st>>>(l.has_ln ? lin.ln_weight + head * l.src_n : nullptr, l.N, l.Npad,
+                                          reinterpret_cast<float*>(p->packed + l.off_g), 1.f, l.src_n, l.split_at, l.split_to);
+    pad_vector_kernel<<<vb, 256, 0, st>>>(l.has_ln ? lin.ln_bias + head * l.src_n : nullptr, l.N, l.Npad,
+                                          reinterpret_cast<float*>(p->packed + l.off_b), 0.f, l.src_n, l.split_at, l.split_to);
     p->launches += 5;
     return 0;
   };
@@ -415,8 +442,10 @@ static int launch_plan(tdmpc2_planner* p, const PlanParams& prm, int ntiles, cud
     p->smem_attr_set[eng] = true;
   }
   const int grid = std::min(ntiles, p->nslots);
-  if (eng == 0) plan_kernel<ENGINE_TC><<<grid, kThreads, kSmemBytes, st>>>(prm);
-  else plan_kernel<ENGINE_SIMT><<<grid, kThreads, kSmemBytes, st>>>(prm);
+  PlanParams prm2 = prm;
+  prm2.prof = p->prof;
+  if (eng == 0) plan_kernel<ENGINE_TC><<<grid, kThreads, kSmemBytes, st>>>(prm2);
+  else plan_kernel<ENGINE_SIMT><<<grid, kThreads, kSmemBytes, st>>>(prm2);
   CUDA_TRY(cudaGetLastError());
   p->launches += 1;
   return 0;

@@ -1,7 +1,7 @@
 // Fused planning kernels for sm_100a (B200).
 //
 // One persistent kernel template, `plan_kernel<ENGINE>`, runs the MLP chains of
-// the TD-MPC2 planner on 128-row tiles.  Three modes share all device code:
+// the TD-MPC2 planner on 128-row tiles.  All modes share the device code:
 //
 //   MODE_ENCODE : rows = environments.      z = encode(obs, task)        (reference world_model.py:103-112)
 //   MODE_PRIOR  : rows = (env, pi-traj).    the P policy-prior rollouts  (reference tdmpc2.py:154-160)
@@ -11,15 +11,21 @@
 //   MODE_VALUE  : MODE_ITER's rollout on caller-given z / actions, no refit (reference tdmpc2.py:122-136)
 //   MODE_LAYER  : one layer, for diagnostics.
 //
-// Every dense layer is `raw = A[128, Kpad] * W[Npad, Kpad]^T` with both operands
+// Every dense layer is `acc = A[128, Kpad] * W[Npad, Kpad]^T` with both operands
 // stored as two fp16 planes (hi, lo; x ~= hi + lo to ~22 bits).  The tcgen05
 // engine accumulates A_lo*W_hi + A_hi*W_lo + A_hi*W_hi in fp32 in TMEM
 // (kind::f16, M=128, N<=256, K=16), operands staged by TMA (128-byte swizzle)
-// through a 2-stage mbarrier pipeline; warp 0 = TMA producer, warp 1 = MMA
-// issuer, warps 4-7 drain TMEM.  The row phase (all warps, one warp per row)
-// then applies bias, LayerNorm, Mish / SimNorm / two-hot-inverse / tanh-Gaussian
-// sampling and writes the next layer's fp16 planes.  Activations live in a
-// per-CTA scratch slot that stays L2-resident.
+// through a 2-stage mbarrier pipeline: warp 0 = TMA producer, warp 1 = MMA
+// issuer, warps 4-11 = epilogue.
+//
+//   * Layers with Npad <= 512 (the whole accumulator fits TMEM) use the FUSED
+//     epilogue: one thread per row reads its accumulator row straight from TMEM
+//     (tcgen05.ld), applies bias + LayerNorm + Mish / SimNorm / two-hot-inverse /
+//     tanh-Gaussian sampling, and writes the next layer's fp16 planes.
+//   * Wider layers (48M / 317M presets) drain N-chunks of 256 columns to an fp32
+//     scratch row buffer and run the same math warp-per-row afterwards.
+//
+// Activations live in a per-CTA scratch slot (global memory, L2-resident).
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -38,18 +44,26 @@ constexpr int kStages = 2;
 constexpr int kAPlane = kTileM * 128;           // 16 KiB: one A plane of a stage
 constexpr int kWPlane = kNch * 128;             // 32 KiB: one W plane of a stage
 constexpr int kStageBytes = 2 * kAPlane + 2 * kWPlane;   // 96 KiB
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;
 constexpr int kWarps = kThreads / 32;
+constexpr int kEpiWarp0 = 4;                    // warps 4..11 are the epilogue warps
+constexpr int kEpiThreads = 256;
 constexpr int kMaxWMaps = 8;
-constexpr int kMaxHeadCols = 256;  // widest head output (2A or num_bins), padded to 128s
+constexpr int kMaxHeadCols = 256;  // widest head output (2A or num_bins)
+constexpr int kFusedMaxN = 512;    // TMEM columns
 constexpr int kSmemCtrl = 2048;    // barriers, tmem ptr, flags (128 B) + G[128] + q1[128]
-constexpr int kSmemRowBuf = kWarps * kMaxHeadCols * 4;  // 8 KiB: one head-output row per warp
+constexpr int kSmemRowBuf = kWarps * kMaxHeadCols * 4;  // one head-output row per warp (wide path)
 constexpr int kSmemRowEnv = kTileM * 4;                 // env index of each tile row
-constexpr int kSmemBytes = kStages * kStageBytes + kSmemCtrl + kSmemRowBuf + kSmemRowEnv + 1024 /*align slack*/;
+constexpr int kSmemVec = 3 * kFusedMaxN * 4;            // bias / ln_g / ln_b of the current layer
+constexpr int kSmemPart = 2 * 2 * kTileM * 4;           // LayerNorm partial sums [2 passes][2 halves][128]
+constexpr int kSmemBytes = kStages * kStageBytes + kSmemCtrl + kSmemRowBuf + kSmemRowEnv + kSmemVec + kSmemPart +
+                           1024 /*align slack*/;
 
 enum Mode { MODE_ENCODE = 0, MODE_PRIOR = 1, MODE_ITER = 2, MODE_VALUE = 3, MODE_LAYER = 4 };
 enum Engine { ENGINE_TC = 0, ENGINE_SIMT = 1 };
 enum Buf { BUF_X = 0, BUF_H1 = 1, BUF_H2 = 2 };
+enum Epi { EPI_LN_MISH = 0, EPI_LN_SIMNORM = 1, EPI_TWOHOT = 2, EPI_PI = 3, EPI_RAW = 4 };
+enum HeadKind { HEAD_REWARD = 0, HEAD_Q1 = 1, HEAD_Q2 = 2 };
 
 struct LayerDev {
   int K, Kpad, N, Npad;
@@ -69,7 +83,8 @@ struct PlanParams {
   CUtensorMap tmH;                 // [slots*4*128, KpadH]
   CUtensorMap tmW[kMaxWMaps];      // weights, one map per Kpad class, box 64 x 128
   const LayerDev* layers;
-  int E, N, P, Ppad, K, H, obs_dim, A, L, M, T, B, num_q, simnorm, num_enc;
+  int E, N, P, Ppad, K, H, obs_dim, A, Apad, L, M, T, B, num_q, simnorm, num_enc;   // Apad = pad32(A): the pi head's
+                                                                                  // log_std logits start at column Apad
   int tiles_per_env, ntiles, KpadX, KpadH, NpadMax;
   int li_enc, li_dyn, li_rew, li_pi, li_q;
   float temperature, min_std, max_std, log_std_min, log_std_dif;
@@ -85,6 +100,24 @@ struct PlanParams {
   long long* elite_idx_out; float* values_out;
   // MODE_LAYER
   int dbg_layer, dbg_mode, dbg_rows; const float* dbg_x; float* dbg_y;
+  long long* prof;   // optional [gridDim.x][16] cycle counters (diagnostics), or nullptr
+};
+
+// What a layer's epilogue has to do besides the activation itself.
+struct EpiArgs {
+  int kind;                 // Epi
+  int dstbuf;               // LN kinds: plane destination buffer (or -1)
+  int dst_col0;
+  float* out_f32;           // LN kinds / RAW: optional fp32 row output
+  int out_pitch;
+  const int* rowmap;        // smem [128]: output row of each tile row (or -1), for out_f32
+  int head;                 // TWOHOT: HeadKind
+  float disc;               // TWOHOT: discount factor applied to this head's value
+  int tile;                 // TWOHOT / PI: tile index (row -> env mapping)
+  const float* eps_base;    // PI: noise tensor, element (e*eps_rows + idx)*A + a
+  int eps_rows;
+  float* act_out;           // PI: optional pi_actions output
+  int t_out;
 };
 
 // ------------------------------------------------------------------------------------ small math
@@ -110,16 +143,24 @@ __device__ __forceinline__ float symexp_f(float x) {   // math.py:50-55
   const float m = expf(fabsf(x)) - 1.f;
   return x > 0.f ? m : (x < 0.f ? -m : 0.f);
 }
-__device__ __forceinline__ void split_store(__half* hi, __half* lo, float x) {
+__device__ __forceinline__ void split_f(float x, __half& h, __half& l) {
   x = fminf(fmaxf(x, -65000.f), 65000.f);
-  const __half h = __float2half_rn(x);
+  h = __float2half_rn(x);
+  l = __float2half_rn(x - __half2float(h));
+}
+__device__ __forceinline__ void split_store(__half* hi, __half* lo, float x) {
+  __half h, l;
+  split_f(x, h, l);
   *hi = h;
-  *lo = __float2half_rn(x - __half2float(h));
+  *lo = l;
 }
 __device__ __forceinline__ float nan_to_num0(float v) {   // torch.nan_to_num(0): nan->0, +-inf -> +-FLT_MAX
   if (isnan(v)) return 0.f;
   if (isinf(v)) return v > 0.f ? 3.4028234663852886e38f : -3.4028234663852886e38f;
   return v;
+}
+__device__ __forceinline__ void epi_bar_sync() {   // named barrier among the 8 epilogue warps
+  asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
 }
 
 // ------------------------------------------------------------------------------------ CTA context
@@ -127,17 +168,23 @@ struct Ctx {
   uint8_t* stage_base;      // kStages * kStageBytes, 1024-aligned
   uint64_t* full;           // [kStages]
   uint64_t* empty;          // [kStages]
-  uint64_t* acc_full;       // [2]
-  uint64_t* acc_empty;      // [2]
+  uint64_t* acc_full;       // [2]  wide path: accumulator slot ready
+  uint64_t* acc_empty;      // [2]  wide path: accumulator slot drained
+  uint64_t* facc;           // [2]  fused path: accumulator chunk ready
   uint32_t* tmem_ptr;
   float* rowbuf;            // [kWarps][kMaxHeadCols]
+  float* vec;               // [3][kFusedMaxN]  bias, ln_g, ln_b (fused path)
+  float* part;              // [2][2][128]      LayerNorm partials (fused path)
   float* G;                 // [128] discounted reward sum
   float* q1;                // [128] first Q head
   int* flags;               // small ints
+  int* rowenv;              // [128]
   uint32_t tmem_base;
   int slot, warp, lane;
   // pipeline counters (each role keeps its own; persist across layers / tiles)
   uint32_t p_it, m_it, a_it, d_it;
+  uint32_t fph[2];          // fused path: phase parity of facc[j] (tracked identically by every thread)
+  long long pf[6];          // per-thread cycle accumulators (diagnostics)
 };
 
 __device__ __forceinline__ __half* plane_ptr(const PlanParams& P, int slot, int buf, int plane) {
@@ -151,274 +198,6 @@ __device__ __forceinline__ int plane_row0(const PlanParams& P, int slot, int buf
 }
 __device__ __forceinline__ float* raw_ptr(const PlanParams& P, int slot) {
   return P.raw + static_cast<size_t>(slot) * kTileM * P.NpadMax;
-}
-
-// ------------------------------------------------------------------------------------ GEMM, tcgen05 engine
-// raw[128, Npad] = (A_hi + A_lo)[128, Kpad] * (W_hi + W_lo)[Npad, Kpad]^T   (scaled by 2^k; row phase unscales)
-__device__ void gemm_tc(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf) {
-  const int nkc = ly.Kpad / kKch;
-  const int nnc = (ly.Npad + kNch - 1) / kNch;
-  if (c.warp == 0) {
-    // ===== TMA producer =====
-    if (c.lane == 0) {
-      const CUtensorMap* tmA = (srcbuf == BUF_X) ? &P.tmX : &P.tmH;
-      const CUtensorMap* tmW = &P.tmW[ly.wmap];
-      const int arow_hi = plane_row0(P, c.slot, srcbuf, 0), arow_lo = plane_row0(P, c.slot, srcbuf, 1);
-      for (int nc = 0; nc < nnc; ++nc) {
-        const int ncols = min(kNch, ly.Npad - nc * kNch);   // 128 or 256
-        for (int kc = 0; kc < nkc; ++kc) {
-          const uint32_t s = c.p_it % kStages, ph = (c.p_it / kStages) & 1;
-          ptx::mbar_wait(&c.empty[s], ph ^ 1);
-          uint8_t* st = c.stage_base + s * kStageBytes;
-          ptx::mbar_expect_tx(&c.full[s], 2 * kAPlane + 2 * ncols * 128);
-          ptx::tma_load_2d(tmA, &c.full[s], st, kc * kKch, arow_hi);
-          ptx::tma_load_2d(tmA, &c.full[s], st + kAPlane, kc * kKch, arow_lo);
-          for (int b = 0; b < ncols / 128; ++b) {
-            const int wr = ly.wrow + nc * kNch + b * 128;
-            ptx::tma_load_2d(tmW, &c.full[s], st + 2 * kAPlane + b * (128 * 128), kc * kKch, wr);
-            ptx::tma_load_2d(tmW, &c.full[s], st + 2 * kAPlane + kWPlane + b * (128 * 128), kc * kKch, wr + ly.Npad);
-          }
-          ++c.p_it;
-        }
-      }
-    }
-  } else if (c.warp == 1) {
-    // ===== MMA issuer =====
-    if (c.lane == 0) {
-      for (int nc = 0; nc < nnc; ++nc) {
-        const int ncols = min(kNch, ly.Npad - nc * kNch);
-        const uint32_t idesc = ptx::make_idesc_f16(kTileM, ncols);
-        const uint32_t slot = c.a_it & 1, aph = (c.a_it >> 1) & 1;
-        ptx::mbar_wait(&c.acc_empty[slot], aph ^ 1);
-        ptx::tc_fence_after();
-        const uint32_t d = c.tmem_base + slot * kNch;
-        for (int kc = 0; kc < nkc; ++kc) {
-          const uint32_t s = c.m_it % kStages, ph = (c.m_it / kStages) & 1;
-          ptx::mbar_wait(&c.full[s], ph);
-          ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(c.stage_base + s * kStageBytes);
-#pragma unroll
-          for (int ks = 0; ks < kKch / 16; ++ks) {
-            const uint64_t a_hi = ptx::make_sw128_kmajor_desc(sa + ks * 32);
-            const uint64_t a_lo = ptx::make_sw128_kmajor_desc(sa + kAPlane + ks * 32);
-            const uint64_t w_hi = ptx::make_sw128_kmajor_desc(sa + 2 * kAPlane + ks * 32);
-            const uint64_t w_lo = ptx::make_sw128_kmajor_desc(sa + 2 * kAPlane + kWPlane + ks * 32);
-            ptx::umma_f16(d, a_lo, w_hi, idesc, (kc | ks) != 0);   // small terms first
-            ptx::umma_f16(d, a_hi, w_lo, idesc, 1);
-            ptx::umma_f16(d, a_hi, w_hi, idesc, 1);
-          }
-          ptx::umma_commit(&c.empty[s]);    // frees the smem stage when these MMAs retire
-          ++c.m_it;
-        }
-        ptx::umma_commit(&c.acc_full[slot]);
-        ++c.a_it;
-      }
-    }
-  } else if (c.warp >= 4) {
-    // ===== TMEM drain: accumulator chunk -> raw scratch (fp32) =====
-    const int q = c.warp & 3;                  // TMEM lane quarter this warp may touch
-    const int row = q * 32 + c.lane;
-    float* rawrow = raw_ptr(P, c.slot) + static_cast<size_t>(row) * P.NpadMax;
-    for (int nc = 0; nc < nnc; ++nc) {
-      const int ncols = min(kNch, ly.Npad - nc * kNch);
-      const uint32_t slot = c.d_it & 1, dph = (c.d_it >> 1) & 1;
-      ptx::mbar_wait(&c.acc_full[slot], dph);
-      ptx::tc_fence_after();
-      for (int c0 = 0; c0 < ncols; c0 += 32) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(c.tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * kNch + c0, v);
-        ptx::tmem_ld_wait();
-        float4* dst = reinterpret_cast<float4*>(rawrow + nc * kNch + c0);
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          __stcg(dst + i, make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                      __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
-      }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&c.acc_empty[slot]);
-      ++c.d_it;
-    }
-  }
-  __syncthreads();
-}
-
-// ------------------------------------------------------------------------------------ GEMM, SIMT engine
-// Same operands, plain fp32 FFMA on CUDA cores (exact products of the split operands).
-__device__ void gemm_simt(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf) {
-  constexpr int BN = 64, BK = 32;
-  float* sA = reinterpret_cast<float*>(c.stage_base);          // [BK][128+4]
-  float* sW = sA + BK * (kTileM + 4);                          // [BK][BN+4]
-  const __half* a_hi = plane_ptr(P, c.slot, srcbuf, 0);
-  const __half* a_lo = plane_ptr(P, c.slot, srcbuf, 1);
-  const int pitch = plane_pitch(P, srcbuf);
-  const int tid = threadIdx.x;
-  const int tr = (tid / 16) * 8, tc = (tid % 16) * 4;          // 8 rows x 4 cols per thread
-  float* rawbase = raw_ptr(P, c.slot);
-  for (int n0 = 0; n0 < ly.Npad; n0 += BN) {
-    float acc[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k0 = 0; k0 < ly.Kpad; k0 += BK) {
-      for (int i = tid; i < kTileM * BK; i += kThreads) {
-        const int r = i / BK, k = i % BK;
-        const size_t o = static_cast<size_t>(r) * pitch + k0 + k;
-        sA[k * (kTileM + 4) + r] = __half2float(__ldcg(a_hi + o)) + __half2float(__ldcg(a_lo + o));
-      }
-      for (int i = tid; i < BN * BK; i += kThreads) {
-        const int n = i / BK, k = i % BK;
-        const size_t o = static_cast<size_t>(n0 + n) * ly.Kpad + k0 + k;
-        sW[k * (BN + 4) + n] = __half2float(ly.w_hi[o]) + __half2float(ly.w_lo[o]);
-      }
-      __syncthreads();
-#pragma unroll 4
-      for (int k = 0; k < BK; ++k) {
-        float a[8], w[4];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = sA[k * (kTileM + 4) + tr + i];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) w[j] = sW[k * (BN + 4) + tc + j];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
-      }
-      __syncthreads();
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        __stcg(rawbase + static_cast<size_t>(tr + i) * P.NpadMax + n0 + tc + j, acc[i][j]);
-  }
-  __syncthreads();
-}
-
-template <int ENGINE>
-__device__ __forceinline__ void gemm(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf) {
-  if (ENGINE == ENGINE_TC) gemm_tc(P, c, ly, srcbuf);
-  else gemm_simt(P, c, ly, srcbuf);
-}
-
-// Make generic-proxy global writes (activation planes) visible to the TMA unit
-// (async proxy) before the next layer's loads, and sync the CTA.
-__device__ __forceinline__ void publish_planes() {
-  __threadfence();
-  ptx::fence_proxy_async_all();
-  __syncthreads();
-}
-
-// ------------------------------------------------------------------------------------ row phases
-enum Act { ACT_MISH = 0, ACT_SIMNORM = 1 };
-
-// LayerNorm (+ Mish | SimNorm) over raw rows; one warp per row, lane-strided columns.
-// Writes fp16 planes into dstbuf columns [dst_col0, dst_col0 + N) and/or fp32 rows to out_f32.
-// REGS: the row (Npad <= 512) is held in 16 registers per lane; otherwise re-read from L2.
-__device__ __forceinline__ float ln_act_one(float y, bool valid, int act) {
-  if (act == ACT_MISH) return mish_f(y);
-  // SimNorm (layers.py:74-88): softmax over groups of 8 consecutive columns = 8 adjacent lanes.
-  float m = valid ? y : -CUDART_INF_F;
-  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
-  const float e = valid ? expf(y - m) : 0.f;
-  float t = e;
-  t += __shfl_xor_sync(0xffffffffu, t, 1);
-  t += __shfl_xor_sync(0xffffffffu, t, 2);
-  t += __shfl_xor_sync(0xffffffffu, t, 4);
-  return valid ? __fdiv_rn(e, t) : 0.f;
-}
-
-template <bool REGS>
-__device__ void rows_ln_act_impl(const PlanParams& P, Ctx& c, const LayerDev& ly, int act, int dstbuf, int dst_col0,
-                                 float* out_f32, int out_pitch, const int* out_rowmap) {
-  const float* rawbase = raw_ptr(P, c.slot);
-  const int N = ly.N;
-  const float invN = 1.f / static_cast<float>(N);
-  __half* dhi = dstbuf >= 0 ? plane_ptr(P, c.slot, dstbuf, 0) : nullptr;
-  __half* dlo = dstbuf >= 0 ? plane_ptr(P, c.slot, dstbuf, 1) : nullptr;
-  const int pitch = dstbuf >= 0 ? plane_pitch(P, dstbuf) : 0;
-  const float inv_scale = ly.inv_scale;
-  const int ncolj = (N + 31) / 32;
-  for (int r = c.warp; r < kTileM; r += kWarps) {
-    const float* rr = rawbase + static_cast<size_t>(r) * P.NpadMax;
-    float v[16];
-    float s = 0.f;
-    if (REGS) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int col = c.lane + 32 * j;
-        v[j] = 0.f;
-        if (col < N) { v[j] = fmaf(__ldcg(rr + col), inv_scale, ly.bias[col]); s += v[j]; }
-      }
-    } else {
-      for (int col = c.lane; col < N; col += 32) s += fmaf(__ldcg(rr + col), inv_scale, ly.bias[col]);
-    }
-    const float mean = warp_sum(s) * invN;
-    float sq = 0.f;
-    if (REGS) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int col = c.lane + 32 * j;
-        if (col < N) { const float d = v[j] - mean; sq = fmaf(d, d, sq); }
-      }
-    } else {
-      for (int col = c.lane; col < N; col += 32) {
-        const float d = fmaf(__ldcg(rr + col), inv_scale, ly.bias[col]) - mean;
-        sq = fmaf(d, d, sq);
-      }
-    }
-    const float var = warp_sum(sq) * invN;
-    const float rstd = 1.f / sqrtf(var + 1e-5f);   // nn.LayerNorm eps (layers.py:101)
-    const int orow = out_rowmap ? out_rowmap[r] : r;
-    auto emit = [&](int col, float x) {
-      const bool valid = col < N;
-      float y = valid ? (x - mean) * rstd * ly.ln_g[col] + ly.ln_b[col] : 0.f;
-      y = ln_act_one(y, valid, act);
-      if (valid) {
-        if (dhi) split_store(dhi + static_cast<size_t>(r) * pitch + dst_col0 + col,
-                             dlo + static_cast<size_t>(r) * pitch + dst_col0 + col, y);
-        if (out_f32 && orow >= 0) out_f32[static_cast<size_t>(orow) * out_pitch + col] = y;
-      }
-    };
-    if (REGS) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (j < ncolj) emit(c.lane + 32 * j, v[j]);
-    } else {
-      for (int j = 0; j < ncolj; ++j) {
-        const int col = c.lane + 32 * j;
-        emit(col, col < N ? fmaf(__ldcg(rr + col), inv_scale, ly.bias[col]) : 0.f);
-      }
-    }
-  }
-}
-__device__ __forceinline__ void rows_ln_act(const PlanParams& P, Ctx& c, const LayerDev& ly, int act, int dstbuf,
-                                            int dst_col0, float* out_f32, int out_pitch, const int* out_rowmap) {
-  if (ly.Npad <= 512) rows_ln_act_impl<true>(P, c, ly, act, dstbuf, dst_col0, out_f32, out_pitch, out_rowmap);
-  else rows_ln_act_impl<false>(P, c, ly, act, dstbuf, dst_col0, out_f32, out_pitch, out_rowmap);
-}
-
-// Head output row -> smem row buffer: out[col] = raw*inv_scale + bias (plain Linear, no LN).
-__device__ __forceinline__ void head_row_to_smem(const PlanParams& P, Ctx& c, const LayerDev& ly, int r, float* buf) {
-  const float* rr = raw_ptr(P, c.slot) + static_cast<size_t>(r) * P.NpadMax;
-  for (int col = c.lane; col < ly.N; col += 32) buf[col] = fmaf(__ldcg(rr + col), ly.inv_scale, ly.bias[col]);
-  __syncwarp();
-}
-
-// two_hot_inv (math.py:74-83): softmax over the bins, expectation under linspace(vmin,vmax,B), symexp.
-__device__ __forceinline__ float two_hot_inv_row(const PlanParams& P, Ctx& c, const float* buf) {
-  float m = -CUDART_INF_F;
-  for (int col = c.lane; col < P.B; col += 32) m = fmaxf(m, buf[col]);
-  m = warp_max(m);
-  float s = 0.f;
-  for (int col = c.lane; col < P.B; col += 32) s += expf(buf[col] - m);
-  s = warp_sum(s);
-  float acc = 0.f;
-  for (int col = c.lane; col < P.B; col += 32) acc = fmaf(__fdiv_rn(expf(buf[col] - m), s), P.bins[col], acc);
-  acc = warp_sum(acc);
-  return symexp_f(acc);
 }
 
 // ------------------------------------------------------------------------------------ row -> (env, sample) mapping
@@ -457,6 +236,600 @@ __device__ __forceinline__ float sample_action(const PlanParams& P, int e, int t
   }
   if (P.masks) v *= P.masks[static_cast<size_t>(task) * P.A + a];
   return v;
+}
+
+// ------------------------------------------------------------------------------------ shared per-row commits
+// Value bookkeeping of _estimate_value (tdmpc2.py:128-136) for one row; called by exactly one thread per row.
+__device__ __forceinline__ void head_commit(const PlanParams& P, Ctx& c, const EpiArgs& ea, int r, float val) {
+  if (ea.head == HEAD_REWARD) {
+    c.G[r] = __fadd_rn(c.G[r], __fmul_rn(ea.disc, val));              // G + discount * reward
+  } else if (ea.head == HEAD_Q1) {
+    c.q1[r] = val;
+  } else {
+    const float qavg = __fmul_rn(__fadd_rn(c.q1[r], val), 0.5f);      // Q.sum(0) / 2
+    float v = __fadd_rn(c.G[r], __fmul_rn(ea.disc, qavg));            // G + discount * Q
+    if (P.mode == MODE_ITER) v = nan_to_num0(v);                        // tdmpc2.py:184
+    const RowMap rm = map_row(P, ea.tile, r);
+    if (rm.env >= 0) {
+      float* dst = (P.mode == MODE_ITER) ? P.values : P.values_out;
+      dst[static_cast<size_t>(rm.env) * P.N + rm.idx] = v;
+    }
+  }
+}
+// a = tanh(mean + eps * exp(log_std)) for one (row, action dim)  (world_model.py:151-174)
+__device__ __forceinline__ float pi_action(const PlanParams& P, float mu, float ls, float eps, int task, int a) {
+  // log_std = low + 0.5 * dif * (tanh(x) + 1)   (math.py:12-13)
+  ls = __fadd_rn(P.log_std_min, __fmul_rn(__fmul_rn(0.5f, P.log_std_dif), __fadd_rn(tanhf(ls), 1.f)));
+  if (P.masks) { const float mk = P.masks[static_cast<size_t>(task) * P.A + a]; mu *= mk; ls *= mk; eps *= mk; }
+  return tanhf(__fadd_rn(mu, __fmul_rn(eps, expf(ls))));
+}
+
+// ------------------------------------------------------------------------------------ TMA producer / MMA issuer
+// chunked == true : wide path, accumulator chunks alternate between two 256-column TMEM slots (acc_full/acc_empty).
+// chunked == false: fused path, chunk nc accumulates into TMEM columns [nc*256, ...) and signals facc[nc].
+__device__ __forceinline__ void tc_producer(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf) {
+  const int nkc = ly.Kpad / kKch;
+  const int nnc = (ly.Npad + kNch - 1) / kNch;
+  const CUtensorMap* tmA = (srcbuf == BUF_X) ? &P.tmX : &P.tmH;
+  const CUtensorMap* tmW = &P.tmW[ly.wmap];
+  const int arow_hi = plane_row0(P, c.slot, srcbuf, 0), arow_lo = plane_row0(P, c.slot, srcbuf, 1);
+  for (int nc = 0; nc < nnc; ++nc) {
+    const int ncols = min(kNch, ly.Npad - nc * kNch);   // 128 or 256
+    for (int kc = 0; kc < nkc; ++kc) {
+      const uint32_t s = c.p_it % kStages, ph = (c.p_it / kStages) & 1;
+      const long long tw = clock64();
+      ptx::mbar_wait(&c.empty[s], ph ^ 1);
+      c.pf[0] += clock64() - tw;
+      uint8_t* st = c.stage_base + s * kStageBytes;
+      ptx::mbar_expect_tx(&c.full[s], 2 * kAPlane + 2 * ncols * 128);
+      ptx::tma_load_2d(tmA, &c.full[s], st, kc * kKch, arow_hi);
+      ptx::tma_load_2d(tmA, &c.full[s], st + kAPlane, kc * kKch, arow_lo);
+      for (int b = 0; b < ncols / 128; ++b) {
+        const int wr = ly.wrow + nc * kNch + b * 128;
+        ptx::tma_load_2d(tmW, &c.full[s], st + 2 * kAPlane + b * (128 * 128), kc * kKch, wr);
+        ptx::tma_load_2d(tmW, &c.full[s], st + 2 * kAPlane + kWPlane + b * (128 * 128), kc * kKch, wr + ly.Npad);
+      }
+      ++c.p_it;
+    }
+  }
+}
+
+template <bool CHUNKED>
+__device__ __forceinline__ void tc_mma(Ctx& c, const LayerDev& ly) {
+  const int nkc = ly.Kpad / kKch;
+  const int nnc = (ly.Npad + kNch - 1) / kNch;
+  for (int nc = 0; nc < nnc; ++nc) {
+    const int ncols = min(kNch, ly.Npad - nc * kNch);
+    const uint32_t idesc = ptx::make_idesc_f16(kTileM, ncols);
+    uint32_t d;
+    uint32_t slot = 0;
+    if (CHUNKED) {
+      slot = c.a_it & 1;
+      const uint32_t aph = (c.a_it >> 1) & 1;
+      ptx::mbar_wait(&c.acc_empty[slot], aph ^ 1);
+      ptx::tc_fence_after();
+      d = c.tmem_base + slot * kNch;
+    } else {
+      d = c.tmem_base + nc * kNch;
+    }
+    for (int kc = 0; kc < nkc; ++kc) {
+      const uint32_t s = c.m_it % kStages, ph = (c.m_it / kStages) & 1;
+      const long long tw = clock64();
+      ptx::mbar_wait(&c.full[s], ph);
+      c.pf[0] += clock64() - tw;
+      ptx::tc_fence_after();
+      const uint32_t sa = ptx::smem_u32(c.stage_base + s * kStageBytes);
+#pragma unroll
+      for (int ks = 0; ks < kKch / 16; ++ks) {
+        const uint64_t a_hi = ptx::make_sw128_kmajor_desc(sa + ks * 32);
+        const uint64_t a_lo = ptx::make_sw128_kmajor_desc(sa + kAPlane + ks * 32);
+        const uint64_t w_hi = ptx::make_sw128_kmajor_desc(sa + 2 * kAPlane + ks * 32);
+        const uint64_t w_lo = ptx::make_sw128_kmajor_desc(sa + 2 * kAPlane + kWPlane + ks * 32);
+        ptx::umma_f16(d, a_lo, w_hi, idesc, (kc | ks) != 0);   // small terms first
+        ptx::umma_f16(d, a_hi, w_lo, idesc, 1);
+        ptx::umma_f16(d, a_hi, w_hi, idesc, 1);
+      }
+      ptx::umma_commit(&c.empty[s]);    // frees the smem stage when these MMAs retire
+      ++c.m_it;
+    }
+    if (CHUNKED) {
+      ptx::umma_commit(&c.acc_full[slot]);
+      ++c.a_it;
+    } else {
+      ptx::umma_commit(&c.facc[nc]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ wide path: GEMM -> raw scratch
+__device__ void gemm_tc_wide(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf) {
+  const int nnc = (ly.Npad + kNch - 1) / kNch;
+  if (c.warp == 0) {
+    if (c.lane == 0) tc_producer(P, c, ly, srcbuf);
+  } else if (c.warp == 1) {
+    if (c.lane == 0) tc_mma<true>(c, ly);
+  } else if (c.warp >= kEpiWarp0 && c.warp < kEpiWarp0 + 4) {
+    // TMEM drain: accumulator chunk -> raw scratch (fp32)
+    const int q = c.warp & 3;                  // TMEM lane quarter this warp may touch
+    const int row = q * 32 + c.lane;
+    float* rawrow = raw_ptr(P, c.slot) + static_cast<size_t>(row) * P.NpadMax;
+    for (int nc = 0; nc < nnc; ++nc) {
+      const int ncols = min(kNch, ly.Npad - nc * kNch);
+      const uint32_t slot = c.d_it & 1, dph = (c.d_it >> 1) & 1;
+      ptx::mbar_wait(&c.acc_full[slot], dph);
+      ptx::tc_fence_after();
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(c.tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * kNch + c0, v);
+        ptx::tmem_ld_wait();
+        float4* dst = reinterpret_cast<float4*>(rawrow + nc * kNch + c0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          __stcg(dst + i, make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                      __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&c.acc_empty[slot]);
+      ++c.d_it;
+    }
+  }
+  __syncthreads();
+}
+
+// Same operands, plain fp32 FFMA on CUDA cores (exact products of the split operands).
+__device__ void gemm_simt(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf) {
+  constexpr int BN = 64, BK = 32;
+  float* sA = reinterpret_cast<float*>(c.stage_base);          // [BK][128+4]
+  float* sW = sA + BK * (kTileM + 4);                          // [BK][BN+4]
+  const __half* a_hi = plane_ptr(P, c.slot, srcbuf, 0);
+  const __half* a_lo = plane_ptr(P, c.slot, srcbuf, 1);
+  const int pitch = plane_pitch(P, srcbuf);
+  const int tid = threadIdx.x;
+  const int tr = ((tid & 255) / 16) * 8, tc = (tid % 16) * 4;   // 8 rows x 4 cols per thread (threads 0..255)
+  float* rawbase = raw_ptr(P, c.slot);
+  for (int n0 = 0; n0 < ly.Npad; n0 += BN) {
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < ly.Kpad; k0 += BK) {
+      for (int i = tid; i < kTileM * BK; i += kThreads) {
+        const int r = i / BK, k = i % BK;
+        const size_t o = static_cast<size_t>(r) * pitch + k0 + k;
+        sA[k * (kTileM + 4) + r] = __half2float(__ldcg(a_hi + o)) + __half2float(__ldcg(a_lo + o));
+      }
+      for (int i = tid; i < BN * BK; i += kThreads) {
+        const int n = i / BK, k = i % BK;
+        const size_t o = static_cast<size_t>(n0 + n) * ly.Kpad + k0 + k;
+        sW[k * (BN + 4) + n] = __half2float(ly.w_hi[o]) + __half2float(ly.w_lo[o]);
+      }
+      __syncthreads();
+      if (tid < 256) {
+#pragma unroll 4
+        for (int k = 0; k < BK; ++k) {
+          float a[8], w[4];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[i] = sA[k * (kTileM + 4) + tr + i];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) w[j] = sW[k * (BN + 4) + tc + j];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        }
+      }
+      __syncthreads();
+    }
+    if (tid < 256) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          __stcg(rawbase + static_cast<size_t>(tr + i) * P.NpadMax + n0 + tc + j, acc[i][j]);
+    }
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------ wide path: row phases (warp per row)
+__device__ __forceinline__ float ln_act_lane(float y, bool valid, int act) {
+  if (act == EPI_LN_MISH) return mish_f(y);
+  // SimNorm (layers.py:74-88): softmax over groups of 8 consecutive columns = 8 adjacent lanes.
+  float m = valid ? y : -CUDART_INF_F;
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+  const float e = valid ? expf(y - m) : 0.f;
+  float t = e;
+  t += __shfl_xor_sync(0xffffffffu, t, 1);
+  t += __shfl_xor_sync(0xffffffffu, t, 2);
+  t += __shfl_xor_sync(0xffffffffu, t, 4);
+  return valid ? __fdiv_rn(e, t) : 0.f;
+}
+
+// LayerNorm (+ Mish | SimNorm) over raw rows; one warp per row, lane-strided columns; raw re-read from L2 per pass.
+__device__ void rows_ln_act(const PlanParams& P, Ctx& c, const LayerDev& ly, const EpiArgs& ea) {
+  const float* rawbase = raw_ptr(P, c.slot);
+  const int N = ly.N;
+  const float invN = 1.f / static_cast<float>(N);
+  __half* dhi = ea.dstbuf >= 0 ? plane_ptr(P, c.slot, ea.dstbuf, 0) : nullptr;
+  __half* dlo = ea.dstbuf >= 0 ? plane_ptr(P, c.slot, ea.dstbuf, 1) : nullptr;
+  const int pitch = ea.dstbuf >= 0 ? plane_pitch(P, ea.dstbuf) : 0;
+  const float inv_scale = ly.inv_scale;
+  const float* bias = ly.bias; const float* lg = ly.ln_g; const float* lb = ly.ln_b;
+  const int ncolj = (N + 31) / 32;
+  for (int r = c.warp; r < kTileM; r += kWarps) {
+    const float* rr = rawbase + static_cast<size_t>(r) * P.NpadMax;
+    float s = 0.f;
+    for (int col = c.lane; col < N; col += 32) s += fmaf(__ldcg(rr + col), inv_scale, bias[col]);
+    const float mean = warp_sum(s) * invN;
+    float sq = 0.f;
+    for (int col = c.lane; col < N; col += 32) {
+      const float d = fmaf(__ldcg(rr + col), inv_scale, bias[col]) - mean;
+      sq = fmaf(d, d, sq);
+    }
+    const float var = warp_sum(sq) * invN;
+    const float rstd = 1.f / sqrtf(var + 1e-5f);   // nn.LayerNorm eps (layers.py:101)
+    const int orow = ea.rowmap ? ea.rowmap[r] : r;
+    for (int j = 0; j < ncolj; ++j) {
+      const int col = c.lane + 32 * j;
+      const bool valid = col < N;
+      float y = 0.f;
+      if (valid) y = (fmaf(__ldcg(rr + col), inv_scale, bias[col]) - mean) * rstd * lg[col] + lb[col];
+      y = ln_act_lane(y, valid, ea.kind);
+      if (valid) {
+        if (dhi) split_store(dhi + static_cast<size_t>(r) * pitch + ea.dst_col0 + col,
+                             dlo + static_cast<size_t>(r) * pitch + ea.dst_col0 + col, y);
+        if (ea.out_f32 && orow >= 0) ea.out_f32[static_cast<size_t>(orow) * ea.out_pitch + col] = y;
+      }
+    }
+  }
+}
+
+// Head output row -> smem row buffer: out[col] = raw*inv_scale + bias (plain Linear, no LN).
+__device__ __forceinline__ void head_row_to_smem(const PlanParams& P, Ctx& c, const LayerDev& ly, int r, float* buf) {
+  const float* rr = raw_ptr(P, c.slot) + static_cast<size_t>(r) * P.NpadMax;
+  for (int col = c.lane; col < ly.N; col += 32) buf[col] = fmaf(__ldcg(rr + col), ly.inv_scale, ly.bias[col]);
+  __syncwarp();
+}
+
+// two_hot_inv (math.py:74-83): softmax over the bins, expectation under linspace(vmin,vmax,B), symexp.
+__device__ __forceinline__ float two_hot_inv_row(const PlanParams& P, Ctx& c, const float* buf) {
+  float m = -CUDART_INF_F;
+  for (int col = c.lane; col < P.B; col += 32) m = fmaxf(m, buf[col]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int col = c.lane; col < P.B; col += 32) s += expf(buf[col] - m);
+  s = warp_sum(s);
+  float acc = 0.f;
+  for (int col = c.lane; col < P.B; col += 32) acc = fmaf(__fdiv_rn(expf(buf[col] - m), s), P.bins[col], acc);
+  acc = warp_sum(acc);
+  return symexp_f(acc);
+}
+
+__device__ void rows_head(const PlanParams& P, Ctx& c, const LayerDev& ly, const EpiArgs& ea) {
+  float* myrow = c.rowbuf + c.warp * kMaxHeadCols;
+  __half* xhi = plane_ptr(P, c.slot, BUF_X, 0);
+  __half* xlo = plane_ptr(P, c.slot, BUF_X, 1);
+  for (int r = c.warp; r < kTileM; r += kWarps) {
+    if (ea.kind == EPI_RAW) {
+      const int orow = ea.rowmap ? ea.rowmap[r] : r;
+      const float* rr = raw_ptr(P, c.slot) + static_cast<size_t>(r) * P.NpadMax;
+      if (orow >= 0)
+        for (int col = c.lane; col < ly.N; col += 32)
+          ea.out_f32[static_cast<size_t>(orow) * ea.out_pitch + col] = fmaf(__ldcg(rr + col), ly.inv_scale, ly.bias[col]);
+      continue;
+    }
+    head_row_to_smem(P, c, ly, r, myrow);
+    if (ea.kind == EPI_TWOHOT) {
+      const float v = two_hot_inv_row(P, c, myrow);
+      if (c.lane == 0) head_commit(P, c, ea, r, v);
+    } else if (ea.kind == EPI_PI) {
+      const RowMap rm = map_row(P, ea.tile, r);
+      const int e = rm.env < 0 ? 0 : rm.env, idx = rm.env < 0 ? 0 : rm.idx;
+      const int task = P.task ? P.task[e] : 0;
+      for (int a = c.lane; a < P.A; a += 32) {
+        const float eps = ea.eps_base[(static_cast<size_t>(e) * ea.eps_rows + idx) * P.A + a];
+        const float act = pi_action(P, myrow[a], myrow[P.Apad + a], eps, task, a);
+        const size_t o = static_cast<size_t>(r) * P.KpadX + P.L + P.T + a;
+        split_store(xhi + o, xlo + o, act);
+        if (ea.act_out && rm.env >= 0)
+          ea.act_out[((static_cast<size_t>(e) * P.H + ea.t_out) * P.P + idx) * P.A + a] = act;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------ fused path: TMEM epilogues
+// Thread-per-row: epilogue warp e (0..7) owns TMEM lanes 32*(e&3).. and the column half (e>>2).
+struct EpiThread {
+  int q, half, row;
+  uint32_t taddr;     // TMEM address of this thread's lane, column 0
+};
+__device__ __forceinline__ EpiThread epi_thread(const Ctx& c) {
+  EpiThread t;
+  const int e = c.warp - kEpiWarp0;
+  t.q = e & 3; t.half = e >> 2; t.row = t.q * 32 + c.lane;
+  t.taddr = c.tmem_base + (static_cast<uint32_t>(t.q * 32) << 16);
+  return t;
+}
+__device__ __forceinline__ void epi_stage_vectors(Ctx& c, const LayerDev& ly, bool with_ln) {
+  const int t = threadIdx.x - kEpiWarp0 * 32;
+  for (int i = t; i < ly.Npad; i += kEpiThreads) {
+    c.vec[i] = ly.bias[i];
+    if (with_ln) { c.vec[kFusedMaxN + i] = ly.ln_g[i]; c.vec[2 * kFusedMaxN + i] = ly.ln_b[i]; }
+  }
+  epi_bar_sync();
+}
+
+// Fast-path activation math for the fused epilogue.  __expf = ex2.approx(x*log2e) (rel. error ~2^-22 + |x|*6e-8),
+// __fdividef = rcp.approx * n (~1.5 ulp): Mish stays within ~1e-6 relative of the exact value.
+__device__ __forceinline__ float mish_fast(float x) {
+  const float e = __expf(x);
+  const float n = e * (e + 2.f);
+  const float r = __fdividef(n, n + 2.f);
+  return x > 20.f ? x : x * r;
+}
+
+// bias + LayerNorm + (Mish | SimNorm); planes and/or fp32 rows out.  All 8 epilogue warps.
+// Pass 1 reads the accumulator row once for shifted first/second moments (the two column halves are merged with
+// Chan's parallel-variance formula), pass 2 re-reads it, normalises, activates and emits.
+__device__ void epi_ln_fused(const PlanParams& P, Ctx& c, const LayerDev& ly, const EpiArgs& ea) {
+  const EpiThread et = epi_thread(c);
+  const int N = ly.N;
+  const int nhalf = ly.Npad / 2;                    // multiple of 64
+  const int cb = et.half * nhalf;                   // this thread's columns: [cb, cb + nhalf) & < N
+  const float inv_scale = ly.inv_scale;
+  epi_stage_vectors(c, ly, true);
+  const float* sb = c.vec; const float* sg = c.vec + kFusedMaxN; const float* sbe = c.vec + 2 * kFusedMaxN;
+  {
+    const long long tw = clock64();
+    ptx::mbar_wait(&c.facc[cb / kNch], c.fph[cb / kNch]);
+    c.pf[2] += clock64() - tw;
+  }
+  ptx::tc_fence_after();
+  // ---- pass 1: shifted moments of this half
+  const int nvalid = max(0, min(N - cb, nhalf));
+  float x0 = 0.f, s = 0.f, q = 0.f;
+  for (int c0 = cb; c0 < cb + nvalid; c0 += 32) {
+    uint32_t v[32];
+    ptx::tmem_ld_32x32(et.taddr + c0, v);
+    ptx::tmem_ld_wait();
+    if (c0 == cb) x0 = fmaf(__uint_as_float(v[0]), inv_scale, sb[c0]);
+    const bool full = (c0 + 32 <= N);
+#pragma unroll
+    for (int i4 = 0; i4 < 32; i4 += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + i4);
+      const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float d = fmaf(__uint_as_float(v[i4 + j]), inv_scale, bb[j]) - x0;
+        if (full || c0 + i4 + j < N) { s += d; q = fmaf(d, d, q); }
+      }
+    }
+  }
+  {
+    const float n_h = static_cast<float>(nvalid);
+    const float mean_h = nvalid > 0 ? x0 + s / n_h : 0.f;
+    const float m2_h = nvalid > 0 ? q - s * s / n_h : 0.f;
+    c.part[et.half * kTileM + et.row] = mean_h;
+    c.part[2 * kTileM + et.half * kTileM + et.row] = m2_h;
+  }
+  epi_bar_sync();
+  float mean, rstd;
+  {
+    const float n0 = static_cast<float>(max(0, min(N, nhalf))), n1 = static_cast<float>(N) - n0;
+    const float mean0 = c.part[et.row], mean1 = c.part[kTileM + et.row];
+    const float delta = mean1 - mean0;
+    const float fN = static_cast<float>(N);
+    mean = mean0 + delta * (n1 / fN);
+    const float m2 = c.part[2 * kTileM + et.row] + c.part[3 * kTileM + et.row] + delta * delta * (n0 * n1 / fN);
+    rstd = rsqrtf(m2 / fN + 1e-5f);                 // nn.LayerNorm eps (layers.py:101), biased variance
+  }
+  const float nmr = -mean * rstd;
+  // ---- pass 2: normalise, activate, emit
+  __half* dhi = ea.dstbuf >= 0 ? plane_ptr(P, c.slot, ea.dstbuf, 0) : nullptr;
+  __half* dlo = ea.dstbuf >= 0 ? plane_ptr(P, c.slot, ea.dstbuf, 1) : nullptr;
+  const int pitch = ea.dstbuf >= 0 ? plane_pitch(P, ea.dstbuf) : 0;
+  const int orow = ea.rowmap ? ea.rowmap[et.row] : et.row;
+  for (int c0 = cb; c0 < cb + nvalid; c0 += 32) {
+    uint32_t v[32];
+    ptx::tmem_ld_32x32(et.taddr + c0, v);
+    ptx::tmem_ld_wait();
+    const bool full = (c0 + 32 <= N);
+    float y[32];
+#pragma unroll
+    for (int i4 = 0; i4 < 32; i4 += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + i4);
+      const float4 g4 = *reinterpret_cast<const float4*>(sg + c0 + i4);
+      const float4 e4 = *reinterpret_cast<const float4*>(sbe + c0 + i4);
+      const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w}, ee[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float x = fmaf(__uint_as_float(v[i4 + j]), inv_scale, bb[j]);
+        const float u = fmaf(x, rstd, nmr);
+        const float t = fmaf(u, gg[j], ee[j]);
+        y[i4 + j] = (full || c0 + i4 + j < N) ? t : -CUDART_INF_F;
+      }
+    }
+    if (ea.kind == EPI_LN_MISH) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) y[i] = mish_fast(y[i]);
+    } else {
+      // SimNorm: softmax over groups of 8 consecutive columns (layers.py:84-88)
+#pragma unroll
+      for (int g0 = 0; g0 < 32; g0 += 8) {
+        float m = y[g0];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) m = fmaxf(m, y[g0 + i]);
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { y[g0 + i] = __expf(y[g0 + i] - m); t += y[g0 + i]; }
+        const float rt = __fdividef(1.f, t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[g0 + i] *= rt;
+      }
+    }
+    if (dhi) {
+      __half* ph = dhi + static_cast<size_t>(et.row) * pitch + ea.dst_col0 + c0;
+      __half* pl = dlo + static_cast<size_t>(et.row) * pitch + ea.dst_col0 + c0;
+      if (full && ((ea.dst_col0 & 7) == 0)) {
+        uint32_t hw[16], lw[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float a0 = fminf(fmaxf(y[2 * i], -65000.f), 65000.f), a1 = fminf(fmaxf(y[2 * i + 1], -65000.f), 65000.f);
+          const __half2 h2 = __floats2half2_rn(a0, a1);
+          const float2 hf = __half22float2(h2);
+          const __half2 l2 = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+          hw[i] = *reinterpret_cast<const uint32_t*>(&h2);
+          lw[i] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          __stcg(reinterpret_cast<uint4*>(ph) + i, make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]));
+          __stcg(reinterpret_cast<uint4*>(pl) + i, make_uint4(lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c0 + i < N) split_store(ph + i, pl + i, y[i]);
+      }
+    }
+    if (ea.out_f32 && orow >= 0) {
+      float* po = ea.out_f32 + static_cast<size_t>(orow) * ea.out_pitch + c0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (c0 + i < N) po[i] = y[i];
+    }
+  }
+}
+
+// Head epilogues (plain Linear outputs, Npad <= 256 so chunk 0 only).  Warps 4..7 (half 0) work; half 1 idles.
+__device__ void epi_head_fused(const PlanParams& P, Ctx& c, const LayerDev& ly, const EpiArgs& ea) {
+  const EpiThread et = epi_thread(c);
+  const float inv_scale = ly.inv_scale;
+  epi_stage_vectors(c, ly, false);
+  const float* sb = c.vec;
+  if (ea.kind == EPI_TWOHOT) {
+    // bins -> smem (second vector slot)
+    for (int i = threadIdx.x - kEpiWarp0 * 32; i < P.B; i += kEpiThreads) c.vec[kFusedMaxN + i] = P.bins[i];
+    epi_bar_sync();
+  }
+  if (et.half != 0) return;
+  {
+    const long long tw = clock64();
+    ptx::mbar_wait(&c.facc[0], c.fph[0]);
+    c.pf[2] += clock64() - tw;
+  }
+  ptx::tc_fence_after();
+  if (ea.kind == EPI_TWOHOT) {
+    const float* bins = c.vec + kFusedMaxN;
+    const int B = P.B;
+    float m = -CUDART_INF_F;
+    for (int c0 = 0; c0 < B; c0 += 32) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(et.taddr + c0, v);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (c0 + i < B) m = fmaxf(m, fmaf(__uint_as_float(v[i]), inv_scale, sb[c0 + i]));
+    }
+    float ssum = 0.f, acc = 0.f;
+    for (int c0 = 0; c0 < B; c0 += 32) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(et.taddr + c0, v);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (c0 + i < B) {
+          const float e = __expf(fmaf(__uint_as_float(v[i]), inv_scale, sb[c0 + i]) - m);
+          ssum += e;
+          acc = fmaf(e, bins[c0 + i], acc);
+        }
+    }
+    head_commit(P, c, ea, et.row, symexp_f(__fdiv_rn(acc, ssum)));
+  } else if (ea.kind == EPI_PI) {
+    const RowMap rm = map_row(P, ea.tile, et.row);
+    const int e = rm.env < 0 ? 0 : rm.env, idx = rm.env < 0 ? 0 : rm.idx;
+    const int task = P.task ? P.task[e] : 0;
+    __half* xhi = plane_ptr(P, c.slot, BUF_X, 0) + static_cast<size_t>(et.row) * P.KpadX + P.L + P.T;
+    __half* xlo = plane_ptr(P, c.slot, BUF_X, 1) + static_cast<size_t>(et.row) * P.KpadX + P.L + P.T;
+    const float* eps = ea.eps_base + (static_cast<size_t>(e) * ea.eps_rows + idx) * P.A;
+    for (int a0 = 0; a0 < P.A; a0 += 32) {
+      uint32_t vm[32], vs[32];
+      ptx::tmem_ld_32x32(et.taddr + a0, vm);            // mean logits, columns [a0, a0+32)
+      ptx::tmem_ld_32x32(et.taddr + P.Apad + a0, vs);   // log_std logits, columns [Apad+a0, Apad+a0+32) (32-aligned)
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int a = a0 + i;
+        if (a < P.A) {
+          const float mu = fmaf(__uint_as_float(vm[i]), inv_scale, sb[a]);
+          const float ls = fmaf(__uint_as_float(vs[i]), inv_scale, sb[P.Apad + a]);
+          const float act = pi_action(P, mu, ls, eps[a], task, a);
+          split_store(xhi + a, xlo + a, act);
+          if (ea.act_out && rm.env >= 0)
+            ea.act_out[((static_cast<size_t>(e) * P.H + ea.t_out) * P.P + idx) * P.A + a] = act;
+        }
+      }
+    }
+  } else {  // EPI_RAW
+    const int orow = ea.rowmap ? ea.rowmap[et.row] : et.row;
+    for (int c0 = 0; c0 < ly.N; c0 += 32) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(et.taddr + c0, v);
+      ptx::tmem_ld_wait();
+      if (orow >= 0) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c0 + i < ly.N)
+            ea.out_f32[static_cast<size_t>(orow) * ea.out_pitch + c0 + i] = fmaf(__uint_as_float(v[i]), inv_scale, sb[c0 + i]);
+      }
+    }
+  }
+}
+
+// Make generic-proxy global writes (activation planes) visible to the TMA unit
+// (async proxy) before the next layer's loads, and sync the CTA.
+__device__ __forceinline__ void publish_planes() {
+  __threadfence();
+  ptx::fence_proxy_async_all();
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------ one layer
+// GEMM + epilogue; on return the epilogue's outputs are published (CTA-synchronised, TMA-visible).
+template <int ENGINE>
+__device__ void run_layer(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf, const EpiArgs& ea) {
+  const bool is_ln = (ea.kind == EPI_LN_MISH || ea.kind == EPI_LN_SIMNORM);
+  const bool fused = (ENGINE == ENGINE_TC) && (ly.Npad <= kFusedMaxN) && (is_ln || ly.Npad <= kNch) &&
+                     (ea.kind != EPI_RAW || ly.Npad <= kNch);
+  if (fused) {
+    const long long tl = clock64();
+    if (c.warp == 0) {
+      if (c.lane == 0) tc_producer(P, c, ly, srcbuf);
+    } else if (c.warp == 1) {
+      if (c.lane == 0) tc_mma<false>(c, ly);
+    } else if (c.warp >= kEpiWarp0) {
+      if (is_ln) epi_ln_fused(P, c, ly, ea);
+      else epi_head_fused(P, c, ly, ea);
+      ptx::tc_fence_before();
+    }
+    c.pf[1] += clock64() - tl;
+    const int nnc = (ly.Npad + kNch - 1) / kNch;      // every thread tracks the facc phases
+    for (int j = 0; j < nnc; ++j) c.fph[j] ^= 1;
+  } else {
+    if (ENGINE == ENGINE_TC) gemm_tc_wide(P, c, ly, srcbuf);
+    else gemm_simt(P, c, ly, srcbuf);
+    if (is_ln) rows_ln_act(P, c, ly, ea);
+    else rows_head(P, c, ly, ea);
+  }
+  const long long tp = clock64();
+  publish_planes();
+  c.pf[3] += clock64() - tp;
+  if (fused) ptx::tc_fence_after();
 }
 
 // ------------------------------------------------------------------------------------ top-k + MPPI refit
@@ -556,23 +929,34 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
     c.empty = c.full + kStages;
     c.acc_full = c.empty + kStages;
     c.acc_empty = c.acc_full + 2;
-    c.tmem_ptr = reinterpret_cast<uint32_t*>(c.acc_empty + 2);
+    c.facc = c.acc_empty + 2;
+    c.tmem_ptr = reinterpret_cast<uint32_t*>(c.facc + 2);
     c.flags = reinterpret_cast<int*>(c.tmem_ptr + 1);          // [8]
     c.G = reinterpret_cast<float*>(ctrl + 128);                 // [128]
     c.q1 = c.G + kTileM;                                        // [128]  (ends at ctrl + 1152 <= kSmemCtrl)
     c.rowbuf = reinterpret_cast<float*>(ctrl + kSmemCtrl);
+    c.rowenv = reinterpret_cast<int*>(ctrl + kSmemCtrl + kSmemRowBuf);
+    c.vec = reinterpret_cast<float*>(ctrl + kSmemCtrl + kSmemRowBuf + kSmemRowEnv);
+    c.part = c.vec + 3 * kFusedMaxN;
   }
   c.slot = blockIdx.x;
   c.warp = threadIdx.x >> 5;
   c.lane = threadIdx.x & 31;
   c.p_it = c.m_it = c.a_it = c.d_it = 0;
+  c.fph[0] = c.fph[1] = 0;
+  for (int i = 0; i < 6; ++i) c.pf[i] = 0;
+  const long long t_kernel0 = clock64();
   c.tmem_base = 0;
-  int* rowenv = reinterpret_cast<int*>(c.rowbuf + kWarps * kMaxHeadCols);   // [128] env of each row (or -1)
+  int* rowenv = c.rowenv;
 
   if (ENGINE == ENGINE_TC) {
     if (threadIdx.x == 0) {
       for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&c.full[s], 1); ptx::mbar_init(&c.empty[s], 1); }
-      for (int s = 0; s < 2; ++s) { ptx::mbar_init(&c.acc_full[s], 1); ptx::mbar_init(&c.acc_empty[s], 4 * 32); }
+      for (int s = 0; s < 2; ++s) {
+        ptx::mbar_init(&c.acc_full[s], 1);
+        ptx::mbar_init(&c.acc_empty[s], 4 * 32);
+        ptx::mbar_init(&c.facc[s], 1);
+      }
       ptx::fence_barrier_init();
       ptx::prefetch_tensormap(&P.tmX);
       ptx::prefetch_tensormap(&P.tmH);
@@ -585,7 +969,6 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
   }
 
   const LayerDev* LY = P.layers;
-  float* myrow = c.rowbuf + c.warp * kMaxHeadCols;
 
   for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
     // ---------------- tile set-up: fill the input planes of X ----------------
@@ -593,6 +976,10 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
     __syncthreads();
     __half* xhi = plane_ptr(P, c.slot, BUF_X, 0);
     __half* xlo = plane_ptr(P, c.slot, BUF_X, 1);
+    EpiArgs ea;
+    ea.kind = EPI_LN_MISH; ea.dstbuf = -1; ea.dst_col0 = 0; ea.out_f32 = nullptr; ea.out_pitch = 0; ea.rowmap = nullptr;
+    ea.head = 0; ea.disc = 0.f; ea.tile = tile; ea.eps_base = nullptr; ea.eps_rows = 0; ea.act_out = nullptr; ea.t_out = 0;
+
     if (P.mode == MODE_LAYER) {
       const LayerDev& ly = LY[P.dbg_layer];
       for (int r = c.warp; r < kTileM; r += kWarps)
@@ -600,19 +987,11 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
           const float x = (r < P.dbg_rows && col < ly.K) ? P.dbg_x[static_cast<size_t>(r) * ly.K + col] : 0.f;
           split_store(xhi + static_cast<size_t>(r) * P.KpadX + col, xlo + static_cast<size_t>(r) * P.KpadX + col, x);
         }
+      for (int r = threadIdx.x; r < kTileM; r += kThreads) rowenv[r] = r < P.dbg_rows ? r : -1;
       publish_planes();
-      gemm<ENGINE>(P, c, ly, BUF_X);
-      if (P.dbg_mode == 0) {
-        for (int r = c.warp; r < P.dbg_rows; r += kWarps)
-          for (int col = c.lane; col < ly.N; col += 32)
-            P.dbg_y[static_cast<size_t>(r) * ly.N + col] =
-                fmaf(__ldcg(raw_ptr(P, c.slot) + static_cast<size_t>(r) * P.NpadMax + col), ly.inv_scale, ly.bias[col]);
-      } else {
-        for (int r = threadIdx.x; r < kTileM; r += kThreads) rowenv[r] = r < P.dbg_rows ? r : -1;
-        __syncthreads();
-        rows_ln_act(P, c, ly, P.dbg_mode == 1 ? ACT_MISH : ACT_SIMNORM, -1, 0, P.dbg_y, ly.N, rowenv);
-      }
-      __syncthreads();
+      ea.kind = P.dbg_mode == 0 ? EPI_RAW : (P.dbg_mode == 1 ? EPI_LN_MISH : EPI_LN_SIMNORM);
+      ea.out_f32 = P.dbg_y; ea.out_pitch = ly.N; ea.rowmap = rowenv;
+      run_layer<ENGINE>(P, c, ly, BUF_X, ea);
       continue;
     }
 
@@ -642,27 +1021,25 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
       publish_planes();
       int src = BUF_X;
       for (int l = 0; l < P.num_enc; ++l) {
-        const LayerDev& ly = LY[P.li_enc + l];
-        gemm<ENGINE>(P, c, ly, src);
         const bool last = (l == P.num_enc - 1);
         const int dst = (src == BUF_H1) ? BUF_H2 : BUF_H1;
-        if (last) rows_ln_act(P, c, ly, ACT_SIMNORM, -1, 0, P.z, P.L, rowenv);
-        else rows_ln_act(P, c, ly, ACT_MISH, dst, 0, nullptr, 0, nullptr);
-        publish_planes();
+        EpiArgs a2 = ea;
+        if (last) { a2.kind = EPI_LN_SIMNORM; a2.dstbuf = -1; a2.out_f32 = P.z; a2.out_pitch = P.L; a2.rowmap = rowenv; }
+        else { a2.kind = EPI_LN_MISH; a2.dstbuf = dst; }
+        run_layer<ENGINE>(P, c, LY[P.li_enc + l], src, a2);
         src = dst;
       }
       continue;
     }
 
     // helper lambdas -----------------------------------------------------------
-    auto run_mlp_hidden = [&](int li0) {   // layers 0 and 1: X -> H1 -> H2 (LN + Mish)
-      gemm<ENGINE>(P, c, LY[li0], BUF_X);
-      rows_ln_act(P, c, LY[li0], ACT_MISH, BUF_H1, 0, nullptr, 0, nullptr);
-      publish_planes();
-      gemm<ENGINE>(P, c, LY[li0 + 1], BUF_H1);
-      rows_ln_act(P, c, LY[li0 + 1], ACT_MISH, BUF_H2, 0, nullptr, 0, nullptr);
-      publish_planes();
-      gemm<ENGINE>(P, c, LY[li0 + 2], BUF_H2);
+    auto run_mlp = [&](int li0, const EpiArgs& last) {   // X -> H1 -> H2 (LN + Mish) -> head epilogue
+      EpiArgs h = ea;
+      h.kind = EPI_LN_MISH; h.dstbuf = BUF_H1;
+      run_layer<ENGINE>(P, c, LY[li0], BUF_X, h);
+      h.dstbuf = BUF_H2;
+      run_layer<ENGINE>(P, c, LY[li0 + 1], BUF_H1, h);
+      run_layer<ENGINE>(P, c, LY[li0 + 2], BUF_H2, last);
     };
     auto write_actions = [&](int t) {      // X action columns <- a_t  (tdmpc2.py:176-181)
       for (int r = c.warp; r < kTileM; r += kWarps) {
@@ -677,35 +1054,14 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
       }
     };
     auto dynamics_step = [&]() {           // z <- next(z, a)  (world_model.py:114-121)
-      run_mlp_hidden(P.li_dyn);
-      rows_ln_act(P, c, LY[P.li_dyn + 2], ACT_SIMNORM, BUF_X, 0, nullptr, 0, nullptr);
-      publish_planes();
+      EpiArgs d = ea;
+      d.kind = EPI_LN_SIMNORM; d.dstbuf = BUF_X; d.dst_col0 = 0;
+      run_mlp(P.li_dyn, d);
     };
-    auto pi_step = [&](const float* eps_base, int eps_rows_per_env, float* act_out, int t_out) {
-      // a = tanh(mean + eps * exp(log_std))  (world_model.py:144-174); writes X action columns.
-      run_mlp_hidden(P.li_pi);
-      const LayerDev& ly = LY[P.li_pi + 2];
-      for (int r = c.warp; r < kTileM; r += kWarps) {
-        const RowMap rm = map_row(P, tile, r);
-        const int e = rm.env < 0 ? 0 : rm.env, idx = rm.env < 0 ? 0 : rm.idx;
-        const int task = P.task ? P.task[e] : 0;
-        head_row_to_smem(P, c, ly, r, myrow);
-        for (int a = c.lane; a < P.A; a += 32) {
-          float mu = myrow[a];
-          float ls = myrow[P.A + a];
-          // log_std = low + 0.5 * dif * (tanh(x) + 1)   (math.py:12-13)
-          ls = __fadd_rn(P.log_std_min, __fmul_rn(__fmul_rn(0.5f, P.log_std_dif), __fadd_rn(tanhf(ls), 1.f)));
-          float eps = eps_base[(static_cast<size_t>(e) * eps_rows_per_env + idx) * P.A + a];
-          if (P.masks) { const float mk = P.masks[static_cast<size_t>(task) * P.A + a]; mu *= mk; ls *= mk; eps *= mk; }
-          const float act = tanhf(__fadd_rn(mu, __fmul_rn(eps, expf(ls))));
-          const size_t o = static_cast<size_t>(r) * P.KpadX + P.L + P.T + a;
-          split_store(xhi + o, xlo + o, act);
-          if (act_out && rm.env >= 0)
-            act_out[((static_cast<size_t>(e) * P.H + t_out) * P.P + idx) * P.A + a] = act;
-        }
-        __syncwarp();
-      }
-      publish_planes();
+    auto pi_step = [&](const float* eps_base, int eps_rows, float* act_out, int t_out) {
+      EpiArgs p = ea;
+      p.kind = EPI_PI; p.eps_base = eps_base; p.eps_rows = eps_rows; p.act_out = act_out; p.t_out = t_out;
+      run_mlp(P.li_pi, p);
     };
 
     if (P.mode == MODE_PRIOR) {
@@ -725,46 +1081,17 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
     for (int t = 0; t < P.H; ++t) {
       write_actions(t);
       publish_planes();
-      // reward (world_model.py:123-130) + two_hot_inv
-      run_mlp_hidden(P.li_rew);
-      {
-        const LayerDev& ly = LY[P.li_rew + 2];
-        const float disc = dpow[t];
-        for (int r = c.warp; r < kTileM; r += kWarps) {
-          head_row_to_smem(P, c, ly, r, myrow);
-          const float rew = two_hot_inv_row(P, c, myrow);
-          if (c.lane == 0) c.G[r] = __fadd_rn(c.G[r], __fmul_rn(disc, rew));   // G + discount * reward
-          __syncwarp();
-        }
-      }
-      __syncthreads();
+      EpiArgs rw = ea;                       // reward (world_model.py:123-130) + two_hot_inv
+      rw.kind = EPI_TWOHOT; rw.head = HEAD_REWARD; rw.disc = dpow[t];
+      run_mlp(P.li_rew, rw);
       dynamics_step();
     }
     pi_step(P.noise_pi, P.N, nullptr, 0);
     const int* qi = P.qidx + static_cast<size_t>(env) * 2;
     for (int h = 0; h < 2; ++h) {
-      const int li = P.li_q + 3 * qi[h];
-      run_mlp_hidden(li);
-      const LayerDev& ly = LY[li + 2];
-      for (int r = c.warp; r < kTileM; r += kWarps) {
-        head_row_to_smem(P, c, ly, r, myrow);
-        const float q = two_hot_inv_row(P, c, myrow);
-        if (c.lane == 0) {
-          if (h == 0) c.q1[r] = q;
-          else {
-            const float qavg = __fmul_rn(__fadd_rn(c.q1[r], q), 0.5f);          // Q.sum(0) / 2
-            float v = __fadd_rn(c.G[r], __fmul_rn(dpow[P.H], qavg));
-            if (P.mode == MODE_ITER) v = nan_to_num0(v);                          // tdmpc2.py:184
-            const RowMap rm = map_row(P, tile, r);
-            if (rm.env >= 0) {
-              float* dst = (P.mode == MODE_ITER) ? P.values : P.values_out;
-              dst[static_cast<size_t>(rm.env) * P.N + rm.idx] = v;
-            }
-          }
-        }
-        __syncwarp();
-      }
-      __syncthreads();
+      EpiArgs qa = ea;
+      qa.kind = EPI_TWOHOT; qa.head = (h == 0) ? HEAD_Q1 : HEAD_Q2; qa.disc = dpow[P.H];
+      run_mlp(P.li_q + 3 * qi[h], qa);
     }
     if (P.mode == MODE_ITER) {
       // last CTA to finish a tile of this environment refits its mean/std
@@ -780,10 +1107,21 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
         __threadfence();
         refit_env(P, c, env, task);
       }
-      __syncthreads();
+      publish_planes();     // refit_env wrote the stage smem through the generic proxy; TMA reuses it next tile
     }
   }
 
+  if (P.prof) {
+    // rows: 0 producer (warp 0 lane 0), 1 MMA issuer (warp 1 lane 0), 2 epilogue thread (warp 4 lane 0), 3 idle warp 2
+    // cols: 0 barrier-wait cycles (empty | full), 1 cycles inside fused layers, 2 facc wait, 3 publish, 5 whole kernel
+    const int who = (threadIdx.x == 0) ? 0 : (threadIdx.x == 32) ? 1 : (threadIdx.x == kEpiWarp0 * 32) ? 2
+                    : (threadIdx.x == 64) ? 3 : -1;
+    if (who >= 0) {
+      long long* o = P.prof + (static_cast<size_t>(blockIdx.x) * 4 + who) * 6;
+      c.pf[5] = clock64() - t_kernel0;
+      for (int i = 0; i < 6; ++i) o[i] = c.pf[i];
+    }
+  }
   if (ENGINE == ENGINE_TC) {
     ptx::tc_fence_before();
     __syncthreads();

@@ -57,13 +57,20 @@ def test_fused_layer_matches_fp64(engine, wl):
             continue
         rows = 128 if li % 2 == 0 else 77
         x = torch.randn(rows, W.shape[1], generator=g)
+        A = cfg.action_dim
+        Apad = (A + 31) // 32 * 32
+        n_out = Apad + A if prefix == "_pi.2" else W.shape[0]
         try:
-            y_lin = pl.debug_layer(li, 0, x.cuda(), W.shape[0]).cpu().double()
+            y_lin = pl.debug_layer(li, 0, x.cuda(), n_out).cpu().double()
         except Exception as e:
             if "wider than the X scratch" in str(e):
                 continue
             raise
         ref = x.double() @ W.double().T + b.double()
+        if prefix == "_pi.2":
+            # the packer moves the log_std rows [A, 2A) to the 32-aligned column pad32(A)
+            assert torch.all(y_lin[:, A:Apad] == 0)
+            y_lin = torch.cat([y_lin[:, :A], y_lin[:, Apad:Apad + A]], dim=1)
         err = (y_lin - ref).abs().max().item()
         worst = max(worst, err)
         assert torch.allclose(y_lin, ref, atol=1e-5, rtol=1e-5), f"{prefix} head={head} linear err {err}"
