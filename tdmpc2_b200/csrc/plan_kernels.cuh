@@ -159,6 +159,14 @@ __device__ __forceinline__ float nan_to_num0(float v) {   // torch.nan_to_num(0)
   if (isinf(v)) return v > 0.f ? 3.4028234663852886e38f : -3.4028234663852886e38f;
   return v;
 }
+__device__ __forceinline__ float4 lds128(const float* p) {   // p must point into shared memory, 16-byte aligned
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(ptx::smem_u32(p)));
+  return r;
+}
+__device__ __forceinline__ void half_bar_sync(int half) {   // named barrier among the 4 warps of one column half
+  asm volatile("bar.sync %0, 128;\n" ::"r"(2 + half) : "memory");
+}
 __device__ __forceinline__ void epi_bar_sync() {   // named barrier among the 8 epilogue warps
   asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
 }
@@ -183,8 +191,8 @@ struct Ctx {
   int slot, warp, lane;
   // pipeline counters (each role keeps its own; persist across layers / tiles)
   uint32_t p_it, m_it, a_it, d_it;
-  uint32_t fph[2];          // fused path: phase parity of facc[j] (tracked identically by every thread)
-  long long pf[6];          // per-thread cycle accumulators (diagnostics)
+  uint32_t fph0, fph1;      // fused path: phase parity of facc[0|1] (tracked identically by every thread)
+  long long pf0, pf1, pf2, pf3;   // per-thread cycle accumulators (diagnostics)
 };
 
 __device__ __forceinline__ __half* plane_ptr(const PlanParams& P, int slot, int buf, int plane) {
@@ -279,7 +287,7 @@ __device__ __forceinline__ void tc_producer(const PlanParams& P, Ctx& c, const L
       const uint32_t s = c.p_it % kStages, ph = (c.p_it / kStages) & 1;
       const long long tw = clock64();
       ptx::mbar_wait(&c.empty[s], ph ^ 1);
-      c.pf[0] += clock64() - tw;
+      c.pf0 += clock64() - tw;
       uint8_t* st = c.stage_base + s * kStageBytes;
       ptx::mbar_expect_tx(&c.full[s], 2 * kAPlane + 2 * ncols * 128);
       ptx::tma_load_2d(tmA, &c.full[s], st, kc * kKch, arow_hi);
@@ -316,7 +324,7 @@ __device__ __forceinline__ void tc_mma(Ctx& c, const LayerDev& ly) {
       const uint32_t s = c.m_it % kStages, ph = (c.m_it / kStages) & 1;
       const long long tw = clock64();
       ptx::mbar_wait(&c.full[s], ph);
-      c.pf[0] += clock64() - tw;
+      c.pf0 += clock64() - tw;
       ptx::tc_fence_after();
       const uint32_t sa = ptx::smem_u32(c.stage_base + s * kStageBytes);
 #pragma unroll
@@ -342,7 +350,7 @@ __device__ __forceinline__ void tc_mma(Ctx& c, const LayerDev& ly) {
 }
 
 // ------------------------------------------------------------------------------------ wide path: GEMM -> raw scratch
-__device__ void gemm_tc_wide(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf) {
+__device__ __forceinline__ void gemm_tc_wide(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf) {
   const int nnc = (ly.Npad + kNch - 1) / kNch;
   if (c.warp == 0) {
     if (c.lane == 0) tc_producer(P, c, ly, srcbuf);
@@ -377,7 +385,7 @@ __device__ void gemm_tc_wide(const PlanParams& P, Ctx& c, const LayerDev& ly, in
 }
 
 // Same operands, plain fp32 FFMA on CUDA cores (exact products of the split operands).
-__device__ void gemm_simt(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf) {
+__device__ __forceinline__ void gemm_simt(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf) {
   constexpr int BN = 64, BK = 32;
   float* sA = reinterpret_cast<float*>(c.stage_base);          // [BK][128+4]
   float* sW = sA + BK * (kTileM + 4);                          // [BK][BN+4]
@@ -449,7 +457,7 @@ __device__ __forceinline__ float ln_act_lane(float y, bool valid, int act) {
 }
 
 // LayerNorm (+ Mish | SimNorm) over raw rows; one warp per row, lane-strided columns; raw re-read from L2 per pass.
-__device__ void rows_ln_act(const PlanParams& P, Ctx& c, const LayerDev& ly, const EpiArgs& ea) {
+__device__ __forceinline__ void rows_ln_act(const PlanParams& P, Ctx& c, const LayerDev& ly, const EpiArgs& ea) {
   const float* rawbase = raw_ptr(P, c.slot);
   const int N = ly.N;
   const float invN = 1.f / static_cast<float>(N);
@@ -508,7 +516,7 @@ __device__ __forceinline__ float two_hot_inv_row(const PlanParams& P, Ctx& c, co
   return symexp_f(acc);
 }
 
-__device__ void rows_head(const PlanParams& P, Ctx& c, const LayerDev& ly, const EpiArgs& ea) {
+__device__ __forceinline__ void rows_head(const PlanParams& P, Ctx& c, const LayerDev& ly, const EpiArgs& ea) {
   float* myrow = c.rowbuf + c.warp * kMaxHeadCols;
   __half* xhi = plane_ptr(P, c.slot, BUF_X, 0);
   __half* xlo = plane_ptr(P, c.slot, BUF_X, 1);
@@ -566,17 +574,27 @@ __device__ __forceinline__ void epi_stage_vectors(Ctx& c, const LayerDev& ly, bo
 
 // Fast-path activation math for the fused epilogue.  __expf = ex2.approx(x*log2e) (rel. error ~2^-22 + |x|*6e-8),
 // __fdividef = rcp.approx * n (~1.5 ulp): Mish stays within ~1e-6 relative of the exact value.
+__device__ __forceinline__ float ex2_ftz(float x) {   // single MUFU.EX2
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {   // single MUFU.RCP
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float exp_fast(float x) { return ex2_ftz(x * 1.4426950408889634f); }
 __device__ __forceinline__ float mish_fast(float x) {
-  const float e = __expf(x);
+  const float e = exp_fast(fminf(x, 30.f));        // x > 30: n/(n+2) == 1 in fp32 already; keeps e*e finite
   const float n = e * (e + 2.f);
-  const float r = __fdividef(n, n + 2.f);
-  return x > 20.f ? x : x * r;
+  return x * (n * rcp_ftz(n + 2.f));
 }
 
 // bias + LayerNorm + (Mish | SimNorm); planes and/or fp32 rows out.  All 8 epilogue warps.
 // Pass 1 reads the accumulator row once for shifted first/second moments (the two column halves are merged with
 // Chan's parallel-variance formula), pass 2 re-reads it, normalises, activates and emits.
-__device__ void epi_ln_fused(const PlanParams& P, Ctx& c, const LayerDev& ly, const EpiArgs& ea) {
+__device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const LayerDev& ly, const EpiArgs& ea) {
   const EpiThread et = epi_thread(c);
   const int N = ly.N;
   const int nhalf = ly.Npad / 2;                    // multiple of 64
@@ -586,14 +604,18 @@ __device__ void epi_ln_fused(const PlanParams& P, Ctx& c, const LayerDev& ly, co
   const float* sb = c.vec; const float* sg = c.vec + kFusedMaxN; const float* sbe = c.vec + 2 * kFusedMaxN;
   {
     const long long tw = clock64();
-    ptx::mbar_wait(&c.facc[cb / kNch], c.fph[cb / kNch]);
-    c.pf[2] += clock64() - tw;
+    ptx::mbar_wait(&c.facc[cb / kNch], (cb / kNch) ? c.fph1 : c.fph0);
+    c.pf2 += clock64() - tw;
   }
   ptx::tc_fence_after();
   // ---- pass 1: shifted moments of this half
   const int nvalid = max(0, min(N - cb, nhalf));
   float x0 = 0.f, s = 0.f, q = 0.f;
+#ifdef TDMPC2_EXP_NOPASS1
+  for (int c0 = cb; c0 < cb + 32 && c0 < cb + nvalid; c0 += 32) {
+#else
   for (int c0 = cb; c0 < cb + nvalid; c0 += 32) {
+#endif
     uint32_t v[32];
     ptx::tmem_ld_32x32(et.taddr + c0, v);
     ptx::tmem_ld_wait();
@@ -601,12 +623,20 @@ __device__ void epi_ln_fused(const PlanParams& P, Ctx& c, const LayerDev& ly, co
     const bool full = (c0 + 32 <= N);
 #pragma unroll
     for (int i4 = 0; i4 < 32; i4 += 4) {
-      const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + i4);
+      const float4 b4 = lds128(sb + c0 + i4);
       const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+      if (full) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float d = fmaf(__uint_as_float(v[i4 + j]), inv_scale, bb[j]) - x0;
-        if (full || c0 + i4 + j < N) { s += d; q = fmaf(d, d, q); }
+        for (int j = 0; j < 4; ++j) {
+          const float d = fmaf(__uint_as_float(v[i4 + j]), inv_scale, bb[j]) - x0;
+          s += d; q = fmaf(d, d, q);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float d = fmaf(__uint_as_float(v[i4 + j]), inv_scale, bb[j]) - x0;
+          if (c0 + i4 + j < N) { s += d; q = fmaf(d, d, q); }
+        }
       }
     }
   }
@@ -634,29 +664,55 @@ __device__ void epi_ln_fused(const PlanParams& P, Ctx& c, const LayerDev& ly, co
   __half* dlo = ea.dstbuf >= 0 ? plane_ptr(P, c.slot, ea.dstbuf, 1) : nullptr;
   const int pitch = ea.dstbuf >= 0 ? plane_pitch(P, ea.dstbuf) : 0;
   const int orow = ea.rowmap ? ea.rowmap[et.row] : et.row;
+  // Plane output goes through a 128B-swizzled smem tile [128 rows x 64 cols] per plane and a TMA store
+  // (thread-per-row global stores would touch 32 cache lines per instruction).  The staging tiles alias
+  // the operand pipeline stages, which are idle here: every MMA of this layer has retired.
+  const bool use_tma = (dhi != nullptr) && (N % 64 == 0) && (ea.dst_col0 % 64 == 0);
+  uint8_t* stg = c.stage_base + et.half * (4 * kAPlane);       // per half: 2 buffers x (hi 16 KiB + lo 16 KiB)
+  const bool leader = (et.q == 0) && (c.lane == 0);
+  const CUtensorMap* tmD = (ea.dstbuf == BUF_X) ? &P.tmX : &P.tmH;
+  const uint32_t swz = static_cast<uint32_t>(et.row & 7);
+  int blk = 0;
   for (int c0 = cb; c0 < cb + nvalid; c0 += 32) {
+    const int sub = (c0 - cb) & 32;                               // 0 | 32: which half of the 64-column block
+    uint8_t* buf = stg + (blk & 1) * (2 * kAPlane);
+    if (use_tma && sub == 0 && blk >= 2) {                        // buffer reuse: its previous store must have read it
+      if (leader) ptx::bulk_wait_read<1>();
+      half_bar_sync(et.half);
+    }
     uint32_t v[32];
+#ifdef TDMPC2_EXP_NOPASS2LD
+    if (c0 == cb) { ptx::tmem_ld_32x32(et.taddr + c0, v); ptx::tmem_ld_wait(); }
+    else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(0.01f * static_cast<float>(i + c0));
+    }
+#else
     ptx::tmem_ld_32x32(et.taddr + c0, v);
     ptx::tmem_ld_wait();
+#endif
     const bool full = (c0 + 32 <= N);
     float y[32];
 #pragma unroll
     for (int i4 = 0; i4 < 32; i4 += 4) {
-      const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + i4);
-      const float4 g4 = *reinterpret_cast<const float4*>(sg + c0 + i4);
-      const float4 e4 = *reinterpret_cast<const float4*>(sbe + c0 + i4);
+      const float4 b4 = lds128(sb + c0 + i4);
+      const float4 g4 = lds128(sg + c0 + i4);
+      const float4 e4 = lds128(sbe + c0 + i4);
       const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w}, ee[4] = {e4.x, e4.y, e4.z, e4.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float x = fmaf(__uint_as_float(v[i4 + j]), inv_scale, bb[j]);
         const float u = fmaf(x, rstd, nmr);
         const float t = fmaf(u, gg[j], ee[j]);
-        y[i4 + j] = (full || c0 + i4 + j < N) ? t : -CUDART_INF_F;
+        y[i4 + j] = t;
+        if (!full && c0 + i4 + j >= N) y[i4 + j] = -CUDART_INF_F;
       }
     }
     if (ea.kind == EPI_LN_MISH) {
+#ifndef TDMPC2_EXP_NOMISH
 #pragma unroll
       for (int i = 0; i < 32; ++i) y[i] = mish_fast(y[i]);
+#endif
     } else {
       // SimNorm: softmax over groups of 8 consecutive columns (layers.py:84-88)
 #pragma unroll
@@ -666,32 +722,57 @@ __device__ void epi_ln_fused(const PlanParams& P, Ctx& c, const LayerDev& ly, co
         for (int i = 1; i < 8; ++i) m = fmaxf(m, y[g0 + i]);
         float t = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { y[g0 + i] = __expf(y[g0 + i] - m); t += y[g0 + i]; }
-        const float rt = __fdividef(1.f, t);
+        for (int i = 0; i < 8; ++i) { y[g0 + i] = exp_fast(y[g0 + i] - m); t += y[g0 + i]; }
+        const float rt = rcp_ftz(t);
 #pragma unroll
         for (int i = 0; i < 8; ++i) y[g0 + i] *= rt;
       }
     }
     if (dhi) {
-      __half* ph = dhi + static_cast<size_t>(et.row) * pitch + ea.dst_col0 + c0;
-      __half* pl = dlo + static_cast<size_t>(et.row) * pitch + ea.dst_col0 + c0;
-      if (full && ((ea.dst_col0 & 7) == 0)) {
+      if (use_tma || (full && ((ea.dst_col0 & 7) == 0))) {
         uint32_t hw[16], lw[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float a0 = fminf(fmaxf(y[2 * i], -65000.f), 65000.f), a1 = fminf(fmaxf(y[2 * i + 1], -65000.f), 65000.f);
+          // |y| <= sqrt(N) max|g| + max|b| after LayerNorm (Mish and SimNorm only shrink it): far inside fp16 range
+          const float a0 = y[2 * i], a1 = y[2 * i + 1];
           const __half2 h2 = __floats2half2_rn(a0, a1);
           const float2 hf = __half22float2(h2);
           const __half2 l2 = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
           hw[i] = *reinterpret_cast<const uint32_t*>(&h2);
           lw[i] = *reinterpret_cast<const uint32_t*>(&l2);
         }
+        if (use_tma) {
+          const uint32_t rowaddr = ptx::smem_u32(buf) + static_cast<uint32_t>(et.row) * 128u;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          __stcg(reinterpret_cast<uint4*>(ph) + i, make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]));
-          __stcg(reinterpret_cast<uint4*>(pl) + i, make_uint4(lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]));
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t chunk = static_cast<uint32_t>((sub >> 3) + i);          // 16-byte chunk index in the 128 B row
+            const uint32_t off = ((chunk ^ swz) << 4);
+            ptx::st_shared_v4(rowaddr + off, hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
+            ptx::st_shared_v4(rowaddr + kAPlane + off, lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]);
+          }
+          if (sub == 32) {                                        // 64-column block complete: hand it to the TMA unit
+            ptx::fence_proxy_async_smem();
+            half_bar_sync(et.half);
+            if (leader) {
+              const int col = ea.dst_col0 + c0 - 32;
+              ptx::tma_store_2d(tmD, buf, col, plane_row0(P, c.slot, ea.dstbuf, 0));
+              ptx::tma_store_2d(tmD, buf + kAPlane, col, plane_row0(P, c.slot, ea.dstbuf, 1));
+              ptx::bulk_commit();
+            }
+            ++blk;
+          }
+        } else {
+          __half* ph = dhi + static_cast<size_t>(et.row) * pitch + ea.dst_col0 + c0;
+          __half* pl = dlo + static_cast<size_t>(et.row) * pitch + ea.dst_col0 + c0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            __stcg(reinterpret_cast<uint4*>(ph) + i, make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]));
+            __stcg(reinterpret_cast<uint4*>(pl) + i, make_uint4(lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]));
+          }
         }
       } else {
+        __half* ph = dhi + static_cast<size_t>(et.row) * pitch + ea.dst_col0 + c0;
+        __half* pl = dlo + static_cast<size_t>(et.row) * pitch + ea.dst_col0 + c0;
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           if (c0 + i < N) split_store(ph + i, pl + i, y[i]);
@@ -704,10 +785,11 @@ __device__ void epi_ln_fused(const PlanParams& P, Ctx& c, const LayerDev& ly, co
         if (c0 + i < N) po[i] = y[i];
     }
   }
+  if (use_tma && leader) ptx::bulk_wait<0>();                     // stores performed before the layer is published
 }
 
 // Head epilogues (plain Linear outputs, Npad <= 256 so chunk 0 only).  Warps 4..7 (half 0) work; half 1 idles.
-__device__ void epi_head_fused(const PlanParams& P, Ctx& c, const LayerDev& ly, const EpiArgs& ea) {
+__device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, const LayerDev& ly, const EpiArgs& ea) {
   const EpiThread et = epi_thread(c);
   const float inv_scale = ly.inv_scale;
   epi_stage_vectors(c, ly, false);
@@ -720,8 +802,8 @@ __device__ void epi_head_fused(const PlanParams& P, Ctx& c, const LayerDev& ly, 
   if (et.half != 0) return;
   {
     const long long tw = clock64();
-    ptx::mbar_wait(&c.facc[0], c.fph[0]);
-    c.pf[2] += clock64() - tw;
+    ptx::mbar_wait(&c.facc[0], c.fph0);
+    c.pf2 += clock64() - tw;
   }
   ptx::tc_fence_after();
   if (ea.kind == EPI_TWOHOT) {
@@ -802,7 +884,7 @@ __device__ __forceinline__ void publish_planes() {
 // ------------------------------------------------------------------------------------ one layer
 // GEMM + epilogue; on return the epilogue's outputs are published (CTA-synchronised, TMA-visible).
 template <int ENGINE>
-__device__ void run_layer(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf, const EpiArgs& ea) {
+__device__ __forceinline__ void run_layer(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf, const EpiArgs& ea) {
   const bool is_ln = (ea.kind == EPI_LN_MISH || ea.kind == EPI_LN_SIMNORM);
   const bool fused = (ENGINE == ENGINE_TC) && (ly.Npad <= kFusedMaxN) && (is_ln || ly.Npad <= kNch) &&
                      (ea.kind != EPI_RAW || ly.Npad <= kNch);
@@ -817,9 +899,9 @@ __device__ void run_layer(const PlanParams& P, Ctx& c, const LayerDev& ly, int s
       else epi_head_fused(P, c, ly, ea);
       ptx::tc_fence_before();
     }
-    c.pf[1] += clock64() - tl;
-    const int nnc = (ly.Npad + kNch - 1) / kNch;      // every thread tracks the facc phases
-    for (int j = 0; j < nnc; ++j) c.fph[j] ^= 1;
+    c.pf1 += clock64() - tl;
+    c.fph0 ^= 1;                                      // every thread tracks the facc phases
+    if (ly.Npad > kNch) c.fph1 ^= 1;
   } else {
     if (ENGINE == ENGINE_TC) gemm_tc_wide(P, c, ly, srcbuf);
     else gemm_simt(P, c, ly, srcbuf);
@@ -828,13 +910,13 @@ __device__ void run_layer(const PlanParams& P, Ctx& c, const LayerDev& ly, int s
   }
   const long long tp = clock64();
   publish_planes();
-  c.pf[3] += clock64() - tp;
+  c.pf3 += clock64() - tp;
   if (fused) ptx::tc_fence_after();
 }
 
 // ------------------------------------------------------------------------------------ top-k + MPPI refit
 // Runs in the LAST CTA to finish a tile of environment e (tdmpc2.py:184-197).
-__device__ void refit_env(const PlanParams& P, Ctx& c, int e, int task) {
+__device__ __forceinline__ void refit_env(const PlanParams& P, Ctx& c, int e, int task) {
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(c.stage_base);
   int nsort = 1;
   while (nsort < P.N) nsort <<= 1;
@@ -943,8 +1025,8 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
   c.warp = threadIdx.x >> 5;
   c.lane = threadIdx.x & 31;
   c.p_it = c.m_it = c.a_it = c.d_it = 0;
-  c.fph[0] = c.fph[1] = 0;
-  for (int i = 0; i < 6; ++i) c.pf[i] = 0;
+  c.fph0 = c.fph1 = 0;
+  c.pf0 = c.pf1 = c.pf2 = c.pf3 = 0;
   const long long t_kernel0 = clock64();
   c.tmem_base = 0;
   int* rowenv = c.rowenv;
@@ -976,136 +1058,134 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
     __syncthreads();
     __half* xhi = plane_ptr(P, c.slot, BUF_X, 0);
     __half* xlo = plane_ptr(P, c.slot, BUF_X, 1);
-    EpiArgs ea;
-    ea.kind = EPI_LN_MISH; ea.dstbuf = -1; ea.dst_col0 = 0; ea.out_f32 = nullptr; ea.out_pitch = 0; ea.rowmap = nullptr;
-    ea.head = 0; ea.disc = 0.f; ea.tile = tile; ea.eps_base = nullptr; ea.eps_rows = 0; ea.act_out = nullptr; ea.t_out = 0;
+    const int env_tile = (P.mode == MODE_ITER || P.mode == MODE_VALUE) ? tile / P.tiles_per_env : 0;
+    const int task_tile = (P.task && (P.mode == MODE_ITER || P.mode == MODE_VALUE)) ? P.task[env_tile] : 0;
 
     if (P.mode == MODE_LAYER) {
       const LayerDev& ly = LY[P.dbg_layer];
-      for (int r = c.warp; r < kTileM; r += kWarps)
-        for (int col = c.lane; col < ly.Kpad; col += 32) {
-          const float x = (r < P.dbg_rows && col < ly.K) ? P.dbg_x[static_cast<size_t>(r) * ly.K + col] : 0.f;
-          split_store(xhi + static_cast<size_t>(r) * P.KpadX + col, xlo + static_cast<size_t>(r) * P.KpadX + col, x);
-        }
+      for (int i = threadIdx.x; i < kTileM * ly.Kpad; i += kThreads) {
+        const int r = i / ly.Kpad, col = i % ly.Kpad;
+        const float x = (r < P.dbg_rows && col < ly.K) ? P.dbg_x[static_cast<size_t>(r) * ly.K + col] : 0.f;
+        split_store(xhi + static_cast<size_t>(r) * P.KpadX + col, xlo + static_cast<size_t>(r) * P.KpadX + col, x);
+      }
       for (int r = threadIdx.x; r < kTileM; r += kThreads) rowenv[r] = r < P.dbg_rows ? r : -1;
-      publish_planes();
-      ea.kind = P.dbg_mode == 0 ? EPI_RAW : (P.dbg_mode == 1 ? EPI_LN_MISH : EPI_LN_SIMNORM);
-      ea.out_f32 = P.dbg_y; ea.out_pitch = ly.N; ea.rowmap = rowenv;
-      run_layer<ENGINE>(P, c, ly, BUF_X, ea);
-      continue;
-    }
-
-    for (int r = c.warp; r < kTileM; r += kWarps) {
-      const RowMap rm = map_row(P, tile, r);
-      const int e = rm.env < 0 ? 0 : rm.env;          // padding rows compute on env 0's data, results dropped
-      const int task = P.task ? P.task[e] : 0;
-      __half* rhi = xhi + static_cast<size_t>(r) * P.KpadX;
-      __half* rlo = xlo + static_cast<size_t>(r) * P.KpadX;
-      if (P.mode == MODE_ENCODE) {
-        // [obs | task_emb]  (world_model.py:108-109)
-        for (int col = c.lane; col < P.obs_dim; col += 32)
-          split_store(rhi + col, rlo + col, P.obs[static_cast<size_t>(e) * P.obs_dim + col]);
-        for (int col = c.lane; col < P.T; col += 32)
-          split_store(rhi + P.obs_dim + col, rlo + P.obs_dim + col, P.emb[static_cast<size_t>(task) * P.T + col]);
-      } else {
-        // [z | task_emb | a]  (world_model.py:119-120)
-        const float* zsrc = P.z_rows ? P.z_rows + (static_cast<size_t>(e) * P.N + (rm.env < 0 ? 0 : rm.idx)) * P.L
-                                     : P.z + static_cast<size_t>(e) * P.L;
-        for (int col = c.lane; col < P.L; col += 32) split_store(rhi + col, rlo + col, zsrc[col]);
-        for (int col = c.lane; col < P.T; col += 32)
-          split_store(rhi + P.L + col, rlo + P.L + col, P.emb[static_cast<size_t>(task) * P.T + col]);
-      }
-    }
-
-    if (P.mode == MODE_ENCODE) {
-      publish_planes();
-      int src = BUF_X;
-      for (int l = 0; l < P.num_enc; ++l) {
-        const bool last = (l == P.num_enc - 1);
-        const int dst = (src == BUF_H1) ? BUF_H2 : BUF_H1;
-        EpiArgs a2 = ea;
-        if (last) { a2.kind = EPI_LN_SIMNORM; a2.dstbuf = -1; a2.out_f32 = P.z; a2.out_pitch = P.L; a2.rowmap = rowenv; }
-        else { a2.kind = EPI_LN_MISH; a2.dstbuf = dst; }
-        run_layer<ENGINE>(P, c, LY[P.li_enc + l], src, a2);
-        src = dst;
-      }
-      continue;
-    }
-
-    // helper lambdas -----------------------------------------------------------
-    auto run_mlp = [&](int li0, const EpiArgs& last) {   // X -> H1 -> H2 (LN + Mish) -> head epilogue
-      EpiArgs h = ea;
-      h.kind = EPI_LN_MISH; h.dstbuf = BUF_H1;
-      run_layer<ENGINE>(P, c, LY[li0], BUF_X, h);
-      h.dstbuf = BUF_H2;
-      run_layer<ENGINE>(P, c, LY[li0 + 1], BUF_H1, h);
-      run_layer<ENGINE>(P, c, LY[li0 + 2], BUF_H2, last);
-    };
-    auto write_actions = [&](int t) {      // X action columns <- a_t  (tdmpc2.py:176-181)
-      for (int r = c.warp; r < kTileM; r += kWarps) {
+    } else if (P.mode == MODE_ENCODE) {
+      // [obs | task_emb]  (world_model.py:108-109)
+      const int W = P.obs_dim + P.T;
+      for (int i = threadIdx.x; i < kTileM * W; i += kThreads) {
+        const int r = i / W, col = i % W;
         const RowMap rm = map_row(P, tile, r);
-        const int e = rm.env < 0 ? 0 : rm.env, n = rm.env < 0 ? 0 : rm.idx;
-        const int task = P.task ? P.task[e] : 0;
-        for (int a = c.lane; a < P.A; a += 32) {
-          const float v = sample_action(P, e, t, n, a, task);
-          const size_t o = static_cast<size_t>(r) * P.KpadX + P.L + P.T + a;
-          split_store(xhi + o, xlo + o, v);
+        const int e = rm.env < 0 ? 0 : rm.env;
+        const float x = col < P.obs_dim ? P.obs[static_cast<size_t>(e) * P.obs_dim + col]
+                                        : P.emb[static_cast<size_t>(P.task ? P.task[e] : 0) * P.T + (col - P.obs_dim)];
+        split_store(xhi + static_cast<size_t>(r) * P.KpadX + col, xlo + static_cast<size_t>(r) * P.KpadX + col, x);
+      }
+    } else {
+      // [z | task_emb | a]  (world_model.py:119-120); the action columns are written per step
+      const int W = P.L + P.T;
+      for (int i = threadIdx.x; i < kTileM * W; i += kThreads) {
+        const int r = i / W, col = i % W;
+        const RowMap rm = map_row(P, tile, r);
+        const int e = rm.env < 0 ? 0 : rm.env;
+        float x;
+        if (col < P.L) {
+          x = P.z_rows ? P.z_rows[(static_cast<size_t>(e) * P.N + (rm.env < 0 ? 0 : rm.idx)) * P.L + col]
+                       : P.z[static_cast<size_t>(e) * P.L + col];
+        } else {
+          x = P.emb[static_cast<size_t>(P.task ? P.task[e] : 0) * P.T + (col - P.L)];
+        }
+        split_store(xhi + static_cast<size_t>(r) * P.KpadX + col, xlo + static_cast<size_t>(r) * P.KpadX + col, x);
+      }
+    }
+    publish_planes();
+
+    // ---------------- the tile's layer program: ONE run_layer call site ----------------
+    //   ENCODE : enc.0 .. enc.(n-1)
+    //   PRIOR  : per t: pi.0-2 [, dyn.0-2 if t < H-1]
+    //   ITER   : per t: [a_t -> X] rew.0-2, dyn.0-2 ; then pi.0-2, q_a.0-2, q_b.0-2
+    int nsteps;
+    if (P.mode == MODE_LAYER) nsteps = 1;
+    else if (P.mode == MODE_ENCODE) nsteps = P.num_enc;
+    else if (P.mode == MODE_PRIOR) nsteps = 6 * (P.H - 1) + 3;
+    else nsteps = 6 * P.H + 9;
+    const float* dpow = P.disc_pow + static_cast<size_t>(task_tile) * (P.H + 1);
+    const int* qi = (P.mode == MODE_ITER || P.mode == MODE_VALUE) ? P.qidx + static_cast<size_t>(env_tile) * 2 : nullptr;
+
+    for (int sidx = 0; sidx < nsteps; ++sidx) {
+      EpiArgs ea;
+      ea.kind = EPI_LN_MISH; ea.dstbuf = -1; ea.dst_col0 = 0; ea.out_f32 = nullptr; ea.out_pitch = 0; ea.rowmap = nullptr;
+      ea.head = 0; ea.disc = 0.f; ea.tile = tile; ea.eps_base = nullptr; ea.eps_rows = 0; ea.act_out = nullptr; ea.t_out = 0;
+      int li, src;
+      if (P.mode == MODE_LAYER) {
+        li = P.dbg_layer; src = BUF_X;
+        ea.kind = P.dbg_mode == 0 ? EPI_RAW : (P.dbg_mode == 1 ? EPI_LN_MISH : EPI_LN_SIMNORM);
+        ea.out_f32 = P.dbg_y; ea.out_pitch = LY[li].N; ea.rowmap = rowenv;
+      } else if (P.mode == MODE_ENCODE) {
+        li = P.li_enc + sidx;
+        src = sidx == 0 ? BUF_X : ((sidx & 1) ? BUF_H1 : BUF_H2);
+        if (sidx == P.num_enc - 1) { ea.kind = EPI_LN_SIMNORM; ea.out_f32 = P.z; ea.out_pitch = P.L; ea.rowmap = rowenv; }
+        else { ea.kind = EPI_LN_MISH; ea.dstbuf = (sidx & 1) ? BUF_H2 : BUF_H1; }
+      } else {
+        // which MLP, which of its 3 layers
+        int mlp, l, t = 0;       // mlp: 0 reward, 1 dynamics, 2 pi, 3 q_a, 4 q_b
+        if (P.mode == MODE_PRIOR) {
+          t = sidx / 6; l = sidx % 6;
+          mlp = l < 3 ? 2 : 1; l %= 3;
+        } else if (sidx < 6 * P.H) {
+          t = sidx / 6; l = sidx % 6;
+          mlp = l < 3 ? 0 : 1; l %= 3;
+          if (mlp == 0 && l == 0) {
+            // X action columns <- a_t  (tdmpc2.py:176-181)
+            for (int i = threadIdx.x; i < kTileM * P.A; i += kThreads) {
+              const int r = i / P.A, a = i % P.A;
+              const RowMap rm = map_row(P, tile, r);
+              const float v = sample_action(P, env_tile, t, rm.env < 0 ? 0 : rm.idx, a, task_tile);
+              const size_t o = static_cast<size_t>(r) * P.KpadX + P.L + P.T + a;
+              split_store(xhi + o, xlo + o, v);
+            }
+            publish_planes();
+          }
+        } else {
+          const int u = sidx - 6 * P.H;
+          mlp = 2 + u / 3; l = u % 3;
+        }
+        src = l == 0 ? BUF_X : (l == 1 ? BUF_H1 : BUF_H2);
+        const int base = mlp == 0 ? P.li_rew : mlp == 1 ? P.li_dyn : mlp == 2 ? P.li_pi : P.li_q + 3 * qi[mlp - 3];
+        li = base + l;
+        if (l < 2) {
+          ea.kind = EPI_LN_MISH; ea.dstbuf = l == 0 ? BUF_H1 : BUF_H2;
+        } else if (mlp == 0) {                 // reward (world_model.py:123-130) + two_hot_inv
+          ea.kind = EPI_TWOHOT; ea.head = HEAD_REWARD; ea.disc = dpow[t];
+        } else if (mlp == 1) {                 // z <- next(z, a)  (world_model.py:114-121)
+          ea.kind = EPI_LN_SIMNORM; ea.dstbuf = BUF_X; ea.dst_col0 = 0;
+        } else if (mlp == 2) {                 // a = pi(z)  (world_model.py:144-174) -> X action columns
+          ea.kind = EPI_PI;
+          if (P.mode == MODE_PRIOR) {          // eps = noise_prior[e, t, p, :]
+            ea.eps_base = P.noise_prior + static_cast<size_t>(t) * P.P * P.A; ea.eps_rows = P.H * P.P;
+            ea.act_out = P.pi_actions; ea.t_out = t;
+          } else {                             // eps = noise_pi[e, n, :]
+            ea.eps_base = P.noise_pi; ea.eps_rows = P.N;
+          }
+        } else {                               // Q heads (world_model.py:186-216)
+          ea.kind = EPI_TWOHOT; ea.head = (mlp == 3) ? HEAD_Q1 : HEAD_Q2; ea.disc = dpow[P.H];
         }
       }
-    };
-    auto dynamics_step = [&]() {           // z <- next(z, a)  (world_model.py:114-121)
-      EpiArgs d = ea;
-      d.kind = EPI_LN_SIMNORM; d.dstbuf = BUF_X; d.dst_col0 = 0;
-      run_mlp(P.li_dyn, d);
-    };
-    auto pi_step = [&](const float* eps_base, int eps_rows, float* act_out, int t_out) {
-      EpiArgs p = ea;
-      p.kind = EPI_PI; p.eps_base = eps_base; p.eps_rows = eps_rows; p.act_out = act_out; p.t_out = t_out;
-      run_mlp(P.li_pi, p);
-    };
-
-    if (P.mode == MODE_PRIOR) {
-      publish_planes();
-      for (int t = 0; t < P.H; ++t) {
-        // eps for step t: noise_prior[e, t, p, :]
-        pi_step(P.noise_prior + static_cast<size_t>(t) * P.P * P.A, P.H * P.P, P.pi_actions, t);
-        if (t < P.H - 1) dynamics_step();
-      }
-      continue;
+      run_layer<ENGINE>(P, c, LY[li], src, ea);
     }
 
-    // ---------------- MODE_ITER / MODE_VALUE: _estimate_value (tdmpc2.py:122-136) ----------------
-    const int env = tile / P.tiles_per_env;
-    const int task = P.task ? P.task[env] : 0;
-    const float* dpow = P.disc_pow + static_cast<size_t>(task) * (P.H + 1);
-    for (int t = 0; t < P.H; ++t) {
-      write_actions(t);
-      publish_planes();
-      EpiArgs rw = ea;                       // reward (world_model.py:123-130) + two_hot_inv
-      rw.kind = EPI_TWOHOT; rw.head = HEAD_REWARD; rw.disc = dpow[t];
-      run_mlp(P.li_rew, rw);
-      dynamics_step();
-    }
-    pi_step(P.noise_pi, P.N, nullptr, 0);
-    const int* qi = P.qidx + static_cast<size_t>(env) * 2;
-    for (int h = 0; h < 2; ++h) {
-      EpiArgs qa = ea;
-      qa.kind = EPI_TWOHOT; qa.head = (h == 0) ? HEAD_Q1 : HEAD_Q2; qa.disc = dpow[P.H];
-      run_mlp(P.li_q + 3 * qi[h], qa);
-    }
     if (P.mode == MODE_ITER) {
       // last CTA to finish a tile of this environment refits its mean/std
       __threadfence();
       __syncthreads();
       if (threadIdx.x == 0) {
-        const unsigned old = atomicAdd(&P.env_counter[env], 1u);
+        const unsigned old = atomicAdd(&P.env_counter[env_tile], 1u);
         c.flags[0] = (old == static_cast<unsigned>(P.tiles_per_env - 1));
-        if (c.flags[0]) P.env_counter[env] = 0;
+        if (c.flags[0]) P.env_counter[env_tile] = 0;
       }
       __syncthreads();
       if (c.flags[0]) {
         __threadfence();
-        refit_env(P, c, env, task);
+        refit_env(P, c, env_tile, task_tile);
       }
       publish_planes();     // refit_env wrote the stage smem through the generic proxy; TMA reuses it next tile
     }
@@ -1118,8 +1198,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
                     : (threadIdx.x == 64) ? 3 : -1;
     if (who >= 0) {
       long long* o = P.prof + (static_cast<size_t>(blockIdx.x) * 4 + who) * 6;
-      c.pf[5] = clock64() - t_kernel0;
-      for (int i = 0; i < 6; ++i) o[i] = c.pf[i];
+      o[0] = c.pf0; o[1] = c.pf1; o[2] = c.pf2; o[3] = c.pf3; o[4] = 0; o[5] = clock64() - t_kernel0;
     }
   }
   if (ENGINE == ENGINE_TC) {
