@@ -174,7 +174,7 @@ int tdmpc2_estimate_value(tdmpc2_planner* p, const float* z, const float* action
 int tdmpc2_debug_layer(tdmpc2_planner* p, int layer, int mode, const float* x, int rows,
                        float* y, void* stream);
 int tdmpc2_planner_layer_count(const tdmpc2_planner* p);
-/* Diagnostics: per-CTA cycle counters.  device_buf: int64 [num_SMs][4 roles][6 counters] or NULL to disable.
+/* Diagnostics: per-CTA cycle counters.  device_buf: int64 [num_SMs][4 roles][12 counters] or NULL to disable.
  * roles: TMA producer, MMA issuer, epilogue thread, idle warp; counters: barrier-wait cycles,
  * cycles inside fused layers, accumulator-ready wait, publish (fence + CTA sync), -, whole kernel. */
 int tdmpc2_planner_set_profile(tdmpc2_planner* p, long long* device_buf);

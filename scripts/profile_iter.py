@@ -24,14 +24,14 @@ for i in range(iters):
     print(f"iter {i}: {e0.elapsed_time(e1):.3f} ms (E={E}, tiles={E * ((cfg.num_samples + 127) // 128)})")
 
 if os.environ.get("TDMPC2_PHASE_PROF"):
-    buf = torch.zeros(148 * 4 * 6, dtype=torch.int64, device=dev)
+    buf = torch.zeros(148 * 4 * 12, dtype=torch.int64, device=dev)
     pl.lib.tdmpc2_planner_set_profile(pl.h, buf.data_ptr())
     a = (n.r[:, 0].contiguous(), n.pi[:, 0].contiguous(), n.qidx[:, 0].contiguous())
     pl.iterate(*a); torch.cuda.synchronize()
     pl.lib.tdmpc2_planner_set_profile(pl.h, None)
-    b = buf.view(148, 4, 6).double().cpu()
+    b = buf.view(148, 4, 12).double().cpu()
     names = ["producer", "mma", "epilogue", "idle"]
-    cols = ["bar_wait", "in_layers", "facc_wait", "publish", "-", "kernel"]
+    cols = ["bar_wait", "in_layers", "facc_wait", "publish", "p2_bufwait", "kernel", "p2_ldtm", "p2_math", "p2_store"]
     m = b.mean(0)
     for r in range(4):
-        print(names[r].ljust(10), "  ".join(f"{cols[k]}={m[r, k] / 1e3:9.1f}k" for k in range(6)))
+        print(names[r].ljust(10), "  ".join(f"{cols[k]}={m[r, k] / 1e3:9.1f}k" for k in range(9)))

@@ -192,7 +192,7 @@ struct Ctx {
   // pipeline counters (each role keeps its own; persist across layers / tiles)
   uint32_t p_it, m_it, a_it, d_it;
   uint32_t fph0, fph1;      // fused path: phase parity of facc[0|1] (tracked identically by every thread)
-  long long pf0, pf1, pf2, pf3;   // per-thread cycle accumulators (diagnostics)
+  long long pf0, pf1, pf2, pf3, pf4, pf5, pf6, pf7;   // per-thread cycle accumulators (diagnostics)
 };
 
 __device__ __forceinline__ __half* plane_ptr(const PlanParams& P, int slot, int buf, int plane) {
@@ -676,10 +676,12 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
   for (int c0 = cb; c0 < cb + nvalid; c0 += 32) {
     const int sub = (c0 - cb) & 32;                               // 0 | 32: which half of the 64-column block
     uint8_t* buf = stg + (blk & 1) * (2 * kAPlane);
+    long long tq = clock64();
     if (use_tma && sub == 0 && blk >= 2) {                        // buffer reuse: its previous store must have read it
       if (leader) ptx::bulk_wait_read<1>();
       half_bar_sync(et.half);
     }
+    { const long long tn = clock64(); c.pf4 += tn - tq; tq = tn; }
     uint32_t v[32];
 #ifdef TDMPC2_EXP_NOPASS2LD
     if (c0 == cb) { ptx::tmem_ld_32x32(et.taddr + c0, v); ptx::tmem_ld_wait(); }
@@ -692,6 +694,7 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
     ptx::tmem_ld_wait();
 #endif
     const bool full = (c0 + 32 <= N);
+    { const long long tn = clock64(); c.pf5 += tn - tq; tq = tn; }
     float y[32];
 #pragma unroll
     for (int i4 = 0; i4 < 32; i4 += 4) {
@@ -761,6 +764,7 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
             }
             ++blk;
           }
+          { const long long tn = clock64(); c.pf7 += tn - tq; tq = tn; }
         } else {
           __half* ph = dhi + static_cast<size_t>(et.row) * pitch + ea.dst_col0 + c0;
           __half* pl = dlo + static_cast<size_t>(et.row) * pitch + ea.dst_col0 + c0;
@@ -1026,7 +1030,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
   c.lane = threadIdx.x & 31;
   c.p_it = c.m_it = c.a_it = c.d_it = 0;
   c.fph0 = c.fph1 = 0;
-  c.pf0 = c.pf1 = c.pf2 = c.pf3 = 0;
+  c.pf0 = c.pf1 = c.pf2 = c.pf3 = c.pf4 = c.pf5 = c.pf6 = c.pf7 = 0;
   const long long t_kernel0 = clock64();
   c.tmem_base = 0;
   int* rowenv = c.rowenv;
@@ -1197,8 +1201,9 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
     const int who = (threadIdx.x == 0) ? 0 : (threadIdx.x == 32) ? 1 : (threadIdx.x == kEpiWarp0 * 32) ? 2
                     : (threadIdx.x == 64) ? 3 : -1;
     if (who >= 0) {
-      long long* o = P.prof + (static_cast<size_t>(blockIdx.x) * 4 + who) * 6;
-      o[0] = c.pf0; o[1] = c.pf1; o[2] = c.pf2; o[3] = c.pf3; o[4] = 0; o[5] = clock64() - t_kernel0;
+      long long* o = P.prof + (static_cast<size_t>(blockIdx.x) * 4 + who) * 12;
+      o[0] = c.pf0; o[1] = c.pf1; o[2] = c.pf2; o[3] = c.pf3; o[4] = c.pf4; o[5] = clock64() - t_kernel0;
+      o[6] = c.pf5; o[7] = c.pf6; o[8] = c.pf7;
     }
   }
   if (ENGINE == ENGINE_TC) {

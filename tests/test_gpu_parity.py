@@ -40,7 +40,7 @@ def _layer_list(cfg):
 
 
 @pytest.mark.parametrize("engine", ENGINES)
-@pytest.mark.parametrize("wl", ["tiny", "tiny-mt", "c1"])
+@pytest.mark.parametrize("wl", ["tiny", "tiny-mt", "c1", "tiny-wide"])
 def test_fused_layer_matches_fp64(engine, wl):
     """One packed layer (GEMM on split fp16 operands + bias + LN + Mish/SimNorm) vs float64.
     Tolerance: 1e-5 abs + 1e-5 rel -- fp32 round-off level (3-pass fp16 split carries ~22 bits)."""
@@ -101,6 +101,7 @@ CASES = [  # workload, E, perturb, emb_scale, eval_mode
     ("tiny-mt", 3, True, 60.0, False),
     ("tiny-mt", 3, True, 1.0, True),
     ("c1", 2, False, 1.0, False),
+    ("tiny-wide", 2, True, 1.0, False),     # hidden width 640 > 512 TMEM columns: drained-chunk path
 ]
 
 
