@@ -31,7 +31,8 @@ if os.environ.get("TDMPC2_PHASE_PROF"):
     pl.lib.tdmpc2_planner_set_profile(pl.h, None)
     b = buf.view(148, 4, 12).double().cpu()
     names = ["producer", "mma", "epilogue", "idle"]
-    cols = ["bar_wait", "in_layers", "facc_wait", "publish", "p2_bufwait", "kernel", "p2_ldtm", "p2_math", "p2_store"]
+    cols = ["bar_wait", "in_layers", "facc_wait", "publish", "setup", "kernel", "actions", "refit", "decode"]
     m = b.mean(0)
+    print("refit max over CTAs: %.1fk  kernel max: %.1fk min: %.1fk" % (b[:, 3, 7].max() / 1e3, b[:, 3, 5].max() / 1e3, b[:, 3, 5].min() / 1e3))
     for r in range(4):
         print(names[r].ljust(10), "  ".join(f"{cols[k]}={m[r, k] / 1e3:9.1f}k" for k in range(9)))

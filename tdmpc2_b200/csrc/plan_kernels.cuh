@@ -44,10 +44,11 @@ constexpr int kStages = 2;
 constexpr int kAPlane = kTileM * 128;           // 16 KiB: one A plane of a stage
 constexpr int kWPlane = kNch * 128;             // 32 KiB: one W plane of a stage
 constexpr int kStageBytes = 2 * kAPlane + 2 * kWPlane;   // 96 KiB
-constexpr int kThreads = 384;
+constexpr int kThreads = 640;
 constexpr int kWarps = kThreads / 32;
-constexpr int kEpiWarp0 = 4;                    // warps 4..11 are the epilogue warps
-constexpr int kEpiThreads = 256;
+constexpr int kEpiWarp0 = 4;                    // warps 4..19 are the epilogue warps: 4 column groups x 4 lane quarters
+constexpr int kEpiGroups = 4;
+constexpr int kEpiThreads = kEpiGroups * 128;
 constexpr int kMaxWMaps = 8;
 constexpr int kMaxHeadCols = 256;  // widest head output (2A or num_bins)
 constexpr int kFusedMaxN = 512;    // TMEM columns
@@ -55,7 +56,7 @@ constexpr int kSmemCtrl = 2048;    // barriers, tmem ptr, flags (128 B) + G[128]
 constexpr int kSmemRowBuf = kWarps * kMaxHeadCols * 4;  // one head-output row per warp (wide path)
 constexpr int kSmemRowEnv = kTileM * 4;                 // env index of each tile row
 constexpr int kSmemVec = 3 * kFusedMaxN * 4;            // bias / ln_g / ln_b of the current layer
-constexpr int kSmemPart = 2 * 2 * kTileM * 4;           // LayerNorm partial sums [2 passes][2 halves][128]
+constexpr int kSmemPart = 2 * kEpiGroups * kTileM * 4;  // LayerNorm partials [mean | M2][group][128]
 constexpr int kSmemBytes = kStages * kStageBytes + kSmemCtrl + kSmemRowBuf + kSmemRowEnv + kSmemVec + kSmemPart +
                            1024 /*align slack*/;
 
@@ -164,8 +165,8 @@ __device__ __forceinline__ float4 lds128(const float* p) {   // p must point int
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(ptx::smem_u32(p)));
   return r;
 }
-__device__ __forceinline__ void half_bar_sync(int half) {   // named barrier among the 4 warps of one column half
-  asm volatile("bar.sync %0, 128;\n" ::"r"(2 + half) : "memory");
+__device__ __forceinline__ void group_bar_sync(int grp) {   // named barrier among the 4 warps of one column group
+  asm volatile("bar.sync %0, 128;\n" ::"r"(2 + grp) : "memory");
 }
 __device__ __forceinline__ void epi_bar_sync() {   // named barrier among the 8 epilogue warps
   asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
@@ -551,15 +552,15 @@ __device__ __forceinline__ void rows_head(const PlanParams& P, Ctx& c, const Lay
 }
 
 // ------------------------------------------------------------------------------------ fused path: TMEM epilogues
-// Thread-per-row: epilogue warp e (0..7) owns TMEM lanes 32*(e&3).. and the column half (e>>2).
+// Thread-per-row: epilogue warp e (0..15) owns TMEM lanes 32*(e&3).. and the column group (e>>2).
 struct EpiThread {
-  int q, half, row;
+  int q, grp, row;
   uint32_t taddr;     // TMEM address of this thread's lane, column 0
 };
 __device__ __forceinline__ EpiThread epi_thread(const Ctx& c) {
   EpiThread t;
   const int e = c.warp - kEpiWarp0;
-  t.q = e & 3; t.half = e >> 2; t.row = t.q * 32 + c.lane;
+  t.q = e & 3; t.grp = e >> 2; t.row = t.q * 32 + c.lane;
   t.taddr = c.tmem_base + (static_cast<uint32_t>(t.q * 32) << 16);
   return t;
 }
@@ -591,31 +592,31 @@ __device__ __forceinline__ float mish_fast(float x) {
   return x * (n * rcp_ftz(n + 2.f));
 }
 
-// bias + LayerNorm + (Mish | SimNorm); planes and/or fp32 rows out.  All 8 epilogue warps.
-// Pass 1 reads the accumulator row once for shifted first/second moments (the two column halves are merged with
-// Chan's parallel-variance formula), pass 2 re-reads it, normalises, activates and emits.
+// bias + LayerNorm + (Mish | SimNorm); planes and/or fp32 rows out.  16 epilogue warps: 4 lane quarters x 4
+// column groups; a group owns whole 64-column blocks (the TMA-store granule).
+// Pass 1 reads the accumulator row once for shifted first/second moments (groups merged with Chan's
+// parallel-variance formula), pass 2 re-reads it 16 columns at a time, normalises, activates and emits.
 __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const LayerDev& ly, const EpiArgs& ea) {
   const EpiThread et = epi_thread(c);
   const int N = ly.N;
-  const int nhalf = ly.Npad / 2;                    // multiple of 64
-  const int cb = et.half * nhalf;                   // this thread's columns: [cb, cb + nhalf) & < N
+  const int nblocks = ly.Npad / 64;
+  const int bpg = (nblocks + kEpiGroups - 1) / kEpiGroups;        // 64-column blocks per group
+  const int cb = et.grp * bpg * 64;                               // this thread's columns: [cb, cb + ncols) & < N
+  const int ncols = max(0, min(bpg * 64, ly.Npad - cb));
+  const int nvalid = max(0, min(N - cb, ncols));
   const float inv_scale = ly.inv_scale;
   epi_stage_vectors(c, ly, true);
   const float* sb = c.vec; const float* sg = c.vec + kFusedMaxN; const float* sbe = c.vec + 2 * kFusedMaxN;
-  {
+  if (nvalid > 0) {
     const long long tw = clock64();
-    ptx::mbar_wait(&c.facc[cb / kNch], (cb / kNch) ? c.fph1 : c.fph0);
+    const int j = min(cb / kNch, 1);
+    ptx::mbar_wait(&c.facc[j], j ? c.fph1 : c.fph0);
     c.pf2 += clock64() - tw;
   }
   ptx::tc_fence_after();
-  // ---- pass 1: shifted moments of this half
-  const int nvalid = max(0, min(N - cb, nhalf));
+  // ---- pass 1: shifted moments of this group's columns
   float x0 = 0.f, s = 0.f, q = 0.f;
-#ifdef TDMPC2_EXP_NOPASS1
-  for (int c0 = cb; c0 < cb + 32 && c0 < cb + nvalid; c0 += 32) {
-#else
   for (int c0 = cb; c0 < cb + nvalid; c0 += 32) {
-#endif
     uint32_t v[32];
     ptx::tmem_ld_32x32(et.taddr + c0, v);
     ptx::tmem_ld_wait();
@@ -641,22 +642,27 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
     }
   }
   {
-    const float n_h = static_cast<float>(nvalid);
-    const float mean_h = nvalid > 0 ? x0 + s / n_h : 0.f;
-    const float m2_h = nvalid > 0 ? q - s * s / n_h : 0.f;
-    c.part[et.half * kTileM + et.row] = mean_h;
-    c.part[2 * kTileM + et.half * kTileM + et.row] = m2_h;
+    const float n_g = static_cast<float>(nvalid);
+    c.part[et.grp * kTileM + et.row] = nvalid > 0 ? x0 + s / n_g : 0.f;                       // group mean
+    c.part[(kEpiGroups + et.grp) * kTileM + et.row] = nvalid > 0 ? q - s * s / n_g : 0.f;     // group M2
   }
   epi_bar_sync();
-  float mean, rstd;
+  float mean = 0.f, rstd;
   {
-    const float n0 = static_cast<float>(max(0, min(N, nhalf))), n1 = static_cast<float>(N) - n0;
-    const float mean0 = c.part[et.row], mean1 = c.part[kTileM + et.row];
-    const float delta = mean1 - mean0;
-    const float fN = static_cast<float>(N);
-    mean = mean0 + delta * (n1 / fN);
-    const float m2 = c.part[2 * kTileM + et.row] + c.part[3 * kTileM + et.row] + delta * delta * (n0 * n1 / fN);
-    rstd = rsqrtf(m2 / fN + 1e-5f);                 // nn.LayerNorm eps (layers.py:101), biased variance
+    float m2 = 0.f, cnt = 0.f;
+#pragma unroll
+    for (int g = 0; g < kEpiGroups; ++g) {
+      const int gb = g * bpg * 64;
+      const float ng = static_cast<float>(max(0, min(N - gb, min(bpg * 64, ly.Npad - gb))));
+      if (ng > 0.f) {
+        const float mg = c.part[g * kTileM + et.row], m2g = c.part[(kEpiGroups + g) * kTileM + et.row];
+        const float tot = cnt + ng, delta = mg - mean;
+        mean += delta * (ng / tot);
+        m2 += m2g + delta * delta * (cnt * ng / tot);
+        cnt = tot;
+      }
+    }
+    rstd = rsqrtf(m2 / static_cast<float>(N) + 1e-5f);            // nn.LayerNorm eps (layers.py:101), biased variance
   }
   const float nmr = -mean * rstd;
   // ---- pass 2: normalise, activate, emit
@@ -668,36 +674,24 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
   // (thread-per-row global stores would touch 32 cache lines per instruction).  The staging tiles alias
   // the operand pipeline stages, which are idle here: every MMA of this layer has retired.
   const bool use_tma = (dhi != nullptr) && (N % 64 == 0) && (ea.dst_col0 % 64 == 0);
-  uint8_t* stg = c.stage_base + et.half * (4 * kAPlane);       // per half: 2 buffers x (hi 16 KiB + lo 16 KiB)
+  uint8_t* buf = c.stage_base + et.grp * (2 * kAPlane);           // per group: hi 16 KiB + lo 16 KiB
   const bool leader = (et.q == 0) && (c.lane == 0);
   const CUtensorMap* tmD = (ea.dstbuf == BUF_X) ? &P.tmX : &P.tmH;
   const uint32_t swz = static_cast<uint32_t>(et.row & 7);
-  int blk = 0;
-  for (int c0 = cb; c0 < cb + nvalid; c0 += 32) {
-    const int sub = (c0 - cb) & 32;                               // 0 | 32: which half of the 64-column block
-    uint8_t* buf = stg + (blk & 1) * (2 * kAPlane);
-    long long tq = clock64();
-    if (use_tma && sub == 0 && blk >= 2) {                        // buffer reuse: its previous store must have read it
-      if (leader) ptx::bulk_wait_read<1>();
-      half_bar_sync(et.half);
+  const uint32_t rowaddr = ptx::smem_u32(buf) + static_cast<uint32_t>(et.row) * 128u;
+  for (int c0 = cb; c0 < cb + nvalid; c0 += 16) {
+    const int sub = (c0 - cb) & 63;                               // 0,16,32,48 within the 64-column block
+    if (use_tma && sub == 0 && c0 != cb) {                        // staging reuse: the previous store must have read it
+      if (leader) ptx::bulk_wait_read<0>();
+      group_bar_sync(et.grp);
     }
-    { const long long tn = clock64(); c.pf4 += tn - tq; tq = tn; }
-    uint32_t v[32];
-#ifdef TDMPC2_EXP_NOPASS2LD
-    if (c0 == cb) { ptx::tmem_ld_32x32(et.taddr + c0, v); ptx::tmem_ld_wait(); }
-    else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(0.01f * static_cast<float>(i + c0));
-    }
-#else
-    ptx::tmem_ld_32x32(et.taddr + c0, v);
+    uint32_t v[16];
+    ptx::tmem_ld_32x16(et.taddr + c0, v);
     ptx::tmem_ld_wait();
-#endif
-    const bool full = (c0 + 32 <= N);
-    { const long long tn = clock64(); c.pf5 += tn - tq; tq = tn; }
-    float y[32];
+    const bool full = (c0 + 16 <= N);
+    float y[16];
 #pragma unroll
-    for (int i4 = 0; i4 < 32; i4 += 4) {
+    for (int i4 = 0; i4 < 16; i4 += 4) {
       const float4 b4 = lds128(sb + c0 + i4);
       const float4 g4 = lds128(sg + c0 + i4);
       const float4 e4 = lds128(sbe + c0 + i4);
@@ -706,20 +700,17 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
       for (int j = 0; j < 4; ++j) {
         const float x = fmaf(__uint_as_float(v[i4 + j]), inv_scale, bb[j]);
         const float u = fmaf(x, rstd, nmr);
-        const float t = fmaf(u, gg[j], ee[j]);
-        y[i4 + j] = t;
+        y[i4 + j] = fmaf(u, gg[j], ee[j]);
         if (!full && c0 + i4 + j >= N) y[i4 + j] = -CUDART_INF_F;
       }
     }
     if (ea.kind == EPI_LN_MISH) {
-#ifndef TDMPC2_EXP_NOMISH
 #pragma unroll
-      for (int i = 0; i < 32; ++i) y[i] = mish_fast(y[i]);
-#endif
+      for (int i = 0; i < 16; ++i) y[i] = mish_fast(y[i]);
     } else {
       // SimNorm: softmax over groups of 8 consecutive columns (layers.py:84-88)
 #pragma unroll
-      for (int g0 = 0; g0 < 32; g0 += 8) {
+      for (int g0 = 0; g0 < 16; g0 += 8) {
         float m = y[g0];
 #pragma unroll
         for (int i = 1; i < 8; ++i) m = fmaxf(m, y[g0 + i]);
@@ -733,9 +724,9 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
     }
     if (dhi) {
       if (use_tma || (full && ((ea.dst_col0 & 7) == 0))) {
-        uint32_t hw[16], lw[16];
+        uint32_t hw[8], lw[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 8; ++i) {
           // |y| <= sqrt(N) max|g| + max|b| after LayerNorm (Mish and SimNorm only shrink it): far inside fp16 range
           const float a0 = y[2 * i], a1 = y[2 * i + 1];
           const __half2 h2 = __floats2half2_rn(a0, a1);
@@ -745,31 +736,28 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
           lw[i] = *reinterpret_cast<const uint32_t*>(&l2);
         }
         if (use_tma) {
-          const uint32_t rowaddr = ptx::smem_u32(buf) + static_cast<uint32_t>(et.row) * 128u;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < 2; ++i) {
             const uint32_t chunk = static_cast<uint32_t>((sub >> 3) + i);          // 16-byte chunk index in the 128 B row
             const uint32_t off = ((chunk ^ swz) << 4);
             ptx::st_shared_v4(rowaddr + off, hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
             ptx::st_shared_v4(rowaddr + kAPlane + off, lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]);
           }
-          if (sub == 32) {                                        // 64-column block complete: hand it to the TMA unit
+          if (sub == 48) {                                        // 64-column block complete: hand it to the TMA unit
             ptx::fence_proxy_async_smem();
-            half_bar_sync(et.half);
+            group_bar_sync(et.grp);
             if (leader) {
-              const int col = ea.dst_col0 + c0 - 32;
+              const int col = ea.dst_col0 + c0 - 48;
               ptx::tma_store_2d(tmD, buf, col, plane_row0(P, c.slot, ea.dstbuf, 0));
               ptx::tma_store_2d(tmD, buf + kAPlane, col, plane_row0(P, c.slot, ea.dstbuf, 1));
               ptx::bulk_commit();
             }
-            ++blk;
           }
-          { const long long tn = clock64(); c.pf7 += tn - tq; tq = tn; }
         } else {
           __half* ph = dhi + static_cast<size_t>(et.row) * pitch + ea.dst_col0 + c0;
           __half* pl = dlo + static_cast<size_t>(et.row) * pitch + ea.dst_col0 + c0;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < 2; ++i) {
             __stcg(reinterpret_cast<uint4*>(ph) + i, make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]));
             __stcg(reinterpret_cast<uint4*>(pl) + i, make_uint4(lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]));
           }
@@ -778,21 +766,21 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
         __half* ph = dhi + static_cast<size_t>(et.row) * pitch + ea.dst_col0 + c0;
         __half* pl = dlo + static_cast<size_t>(et.row) * pitch + ea.dst_col0 + c0;
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
+        for (int i = 0; i < 16; ++i)
           if (c0 + i < N) split_store(ph + i, pl + i, y[i]);
       }
     }
     if (ea.out_f32 && orow >= 0) {
       float* po = ea.out_f32 + static_cast<size_t>(orow) * ea.out_pitch + c0;
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
+      for (int i = 0; i < 16; ++i)
         if (c0 + i < N) po[i] = y[i];
     }
   }
   if (use_tma && leader) ptx::bulk_wait<0>();                     // stores performed before the layer is published
 }
 
-// Head epilogues (plain Linear outputs, Npad <= 256 so chunk 0 only).  Warps 4..7 (half 0) work; half 1 idles.
+// Head epilogues (plain Linear outputs, Npad <= 256 so chunk 0 only).  Column group 0 (warps 4..7) works.
 __device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, const LayerDev& ly, const EpiArgs& ea) {
   const EpiThread et = epi_thread(c);
   const float inv_scale = ly.inv_scale;
@@ -803,7 +791,7 @@ __device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, cons
     for (int i = threadIdx.x - kEpiWarp0 * 32; i < P.B; i += kEpiThreads) c.vec[kFusedMaxN + i] = P.bins[i];
     epi_bar_sync();
   }
-  if (et.half != 0) return;
+  if (et.grp != 0) return;
   {
     const long long tw = clock64();
     ptx::mbar_wait(&c.facc[0], c.fph0);
@@ -913,7 +901,11 @@ __device__ __forceinline__ void run_layer(const PlanParams& P, Ctx& c, const Lay
     else rows_head(P, c, ly, ea);
   }
   const long long tp = clock64();
-  publish_planes();
+  // LN layers that went out through TMA stores wrote nothing through the generic proxy: the leaders have
+  // waited for their bulk groups, so a CTA barrier is all the next layer's TMA loads need.
+  const bool tma_only = fused && is_ln && ea.dstbuf >= 0 && (ly.N % 64 == 0) && (ea.dst_col0 % 64 == 0) && !ea.out_f32;
+  if (tma_only) __syncthreads();
+  else publish_planes();
   c.pf3 += clock64() - tp;
   if (fused) ptx::tc_fence_after();
 }
@@ -979,14 +971,26 @@ __device__ __forceinline__ void refit_env(const PlanParams& P, Ctx& c, int e, in
   __syncthreads();
   const float denom = red[1];
   for (int k = threadIdx.x; k < P.K; k += kThreads) P.score[static_cast<size_t>(e) * P.K + k] = escore[k];
-  for (int i = threadIdx.x; i < P.H * P.A; i += kThreads) {
+  // Gather the elites' actions once, all loads independent (the weighted sums below then run out of smem).
+  const int HA = P.H * P.A;
+  float* eact = reinterpret_cast<float*>(c.stage_base + 65536);          // [K][H*A]; keys/score/idx stay below 64 KiB
+  const bool staged = static_cast<size_t>(P.K) * HA * 4 <= static_cast<size_t>(kStages * kStageBytes - 65536) &&
+                      static_cast<size_t>(nsort) * 8 + static_cast<size_t>(P.K) * 8 + 16 <= 65536;
+  if (staged) {
+    for (int i = threadIdx.x; i < P.K * HA; i += kThreads) {
+      const int k = i / HA, ta = i % HA;
+      eact[i] = sample_action(P, e, ta / P.A, eidx[k], ta % P.A, task);
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < HA; i += kThreads) {
     const int t = i / P.A, a = i % P.A;
     float m = 0.f;
-    for (int k = 0; k < P.K; ++k) m = fmaf(escore[k], sample_action(P, e, t, eidx[k], a, task), m);
+    for (int k = 0; k < P.K; ++k) m = fmaf(escore[k], staged ? eact[k * HA + i] : sample_action(P, e, t, eidx[k], a, task), m);
     m = __fdiv_rn(m, denom);
     float var = 0.f;
     for (int k = 0; k < P.K; ++k) {
-      const float act = sample_action(P, e, t, eidx[k], a, task);
+      const float act = staged ? eact[k * HA + i] : sample_action(P, e, t, eidx[k], a, task);
       const float d = act - m;
       var = fmaf(escore[k], d * d, var);
       if (t == 0) P.elite_act0[(static_cast<size_t>(e) * P.K + k) * P.A + a] = act;
@@ -994,7 +998,8 @@ __device__ __forceinline__ void refit_env(const PlanParams& P, Ctx& c, int e, in
     float sd = sqrtf(__fdiv_rn(var, denom));
     sd = fminf(fmaxf(sd, P.min_std), P.max_std);
     if (P.masks) { const float mk = P.masks[static_cast<size_t>(task) * P.A + a]; m *= mk; sd *= mk; }
-    // sample_action() above read the OLD mean/std of this (t, a) only: safe to overwrite now.
+    // every read of the OLD mean/std of this environment happened above (eact gather, or this thread's own
+    // (t, a) in the unstaged path): safe to overwrite now.
     const size_t sa = (static_cast<size_t>(e) * P.H + t) * P.A + a;
     P.mean[sa] = m;
     P.std[sa] = sd;
@@ -1058,6 +1063,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
 
   for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
     // ---------------- tile set-up: fill the input planes of X ----------------
+    const long long t_setup = clock64();
     for (int r = threadIdx.x; r < kTileM; r += kThreads) { rowenv[r] = map_row(P, tile, r).env; c.G[r] = 0.f; c.q1[r] = 0.f; }
     __syncthreads();
     __half* xhi = plane_ptr(P, c.slot, BUF_X, 0);
@@ -1084,6 +1090,35 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
                                         : P.emb[static_cast<size_t>(P.task ? P.task[e] : 0) * P.T + (col - P.obs_dim)];
         split_store(xhi + static_cast<size_t>(r) * P.KpadX + col, xlo + static_cast<size_t>(r) * P.KpadX + col, x);
       }
+    } else if (P.mode == MODE_ITER && !P.z_rows && ((P.L & 7) == 0) && ((P.T & 7) == 0) && (P.L + P.T) / 8 <= kThreads) {
+      // [z | task_emb | .]: every row of an ITER tile carries the SAME latent (z.repeat(N), tdmpc2.py:163):
+      // split 8 columns once, then broadcast them down the rows with 16-byte stores.
+      const int nch = (P.L + P.T) / 8;
+      const int ngrp = kThreads / nch;
+      const int ch = threadIdx.x % nch, rg = threadIdx.x / nch;
+      if (rg < ngrp) {
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float x[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int col = ch * 8 + 2 * j + u;
+            x[u] = col < P.L ? P.z[static_cast<size_t>(env_tile) * P.L + col]
+                             : P.emb[static_cast<size_t>(task_tile) * P.T + (col - P.L)];
+            x[u] = fminf(fmaxf(x[u], -65000.f), 65000.f);
+          }
+          const __half2 h2 = __floats2half2_rn(x[0], x[1]);
+          const float2 hf = __half22float2(h2);
+          const __half2 l2 = __floats2half2_rn(x[0] - hf.x, x[1] - hf.y);
+          hw[j] = *reinterpret_cast<const uint32_t*>(&h2);
+          lw[j] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+        for (int r = rg; r < kTileM; r += ngrp) {
+          __stcg(reinterpret_cast<uint4*>(xhi + static_cast<size_t>(r) * P.KpadX + ch * 8), make_uint4(hw[0], hw[1], hw[2], hw[3]));
+          __stcg(reinterpret_cast<uint4*>(xlo + static_cast<size_t>(r) * P.KpadX + ch * 8), make_uint4(lw[0], lw[1], lw[2], lw[3]));
+        }
+      }
     } else {
       // [z | task_emb | a]  (world_model.py:119-120); the action columns are written per step
       const int W = P.L + P.T;
@@ -1102,6 +1137,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
       }
     }
     publish_planes();
+    c.pf4 += clock64() - t_setup;
 
     // ---------------- the tile's layer program: ONE run_layer call site ----------------
     //   ENCODE : enc.0 .. enc.(n-1)
@@ -1113,7 +1149,9 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
     else if (P.mode == MODE_PRIOR) nsteps = 6 * (P.H - 1) + 3;
     else nsteps = 6 * P.H + 9;
     const float* dpow = P.disc_pow + static_cast<size_t>(task_tile) * (P.H + 1);
-    const int* qi = (P.mode == MODE_ITER || P.mode == MODE_VALUE) ? P.qidx + static_cast<size_t>(env_tile) * 2 : nullptr;
+    int qi[2] = {0, 0};
+    if (P.mode == MODE_ITER || P.mode == MODE_VALUE) { qi[0] = P.qidx[static_cast<size_t>(env_tile) * 2]; qi[1] = P.qidx[static_cast<size_t>(env_tile) * 2 + 1]; }
+    const float disc_H = dpow[P.H];
 
     for (int sidx = 0; sidx < nsteps; ++sidx) {
       EpiArgs ea;
@@ -1140,21 +1178,51 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
           mlp = l < 3 ? 0 : 1; l %= 3;
           if (mlp == 0 && l == 0) {
             // X action columns <- a_t  (tdmpc2.py:176-181)
-            for (int i = threadIdx.x; i < kTileM * P.A; i += kThreads) {
-              const int r = i / P.A, a = i % P.A;
-              const RowMap rm = map_row(P, tile, r);
-              const float v = sample_action(P, env_tile, t, rm.env < 0 ? 0 : rm.idx, a, task_tile);
-              const size_t o = static_cast<size_t>(r) * P.KpadX + P.L + P.T + a;
-              split_store(xhi + o, xlo + o, v);
+            const long long t_act = clock64();
+            if (P.actions_explicit) {
+              for (int i = threadIdx.x; i < kTileM * P.A; i += kThreads) {
+                const int r = i / P.A, a = i % P.A;
+                const RowMap rm = map_row(P, tile, r);
+                const float v = sample_action(P, env_tile, t, rm.env < 0 ? 0 : rm.idx, a, task_tile);
+                const size_t o = static_cast<size_t>(r) * P.KpadX + P.L + P.T + a;
+                split_store(xhi + o, xlo + o, v);
+              }
+            } else {
+              // mean/std/mask of step t staged in smem, then one pass of independent, coalesced noise loads
+              float* sm_mean = c.rowbuf; float* sm_std = c.rowbuf + kMaxHeadCols; float* sm_mask = c.rowbuf + 2 * kMaxHeadCols;
+              for (int a = threadIdx.x; a < P.A; a += kThreads) {
+                const size_t sa = (static_cast<size_t>(env_tile) * P.H + t) * P.A + a;
+                sm_mean[a] = P.mean[sa]; sm_std[a] = P.std[sa];
+                sm_mask[a] = P.masks ? P.masks[static_cast<size_t>(task_tile) * P.A + a] : 1.f;
+              }
+              __syncthreads();
+              const int n0 = (tile % P.tiles_per_env) * kTileM;
+              const float* nz = P.noise_r + (static_cast<size_t>(env_tile) * P.H + t) * (P.N - P.P) * P.A;
+              const float* pa = P.pi_actions + (static_cast<size_t>(env_tile) * P.H + t) * P.P * P.A;
+#pragma unroll 4
+              for (int i = threadIdx.x; i < kTileM * P.A; i += kThreads) {
+                const int r = i / P.A, a = i % P.A;
+                const int n = min(n0 + r, P.N - 1);
+                float v;
+                if (n < P.P) v = pa[static_cast<size_t>(n) * P.A + a];
+                else {
+                  v = __fadd_rn(sm_mean[a], __fmul_rn(sm_std[a], nz[static_cast<size_t>(n - P.P) * P.A + a]));
+                  v = fminf(fmaxf(v, -1.f), 1.f);
+                }
+                v *= sm_mask[a];
+                const size_t o = static_cast<size_t>(r) * P.KpadX + P.L + P.T + a;
+                split_store(xhi + o, xlo + o, v);
+              }
             }
             publish_planes();
+            c.pf5 += clock64() - t_act;
           }
         } else {
           const int u = sidx - 6 * P.H;
           mlp = 2 + u / 3; l = u % 3;
         }
         src = l == 0 ? BUF_X : (l == 1 ? BUF_H1 : BUF_H2);
-        const int base = mlp == 0 ? P.li_rew : mlp == 1 ? P.li_dyn : mlp == 2 ? P.li_pi : P.li_q + 3 * qi[mlp - 3];
+        const int base = mlp == 0 ? P.li_rew : mlp == 1 ? P.li_dyn : mlp == 2 ? P.li_pi : P.li_q + 3 * (mlp == 3 ? qi[0] : qi[1]);
         li = base + l;
         if (l < 2) {
           ea.kind = EPI_LN_MISH; ea.dstbuf = l == 0 ? BUF_H1 : BUF_H2;
@@ -1171,12 +1239,13 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
             ea.eps_base = P.noise_pi; ea.eps_rows = P.N;
           }
         } else {                               // Q heads (world_model.py:186-216)
-          ea.kind = EPI_TWOHOT; ea.head = (mlp == 3) ? HEAD_Q1 : HEAD_Q2; ea.disc = dpow[P.H];
+          ea.kind = EPI_TWOHOT; ea.head = (mlp == 3) ? HEAD_Q1 : HEAD_Q2; ea.disc = disc_H;
         }
       }
       run_layer<ENGINE>(P, c, LY[li], src, ea);
     }
 
+    const long long t_refit = clock64();
     if (P.mode == MODE_ITER) {
       // last CTA to finish a tile of this environment refits its mean/std
       __threadfence();
@@ -1193,6 +1262,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
       }
       publish_planes();     // refit_env wrote the stage smem through the generic proxy; TMA reuses it next tile
     }
+    c.pf6 += clock64() - t_refit;
   }
 
   if (P.prof) {
