@@ -24,15 +24,23 @@ for i in range(iters):
     print(f"iter {i}: {e0.elapsed_time(e1):.3f} ms (E={E}, tiles={E * ((cfg.num_samples + 127) // 128)})")
 
 if os.environ.get("TDMPC2_PHASE_PROF"):
-    buf = torch.zeros(148 * 4 * 12, dtype=torch.int64, device=dev)
+    buf = torch.zeros(148 * 4 * 12 + 32 * 16, dtype=torch.int64, device=dev)
     pl.lib.tdmpc2_planner_set_profile(pl.h, buf.data_ptr())
     a = (n.r[:, 0].contiguous(), n.pi[:, 0].contiguous(), n.qidx[:, 0].contiguous())
     pl.iterate(*a); torch.cuda.synchronize()
     pl.lib.tdmpc2_planner_set_profile(pl.h, None)
-    b = buf.view(148, 4, 12).double().cpu()
+    b = buf[:148 * 4 * 12].view(148, 4, 12).double().cpu()
+    tr = buf[148 * 4 * 12:].view(32, 16).cpu()
     names = ["producer", "mma", "epilogue", "idle"]
     cols = ["bar_wait", "in_layers", "facc_wait", "publish", "setup", "kernel", "actions", "refit", "decode"]
     m = b.mean(0)
     print("refit max over CTAs: %.1fk  kernel max: %.1fk min: %.1fk" % (b[:, 3, 7].max() / 1e3, b[:, 3, 5].max() / 1e3, b[:, 3, 5].min() / 1e3))
     for r in range(4):
         print(names[r].ljust(10), "  ".join(f"{cols[k]}={m[r, k] / 1e3:9.1f}k" for k in range(9)))
+
+    if os.environ.get("TDMPC2_TRACE"):
+        ev = ["start", "tma0", "mma0", "mmaL", "e0acc", "e0p1", "e0bar", "e0p2", "e0bw", "end", "e3acc", "e3p2"]
+        t00 = int(tr[0, 0])
+        for st in range(27):
+            t0 = int(tr[st, 0])
+            print(f"step {st:2d} @{(t0 - t00) / 1e3:8.1f}k  " + " ".join(f"{ev[k]}={(int(tr[st, k]) - t0) / 1e3:6.1f}" for k in range(1, 12) if int(tr[st, k]) > 0))

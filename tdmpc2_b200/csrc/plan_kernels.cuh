@@ -172,6 +172,13 @@ __device__ __forceinline__ void epi_bar_sync() {   // named barrier among the 8 
   asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
 }
 
+// Diagnostics: raw clock stamps of CTA 0 (events x layers) appended after the per-CTA counters.
+#define TDMPC2_TRACE(P_, c_, ev_)                                                                         \
+  do {                                                                                                    \
+    if ((P_).prof && blockIdx.x == 0 && (c_).trace_step < 32)                                              \
+      (P_).prof[148 * 4 * 12 + (c_).trace_step * 16 + (ev_)] = clock64();                                  \
+  } while (0)
+
 // ------------------------------------------------------------------------------------ CTA context
 struct Ctx {
   uint8_t* stage_base;      // kStages * kStageBytes, 1024-aligned
@@ -194,6 +201,7 @@ struct Ctx {
   uint32_t p_it, m_it, a_it, d_it;
   uint32_t fph0, fph1;      // fused path: phase parity of facc[0|1] (tracked identically by every thread)
   long long pf0, pf1, pf2, pf3, pf4, pf5, pf6, pf7;   // per-thread cycle accumulators (diagnostics)
+  int trace_step;
 };
 
 __device__ __forceinline__ __half* plane_ptr(const PlanParams& P, int slot, int buf, int plane) {
@@ -291,6 +299,7 @@ __device__ __forceinline__ void tc_producer(const PlanParams& P, Ctx& c, const L
       c.pf0 += clock64() - tw;
       uint8_t* st = c.stage_base + s * kStageBytes;
       ptx::mbar_expect_tx(&c.full[s], 2 * kAPlane + 2 * ncols * 128);
+      if (nc == 0 && kc == 0) TDMPC2_TRACE(P, c, 1);
       ptx::tma_load_2d(tmA, &c.full[s], st, kc * kKch, arow_hi);
       ptx::tma_load_2d(tmA, &c.full[s], st + kAPlane, kc * kKch, arow_lo);
       for (int b = 0; b < ncols / 128; ++b) {
@@ -304,7 +313,7 @@ __device__ __forceinline__ void tc_producer(const PlanParams& P, Ctx& c, const L
 }
 
 template <bool CHUNKED>
-__device__ __forceinline__ void tc_mma(Ctx& c, const LayerDev& ly) {
+__device__ __forceinline__ void tc_mma(const PlanParams& P, Ctx& c, const LayerDev& ly) {
   const int nkc = ly.Kpad / kKch;
   const int nnc = (ly.Npad + kNch - 1) / kNch;
   for (int nc = 0; nc < nnc; ++nc) {
@@ -326,6 +335,7 @@ __device__ __forceinline__ void tc_mma(Ctx& c, const LayerDev& ly) {
       const long long tw = clock64();
       ptx::mbar_wait(&c.full[s], ph);
       c.pf0 += clock64() - tw;
+      if (!CHUNKED && nc == 0 && kc == 0) TDMPC2_TRACE(P, c, 2);
       ptx::tc_fence_after();
       const uint32_t sa = ptx::smem_u32(c.stage_base + s * kStageBytes);
 #pragma unroll
@@ -346,6 +356,7 @@ __device__ __forceinline__ void tc_mma(Ctx& c, const LayerDev& ly) {
       ++c.a_it;
     } else {
       ptx::umma_commit(&c.facc[nc]);
+      if (nc == nnc - 1) TDMPC2_TRACE(P, c, 3);
     }
   }
 }
@@ -356,7 +367,7 @@ __device__ __forceinline__ void gemm_tc_wide(const PlanParams& P, Ctx& c, const 
   if (c.warp == 0) {
     if (c.lane == 0) tc_producer(P, c, ly, srcbuf);
   } else if (c.warp == 1) {
-    if (c.lane == 0) tc_mma<true>(c, ly);
+    if (c.lane == 0) tc_mma<true>(P, c, ly);
   } else if (c.warp >= kEpiWarp0 && c.warp < kEpiWarp0 + 4) {
     // TMEM drain: accumulator chunk -> raw scratch (fp32)
     const int q = c.warp & 3;                  // TMEM lane quarter this warp may touch
@@ -586,6 +597,19 @@ __device__ __forceinline__ float rcp_ftz(float x) {   // single MUFU.RCP
   return r;
 }
 __device__ __forceinline__ float exp_fast(float x) { return ex2_ftz(x * 1.4426950408889634f); }
+// Packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2 on sm_100): two elements per instruction on the FP32 pipe,
+// which is what bounds the fused epilogue.
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 mish_fast2(float2 x) {
+  const float2 a = f2(fminf(x.x, 30.f), fminf(x.y, 30.f));
+  const float2 z = __fmul2_rn(a, f2s(1.4426950408889634f));
+  const float2 e = f2(ex2_ftz(z.x), ex2_ftz(z.y));
+  const float2 n = __fmul2_rn(e, __fadd2_rn(e, f2s(2.f)));
+  const float2 d = __fadd2_rn(n, f2s(2.f));
+  const float2 r = f2(rcp_ftz(d.x), rcp_ftz(d.y));
+  return __fmul2_rn(x, __fmul2_rn(n, r));
+}
 __device__ __forceinline__ float mish_fast(float x) {
   const float e = exp_fast(fminf(x, 30.f));        // x > 30: n/(n+2) == 1 in fp32 already; keeps e*e finite
   const float n = e * (e + 2.f);
@@ -613,24 +637,30 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
     ptx::mbar_wait(&c.facc[j], j ? c.fph1 : c.fph0);
     c.pf2 += clock64() - tw;
   }
+  const bool tr0 = (et.grp == 0 && et.q == 0 && c.lane == 0), tr3 = (et.grp == 3 && et.q == 0 && c.lane == 0);
+  if (tr0) TDMPC2_TRACE(P, c, 4);
+  if (tr3) TDMPC2_TRACE(P, c, 10);
   ptx::tc_fence_after();
   // ---- pass 1: shifted moments of this group's columns
   float x0 = 0.f, s = 0.f, q = 0.f;
-  for (int c0 = cb; c0 < cb + nvalid; c0 += 32) {
-    uint32_t v[32];
-    ptx::tmem_ld_32x32(et.taddr + c0, v);
+  float2 s2 = f2s(0.f), q2 = f2s(0.f);
+  for (int c0 = cb; c0 < cb + nvalid; c0 += 16) {
+    uint32_t v[16];
+    ptx::tmem_ld_32x16(et.taddr + c0, v);
     ptx::tmem_ld_wait();
     if (c0 == cb) x0 = fmaf(__uint_as_float(v[0]), inv_scale, sb[c0]);
-    const bool full = (c0 + 32 <= N);
+    const bool full = (c0 + 16 <= N);
 #pragma unroll
-    for (int i4 = 0; i4 < 32; i4 += 4) {
+    for (int i4 = 0; i4 < 16; i4 += 4) {
       const float4 b4 = lds128(sb + c0 + i4);
       const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
       if (full) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float d = fmaf(__uint_as_float(v[i4 + j]), inv_scale, bb[j]) - x0;
-          s += d; q = fmaf(d, d, q);
+        for (int j = 0; j < 4; j += 2) {
+          const float2 xv = __ffma2_rn(f2(__uint_as_float(v[i4 + j]), __uint_as_float(v[i4 + j + 1])), f2s(inv_scale),
+                                       f2(bb[j] - x0, bb[j + 1] - x0));
+          s2 = __fadd2_rn(s2, xv);
+          q2 = __ffma2_rn(xv, xv, q2);
         }
       } else {
 #pragma unroll
@@ -641,12 +671,16 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
       }
     }
   }
+  s += s2.x + s2.y;
+  q += q2.x + q2.y;
   {
     const float n_g = static_cast<float>(nvalid);
     c.part[et.grp * kTileM + et.row] = nvalid > 0 ? x0 + s / n_g : 0.f;                       // group mean
     c.part[(kEpiGroups + et.grp) * kTileM + et.row] = nvalid > 0 ? q - s * s / n_g : 0.f;     // group M2
   }
+  if (tr0) TDMPC2_TRACE(P, c, 5);
   epi_bar_sync();
+  if (tr0) { float dummy = c.part[et.row]; if (dummy == 123.456f) c.pf7++; TDMPC2_TRACE(P, c, 6); }
   float mean = 0.f, rstd;
   {
     float m2 = 0.f, cnt = 0.f;
@@ -681,10 +715,12 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
   const uint32_t rowaddr = ptx::smem_u32(buf) + static_cast<uint32_t>(et.row) * 128u;
   for (int c0 = cb; c0 < cb + nvalid; c0 += 16) {
     const int sub = (c0 - cb) & 63;                               // 0,16,32,48 within the 64-column block
+#ifndef TDMPC2_EXP_NOWAIT
     if (use_tma && sub == 0 && c0 != cb) {                        // staging reuse: the previous store must have read it
       if (leader) ptx::bulk_wait_read<0>();
       group_bar_sync(et.grp);
     }
+#endif
     uint32_t v[16];
     ptx::tmem_ld_32x16(et.taddr + c0, v);
     ptx::tmem_ld_wait();
@@ -697,16 +733,20 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
       const float4 e4 = lds128(sbe + c0 + i4);
       const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w}, ee[4] = {e4.x, e4.y, e4.z, e4.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float x = fmaf(__uint_as_float(v[i4 + j]), inv_scale, bb[j]);
-        const float u = fmaf(x, rstd, nmr);
-        y[i4 + j] = fmaf(u, gg[j], ee[j]);
-        if (!full && c0 + i4 + j >= N) y[i4 + j] = -CUDART_INF_F;
+      for (int j = 0; j < 4; j += 2) {
+        const float2 x = __ffma2_rn(f2(__uint_as_float(v[i4 + j]), __uint_as_float(v[i4 + j + 1])), f2s(inv_scale), f2(bb[j], bb[j + 1]));
+        const float2 u = __ffma2_rn(x, f2s(rstd), f2s(nmr));
+        float2 t = __ffma2_rn(u, f2(gg[j], gg[j + 1]), f2(ee[j], ee[j + 1]));
+        if (ea.kind == EPI_LN_MISH) t = mish_fast2(t);
+        y[i4 + j] = t.x; y[i4 + j + 1] = t.y;
       }
     }
-    if (ea.kind == EPI_LN_MISH) {
+    if (!full) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) y[i] = mish_fast(y[i]);
+      for (int i = 0; i < 16; ++i)
+        if (c0 + i >= N) y[i] = (ea.kind == EPI_LN_MISH) ? 0.f : -CUDART_INF_F;
+    }
+    if (ea.kind == EPI_LN_MISH) {
     } else {
       // SimNorm: softmax over groups of 8 consecutive columns (layers.py:84-88)
 #pragma unroll
@@ -731,7 +771,8 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
           const float a0 = y[2 * i], a1 = y[2 * i + 1];
           const __half2 h2 = __floats2half2_rn(a0, a1);
           const float2 hf = __half22float2(h2);
-          const __half2 l2 = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+          const float2 df = __fadd2_rn(f2(a0, a1), f2(-hf.x, -hf.y));
+          const __half2 l2 = __floats2half2_rn(df.x, df.y);
           hw[i] = *reinterpret_cast<const uint32_t*>(&h2);
           lw[i] = *reinterpret_cast<const uint32_t*>(&l2);
         }
@@ -746,7 +787,11 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
           if (sub == 48) {                                        // 64-column block complete: hand it to the TMA unit
             ptx::fence_proxy_async_smem();
             group_bar_sync(et.grp);
+#ifdef TDMPC2_EXP_NOTMA
+            if (leader && c0 < 0) {
+#else
             if (leader) {
+#endif
               const int col = ea.dst_col0 + c0 - 48;
               ptx::tma_store_2d(tmD, buf, col, plane_row0(P, c.slot, ea.dstbuf, 0));
               ptx::tma_store_2d(tmD, buf + kAPlane, col, plane_row0(P, c.slot, ea.dstbuf, 1));
@@ -777,7 +822,12 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
         if (c0 + i < N) po[i] = y[i];
     }
   }
+  if (tr0) TDMPC2_TRACE(P, c, 7);
+  if (tr3) TDMPC2_TRACE(P, c, 11);
+#ifndef TDMPC2_EXP_NOWAIT
   if (use_tma && leader) ptx::bulk_wait<0>();                     // stores performed before the layer is published
+#endif
+  if (tr0) TDMPC2_TRACE(P, c, 8);
 }
 
 // Head epilogues (plain Linear outputs, Npad <= 256 so chunk 0 only).  Column group 0 (warps 4..7) works.
@@ -831,13 +881,13 @@ __device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, cons
     __half* xhi = plane_ptr(P, c.slot, BUF_X, 0) + static_cast<size_t>(et.row) * P.KpadX + P.L + P.T;
     __half* xlo = plane_ptr(P, c.slot, BUF_X, 1) + static_cast<size_t>(et.row) * P.KpadX + P.L + P.T;
     const float* eps = ea.eps_base + (static_cast<size_t>(e) * ea.eps_rows + idx) * P.A;
-    for (int a0 = 0; a0 < P.A; a0 += 32) {
-      uint32_t vm[32], vs[32];
-      ptx::tmem_ld_32x32(et.taddr + a0, vm);            // mean logits, columns [a0, a0+32)
-      ptx::tmem_ld_32x32(et.taddr + P.Apad + a0, vs);   // log_std logits, columns [Apad+a0, Apad+a0+32) (32-aligned)
+    for (int a0 = 0; a0 < P.A; a0 += 16) {
+      uint32_t vm[16], vs[16];
+      ptx::tmem_ld_32x16(et.taddr + a0, vm);            // mean logits, columns [a0, a0+16)
+      ptx::tmem_ld_32x16(et.taddr + P.Apad + a0, vs);   // log_std logits, columns [Apad+a0, Apad+a0+16) (aligned)
       ptx::tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
+      for (int i = 0; i < 16; ++i) {
         const int a = a0 + i;
         if (a < P.A) {
           const float mu = fmaf(__uint_as_float(vm[i]), inv_scale, sb[a]);
@@ -882,10 +932,11 @@ __device__ __forceinline__ void run_layer(const PlanParams& P, Ctx& c, const Lay
                      (ea.kind != EPI_RAW || ly.Npad <= kNch);
   if (fused) {
     const long long tl = clock64();
+    if (threadIdx.x == 0) TDMPC2_TRACE(P, c, 0);
     if (c.warp == 0) {
       if (c.lane == 0) tc_producer(P, c, ly, srcbuf);
     } else if (c.warp == 1) {
-      if (c.lane == 0) tc_mma<false>(c, ly);
+      if (c.lane == 0) tc_mma<false>(P, c, ly);
     } else if (c.warp >= kEpiWarp0) {
       if (is_ln) epi_ln_fused(P, c, ly, ea);
       else epi_head_fused(P, c, ly, ea);
@@ -907,6 +958,7 @@ __device__ __forceinline__ void run_layer(const PlanParams& P, Ctx& c, const Lay
   if (tma_only) __syncthreads();
   else publish_planes();
   c.pf3 += clock64() - tp;
+  if (threadIdx.x == 64 && fused) TDMPC2_TRACE(P, c, 9);
   if (fused) ptx::tc_fence_after();
 }
 
@@ -1036,6 +1088,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
   c.p_it = c.m_it = c.a_it = c.d_it = 0;
   c.fph0 = c.fph1 = 0;
   c.pf0 = c.pf1 = c.pf2 = c.pf3 = c.pf4 = c.pf5 = c.pf6 = c.pf7 = 0;
+  c.trace_step = 1 << 30;
   const long long t_kernel0 = clock64();
   c.tmem_base = 0;
   int* rowenv = c.rowenv;
@@ -1149,9 +1202,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
     else if (P.mode == MODE_PRIOR) nsteps = 6 * (P.H - 1) + 3;
     else nsteps = 6 * P.H + 9;
     const float* dpow = P.disc_pow + static_cast<size_t>(task_tile) * (P.H + 1);
-    int qi[2] = {0, 0};
-    if (P.mode == MODE_ITER || P.mode == MODE_VALUE) { qi[0] = P.qidx[static_cast<size_t>(env_tile) * 2]; qi[1] = P.qidx[static_cast<size_t>(env_tile) * 2 + 1]; }
-    const float disc_H = dpow[P.H];
+    const int* qi = (P.mode == MODE_ITER || P.mode == MODE_VALUE) ? P.qidx + static_cast<size_t>(env_tile) * 2 : nullptr;
 
     for (int sidx = 0; sidx < nsteps; ++sidx) {
       EpiArgs ea;
@@ -1222,7 +1273,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
           mlp = 2 + u / 3; l = u % 3;
         }
         src = l == 0 ? BUF_X : (l == 1 ? BUF_H1 : BUF_H2);
-        const int base = mlp == 0 ? P.li_rew : mlp == 1 ? P.li_dyn : mlp == 2 ? P.li_pi : P.li_q + 3 * (mlp == 3 ? qi[0] : qi[1]);
+        const int base = mlp == 0 ? P.li_rew : mlp == 1 ? P.li_dyn : mlp == 2 ? P.li_pi : P.li_q + 3 * qi[mlp - 3];
         li = base + l;
         if (l < 2) {
           ea.kind = EPI_LN_MISH; ea.dstbuf = l == 0 ? BUF_H1 : BUF_H2;
@@ -1239,9 +1290,10 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
             ea.eps_base = P.noise_pi; ea.eps_rows = P.N;
           }
         } else {                               // Q heads (world_model.py:186-216)
-          ea.kind = EPI_TWOHOT; ea.head = (mlp == 3) ? HEAD_Q1 : HEAD_Q2; ea.disc = disc_H;
+          ea.kind = EPI_TWOHOT; ea.head = (mlp == 3) ? HEAD_Q1 : HEAD_Q2; ea.disc = dpow[P.H];
         }
       }
+      c.trace_step = (tile == blockIdx.x) ? sidx : (1 << 30);
       run_layer<ENGINE>(P, c, LY[li], src, ea);
     }
 
