@@ -145,9 +145,12 @@ __device__ __forceinline__ float symexp_f(float x) {   // math.py:50-55
   return x > 0.f ? m : (x < 0.f ? -m : 0.f);
 }
 __device__ __forceinline__ void split_f(float x, __half& h, __half& l) {
+  // finite values are clamped into fp16 range; NaN / +-inf stay non-finite so that they poison the row exactly
+  // as they do in the reference (whose planner then zeroes the value: nan_to_num, tdmpc2.py:184)
+  const bool finite = fabsf(x) <= 3.0e38f;
   x = fminf(fmaxf(x, -65000.f), 65000.f);
-  h = __float2half_rn(x);
-  l = __float2half_rn(x - __half2float(h));
+  h = finite ? __float2half_rn(x) : __ushort_as_half(static_cast<unsigned short>(0x7fff));
+  l = __float2half_rn(finite ? x - __half2float(h) : 0.f);
 }
 __device__ __forceinline__ void split_store(__half* hi, __half* lo, float x) {
   __half h, l;

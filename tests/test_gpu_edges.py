@@ -1,0 +1,119 @@
+"""Edge cases of the planning path on the GPU (through the C ABI / agent API) against the oracle:
+ragged sample counts (N not a multiple of the 128-row tile), no policy-prior trajectories, horizon 1,
+odd environment counts, single-env reference shapes, NaN guard, checkpoint round trip."""
+import pytest
+import torch
+
+from tdmpc2_b200.config import workload
+from tdmpc2_b200.synth import synth_state_dict
+from helpers import stable_positions, boundary_separated
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_and_compare(cfg, E, sd, seed=11, eval_mode=False, obs_scale=1.0, atol_v=5e-5):
+    from oracle.plan_oracle import draw_noise as oracle_noise, plan_oracle
+    from tdmpc2_b200.planner import Noise, Planner
+    g = torch.Generator().manual_seed(seed)
+    obs = obs_scale * torch.randn(E, cfg.obs_shape["state"][0], generator=g)
+    prev = 0.3 * torch.randn(E, cfg.horizon, cfg.action_dim, generator=g)
+    t0 = [bool((i + 1) % 2) for i in range(E)]
+    task = [(3 * i + 1) % len(cfg.tasks) for i in range(E)] if cfg.multitask else None
+    n = oracle_noise(cfg, 70 + seed, E, eval_mode=eval_mode)
+    want = plan_oracle(cfg, sd, obs, task=task, t0=t0, prev_mean=prev, noise=n, eval_mode=eval_mode)
+    pl = Planner(cfg, E, "cuda:0")
+    pl.pack(sd)
+    noise = Noise(n.prior.cuda().contiguous(), n.r.cuda().contiguous(), n.pi.cuda().contiguous(),
+                  n.qidx.to(torch.int32).cuda().contiguous(), n.expo.cuda().contiguous(),
+                  None if eval_mode else n.final.cuda().contiguous())
+    taskv = torch.tensor(task, dtype=torch.int32).cuda() if task is not None else None
+    action, new_mean, tr = pl.plan(obs.cuda().contiguous(), taskv, torch.tensor(t0, dtype=torch.uint8).cuda(),
+                                   prev.cuda().contiguous(), noise, trace=True)
+    torch.cuda.synchronize()
+    K, n_ok = cfg.num_elites, 0
+    for e in range(E):
+        clean = True
+        for it in range(cfg.iterations):
+            if not clean:
+                break
+            got, ref = tr["values"][e, it].cpu(), want.values[e, it]
+            assert torch.allclose(got, ref, atol=atol_v, rtol=1e-5), f"env {e} it {it}: {(got - ref).abs().max():.3e}"
+            st = stable_positions(ref, K, 1e-4) if K < cfg.num_samples else torch.zeros(K, dtype=torch.bool)
+            assert torch.equal(tr["elite_idx"][e, it].cpu()[st], want.elite_idx[e, it][st])
+            clean = bool(boundary_separated(ref, K, 1e-4)) if K < cfg.num_samples else True
+        if clean:
+            assert torch.allclose(new_mean[e].cpu(), want.mean[e], atol=1e-4, rtol=0)
+            n_ok += 1
+    assert n_ok > 0
+    return action.cpu(), want
+
+
+@pytest.mark.parametrize("over", [
+    dict(num_samples=200, num_elites=24, num_pi_trajs=8),      # ragged: 2 tiles, second one 72 rows
+    dict(num_samples=128, num_elites=16, num_pi_trajs=0),      # no policy-prior trajectories
+    dict(num_samples=96, num_elites=96, num_pi_trajs=5),       # every sample is an elite; N < one tile
+    dict(horizon=1, num_samples=128, num_elites=16),           # single-step rollout
+    dict(num_q=2, iterations=1),                               # smallest ensemble, one iteration
+])
+def test_ragged_and_degenerate_shapes(over):
+    cfg = workload("tiny", num_envs=3, **over)
+    sd = synth_state_dict(cfg, seed=21, perturb=True)
+    _run_and_compare(cfg, 3, sd)
+
+
+def test_multitask_odd_env_count_eval_mode():
+    cfg = workload("tiny-mt", num_envs=5, num_samples=160, num_elites=20)
+    sd = synth_state_dict(cfg, seed=22, perturb=True, emb_scale=60.0)
+    action, want = _run_and_compare(cfg, 5, sd, eval_mode=True)
+    assert action.abs().max() <= 1.0
+
+
+def test_nan_values_are_zeroed_like_nan_to_num():
+    """Infinite observations make every trajectory value NaN; tdmpc2.py:184 turns them into 0."""
+    from tdmpc2_b200.planner import Planner, draw_noise
+    cfg = workload("tiny", num_envs=1)
+    sd = synth_state_dict(cfg, seed=23, perturb=True)
+    pl = Planner(cfg, 1, "cuda:0")
+    pl.pack(sd)
+    obs = torch.full((1, cfg.obs_shape["state"][0]), float("inf"), device="cuda")
+    n = draw_noise(cfg, 1, "cuda:0")
+    action, mean, tr = pl.plan(obs, None, torch.ones(1, dtype=torch.uint8, device="cuda"),
+                               torch.zeros(1, cfg.horizon, cfg.action_dim, device="cuda"), n, trace=True)
+    torch.cuda.synchronize()
+    assert torch.all(tr["values"] == 0)
+    # all-equal values: ties resolve to the lowest indices, like a stable descending sort
+    assert torch.equal(tr["elite_idx"][0, 0].cpu(), torch.arange(cfg.num_elites))
+    assert torch.isfinite(action).all() and torch.isfinite(mean).all()
+
+
+def test_agent_api_shapes_state_and_checkpoint(tmp_path):
+    """Reference-shaped surface: act() on CPU obs returns a CPU action in [-1,1]; _prev_mean is carried;
+    save()/load() round-trips through the reference's {"model": state_dict} format."""
+    from tdmpc2_b200.tdmpc2 import TDMPC2
+    cfg = workload("tiny", num_envs=1)
+    agent = TDMPC2(cfg, device="cuda:0")
+    agent.load(synth_state_dict(cfg, seed=24, perturb=True))
+    agent.generator = torch.Generator(device="cuda:0").manual_seed(5)
+    obs = torch.randn(cfg.obs_shape["state"][0])
+    a0 = agent.act(obs, t0=True)
+    assert a0.device.type == "cpu" and a0.shape == (cfg.action_dim,) and a0.abs().max() <= 1
+    pm = agent._prev_mean.clone()
+    assert pm.shape == (cfg.horizon, cfg.action_dim) and pm.abs().sum() > 0
+    a1 = agent.act(obs, t0=False, eval_mode=True)
+    assert not torch.equal(agent._prev_mean, pm)
+    fp = tmp_path / "agent.pt"
+    agent.save(fp)
+    other = TDMPC2(workload("tiny", num_envs=1), device="cuda:0")
+    other.load(str(fp))
+    other.generator = torch.Generator(device="cuda:0").manual_seed(5)
+    agent.generator = torch.Generator(device="cuda:0").manual_seed(5)
+    agent._prev_mean.zero_(); other._prev_mean.zero_()
+    assert torch.equal(agent.act(obs, t0=True), other.act(obs, t0=True))
+    # batched agent: [E, obs] in, [E, A] out, one _prev_mean per environment
+    cfgb = workload("tiny", num_envs=4)
+    b = TDMPC2(cfgb, device="cuda:0")
+    b.load(synth_state_dict(cfgb, seed=24, perturb=True))
+    out = b.act(torch.randn(4, cfgb.obs_shape["state"][0]), t0=torch.tensor([True, False, True, False]))
+    assert out.shape == (4, cfgb.action_dim) and b._prev_mean.shape == (4, cfgb.horizon, cfgb.action_dim)
+    with pytest.raises(ValueError):
+        b.act(torch.randn(3, cfgb.obs_shape["state"][0]))
