@@ -278,6 +278,13 @@ def main():
             dist.destroy_process_group()
         return
     peaks, peak_src = load_peaks()
+    traffic = None
+    try:   # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture of this workload
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            if args.workload == "c2" and E_local == 256:
+                traffic = json.load(f)["dram_bytes_per_launch"]
+    except Exception:
+        traffic = None
     L, M, A_, T, B = cfg.latent_dim, cfg.mlp_dim, cfg.action_dim, cfg.task_dim, cfg.num_bins
     D = L + T + A_
     w = lambda i, h, o: i * h + h * h + h * o
@@ -304,7 +311,7 @@ def main():
                 "h2d_bytes_per_step": int(E_local * obs_dim * 4), "d2h_bytes_per_step": int(E_total * A_ * 4)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "plan_kernel<tcgen05> MODE_ITER (one CEM iteration)",
+                     "traffic": traffic, "kernel": "plan_kernel<tcgen05> MODE_ITER (one CEM iteration)",
                      "ms_per_launch": ms_iter, "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({peak_src}, burst)",
                      "note": "achieved counts ALGORITHMIC flops (2 Q heads, 1x); the fp32-parity path issues 3 fp16 MMAs "
                              "per product, so its ceiling is peak/3"},

@@ -297,13 +297,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_map(EncodeTiledFn enc, CUtensorMap* m, void* base, uint64_t kpad, uint64_t rows) {
+static int make_map(EncodeTiledFn enc, CUtensorMap* m, void* base, uint64_t kpad, uint64_t rows, int box_cols = kKch) {
   cuuint64_t dims[2] = {kpad, rows};
   cuuint64_t strides[1] = {kpad * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(kKch), 128};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), 128};
   cuuint32_t estr[2] = {1, 1};
+  // 64-column boxes (operand loads): 128-byte rows, 128B swizzle; 32-column boxes (epilogue stores): 64B swizzle
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   box_cols == kKch ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(TDMPC2_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) kpad=%llu rows=%llu", (int)r,
                                      (unsigned long long)kpad, (unsigned long long)rows);
   return 0;
@@ -328,6 +330,8 @@ extern "C" int tdmpc2_planner_bind(tdmpc2_planner* p, void* packed, void* worksp
   int rc;
   if ((rc = make_map(enc, &B.tmX, p->ws + p->off_X, p->KpadX, static_cast<uint64_t>(p->nslots) * 2 * kTileM))) return rc;
   if ((rc = make_map(enc, &B.tmH, p->ws + p->off_H, p->KpadH, static_cast<uint64_t>(p->nslots) * 4 * kTileM))) return rc;
+  if ((rc = make_map(enc, &B.tmXs, p->ws + p->off_X, p->KpadX, static_cast<uint64_t>(p->nslots) * 2 * kTileM, 32))) return rc;
+  if ((rc = make_map(enc, &B.tmHs, p->ws + p->off_H, p->KpadH, static_cast<uint64_t>(p->nslots) * 4 * kTileM, 32))) return rc;
   for (int m = 0; m < p->nmaps; ++m)
     if ((rc = make_map(enc, &B.tmW[m], p->packed + p->map_off[m], p->map_kpad[m], p->map_rows[m]))) return rc;
 

