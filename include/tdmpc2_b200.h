@@ -50,7 +50,10 @@ typedef enum tdmpc2_status {
 /* GEMM engine used by the fused MLP kernels. */
 typedef enum tdmpc2_engine {
   TDMPC2_ENGINE_TCGEN05 = 0,   /* TMA + tcgen05.mma (3x fp16-split, fp32 TMEM accumulate): the product path */
-  TDMPC2_ENGINE_SIMT = 1       /* CUDA-core fp32 FFMA over the same packed operands: bring-up / diagnostics  */
+  TDMPC2_ENGINE_SIMT = 1,      /* CUDA-core fp32 FFMA over the same packed operands: bring-up / diagnostics  */
+  TDMPC2_ENGINE_TCGEN05_2SM = 2 /* as 0, but CEM iterations run on CTA pairs (tcgen05 cta_group::2, M = 256):
+                                  each CTA streams half of every weight tile.  Falls back to 0 when a model has
+                                  layers wider than TMEM or an odd number of 128-row tiles per environment */
 } tdmpc2_engine;
 
 /* Planner + model dimensions.  Mirrors the keys the reference reads from cfg:

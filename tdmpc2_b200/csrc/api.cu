@@ -126,7 +126,7 @@ struct tdmpc2_planner {
   uint8_t* ws = nullptr;
   PlanParams base;
   int engine = TDMPC2_ENGINE_TCGEN05;
-  bool bound = false, weights_ok = false, smem_attr_set[2] = {false, false};
+  bool bound = false, weights_ok = false, smem_attr_set[2] = {false, false}, smem_attr_pair = false, all_fused = true;
   int64_t launches = 0;
   const int32_t* cur_task = nullptr;
   long long* prof = nullptr;
@@ -221,7 +221,7 @@ extern "C" int tdmpc2_planner_create(const tdmpc2_dims* dims, tdmpc2_planner** o
   p->KpadX = std::max(pad_to(D, kKch), pad_to(d.obs_dim + T, kKch));
   p->KpadH = std::max(pad_to(M, kKch), pad_to(d.enc_dim, kKch));
   p->NpadMax = 0;
-  for (auto& l : p->layers) p->NpadMax = std::max(p->NpadMax, l.Npad);
+  for (auto& l : p->layers) { p->NpadMax = std::max(p->NpadMax, l.Npad); if (l.Npad > kFusedMaxN) p->all_fused = false; }
   p->Ppad = 1;
   while (p->Ppad < d.num_pi_trajs) p->Ppad <<= 1;
   p->tiles_per_env = (d.num_samples + kTileM - 1) / kTileM;
@@ -288,7 +288,8 @@ extern "C" int tdmpc2_planner_set_profile(tdmpc2_planner* p, long long* device_b
   return 0;
 }
 extern "C" int tdmpc2_planner_set_engine(tdmpc2_planner* p, int engine) {
-  if (!p || (engine != TDMPC2_ENGINE_TCGEN05 && engine != TDMPC2_ENGINE_SIMT)) return fail(TDMPC2_ERR_INVALID, "bad engine");
+  if (!p || (engine != TDMPC2_ENGINE_TCGEN05 && engine != TDMPC2_ENGINE_SIMT && engine != TDMPC2_ENGINE_TCGEN05_2SM))
+    return fail(TDMPC2_ERR_INVALID, "bad engine");
   p->engine = engine;
   return 0;
 }
@@ -445,10 +446,26 @@ static int launch_plan(tdmpc2_planner* p, const PlanParams& prm, int ntiles, cud
     else CUDA_TRY(cudaFuncSetAttribute(plan_kernel<ENGINE_SIMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     p->smem_attr_set[eng] = true;
   }
-  const int grid = std::min(ntiles, p->nslots);
+  int grid = std::min(ntiles, p->nslots);
   PlanParams prm2 = prm;
   prm2.prof = p->prof;
-  if (eng == 0) plan_kernel<ENGINE_TC><<<grid, kThreads, kSmemBytes, st>>>(prm2);
+  // CTA-pair (cta_group::2) launch: CEM iterations only, whole pairs of tiles of one environment, fused layers only
+  bool pair = (p->engine == TDMPC2_ENGINE_TCGEN05_2SM) && prm.mode == MODE_ITER && (p->tiles_per_env % 2 == 0) &&
+              (ntiles % 2 == 0) && p->all_fused;
+  if (pair) {
+    if (!p->smem_attr_pair) {
+      CUDA_TRY(cudaFuncSetAttribute(plan_kernel<ENGINE_TC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      p->smem_attr_pair = true;
+    }
+    grid &= ~1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, plan_kernel<ENGINE_TC, true>, prm2));
+  } else if (eng == 0) plan_kernel<ENGINE_TC><<<grid, kThreads, kSmemBytes, st>>>(prm2);
   else plan_kernel<ENGINE_SIMT><<<grid, kThreads, kSmemBytes, st>>>(prm2);
   CUDA_TRY(cudaGetLastError());
   p->launches += 1;

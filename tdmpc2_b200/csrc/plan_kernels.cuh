@@ -214,6 +214,7 @@ struct Ctx {
   int* rowenv;              // [128]
   uint32_t tmem_base;
   int slot, warp, lane;
+  int cg2, rank;             // CTA-pair mode (tcgen05 cta_group::2): pair rank 0 = leader issues the MMAs
   // pipeline counters (each role keeps its own; persist across layers / tiles)
   uint32_t pa_it, pw_it, ma_it, mw_it, a_it, d_it;
   uint32_t fph0, fph1;      // fused path: phase parity of facc[0|1] (tracked identically by every thread)
@@ -309,9 +310,16 @@ __device__ __forceinline__ void prod_load_a(const PlanParams& P, Ctx& c, const C
   ptx::mbar_wait(&c.a_empty[s], ph ^ 1);
   c.pf0 += clock64() - tw;
   uint8_t* st = c.stage_base + s * kASlotBytes;
-  ptx::mbar_expect_tx(&c.a_full[s], kASlotBytes);
-  ptx::tma_load_2d(tmA, &c.a_full[s], st, kc * kKch, arow_hi);
-  ptx::tma_load_2d(tmA, &c.a_full[s], st + kAPlane, kc * kKch, arow_lo);
+  if (c.cg2) {
+    // both CTAs of the pair stream their own 128 rows; the bytes of both land on the leader's barrier
+    if (c.rank == 0) ptx::mbar_expect_tx(&c.a_full[s], 2 * kASlotBytes);
+    ptx::tma_load_2d_2sm(tmA, &c.a_full[s], st, kc * kKch, arow_hi);
+    ptx::tma_load_2d_2sm(tmA, &c.a_full[s], st + kAPlane, kc * kKch, arow_lo);
+  } else {
+    ptx::mbar_expect_tx(&c.a_full[s], kASlotBytes);
+    ptx::tma_load_2d(tmA, &c.a_full[s], st, kc * kKch, arow_hi);
+    ptx::tma_load_2d(tmA, &c.a_full[s], st + kAPlane, kc * kKch, arow_lo);
+  }
   ++c.pa_it;
 }
 __device__ __forceinline__ void prod_load_w(Ctx& c, const CUtensorMap* tmW, const LayerDev& ly, int kc, int nc) {
@@ -321,11 +329,20 @@ __device__ __forceinline__ void prod_load_w(Ctx& c, const CUtensorMap* tmW, cons
   ptx::mbar_wait(&c.w_empty[s], ph ^ 1);
   c.pf0 += clock64() - tw;
   uint8_t* st = c.stage_base + kWRingOff + s * kWSlotBytes;
-  ptx::mbar_expect_tx(&c.w_full[s], 2 * ncols * 128);
-  for (int b = 0; b < ncols / 128; ++b) {
-    const int wr = ly.wrow + nc * kNch + b * 128;
-    ptx::tma_load_2d(tmW, &c.w_full[s], st + b * (128 * 128), kc * kKch, wr);
-    ptx::tma_load_2d(tmW, &c.w_full[s], st + kWPlane + b * (128 * 128), kc * kKch, wr + ly.Npad);
+  if (c.cg2) {
+    // each CTA streams HALF of the N-chunk's weight rows (one 128-row box per plane; for a 128-column chunk only
+    // its first 64 rows are consumed): the pair MMA reads B rows [0, N/2) from the leader and [N/2, N) from the peer
+    if (c.rank == 0) ptx::mbar_expect_tx(&c.w_full[s], 2 * (2 * 128 * 128));
+    const int wr = ly.wrow + nc * kNch + c.rank * (ncols / 2);
+    ptx::tma_load_2d_2sm(tmW, &c.w_full[s], st, kc * kKch, wr);
+    ptx::tma_load_2d_2sm(tmW, &c.w_full[s], st + kWPlane, kc * kKch, wr + ly.Npad);
+  } else {
+    ptx::mbar_expect_tx(&c.w_full[s], 2 * ncols * 128);
+    for (int b = 0; b < ncols / 128; ++b) {
+      const int wr = ly.wrow + nc * kNch + b * 128;
+      ptx::tma_load_2d(tmW, &c.w_full[s], st + b * (128 * 128), kc * kKch, wr);
+      ptx::tma_load_2d(tmW, &c.w_full[s], st + kWPlane + b * (128 * 128), kc * kKch, wr + ly.Npad);
+    }
   }
   ++c.pw_it;
 }
@@ -353,16 +370,22 @@ __device__ __forceinline__ void tc_producer(const PlanParams& P, Ctx& c, const L
 }
 
 // 12 MMAs of one (A K-chunk, W K-chunk x N-chunk) pair: A_lo*W_hi + A_hi*W_lo + A_hi*W_hi, 4 K-steps of 16.
-__device__ __forceinline__ void mma_stage(uint32_t d, uint32_t sa, uint32_t sw, uint32_t idesc, bool first) {
+__device__ __forceinline__ void mma_stage(uint32_t d, uint32_t sa, uint32_t sw, uint32_t idesc, bool first, bool cg2) {
 #pragma unroll
   for (int ks = 0; ks < kKch / 16; ++ks) {
     const uint64_t a_hi = ptx::make_sw128_kmajor_desc(sa + ks * 32);
     const uint64_t a_lo = ptx::make_sw128_kmajor_desc(sa + kAPlane + ks * 32);
     const uint64_t w_hi = ptx::make_sw128_kmajor_desc(sw + ks * 32);
     const uint64_t w_lo = ptx::make_sw128_kmajor_desc(sw + kWPlane + ks * 32);
-    ptx::umma_f16(d, a_lo, w_hi, idesc, !(first && ks == 0));   // small terms first
-    ptx::umma_f16(d, a_hi, w_lo, idesc, 1);
-    ptx::umma_f16(d, a_hi, w_hi, idesc, 1);
+    if (cg2) {
+      ptx::umma_f16_2sm(d, a_lo, w_hi, idesc, !(first && ks == 0));
+      ptx::umma_f16_2sm(d, a_hi, w_lo, idesc, 1);
+      ptx::umma_f16_2sm(d, a_hi, w_hi, idesc, 1);
+    } else {
+      ptx::umma_f16(d, a_lo, w_hi, idesc, !(first && ks == 0));   // small terms first
+      ptx::umma_f16(d, a_hi, w_lo, idesc, 1);
+      ptx::umma_f16(d, a_hi, w_hi, idesc, 1);
+    }
   }
 }
 __device__ __forceinline__ uint32_t mma_wait_a(Ctx& c) {
@@ -394,14 +417,17 @@ __device__ __forceinline__ void tc_mma(const PlanParams& P, Ctx& c, const LayerD
         ptx::tc_fence_after();
         const int ncols = min(kNch, ly.Npad - nc * kNch);
         mma_stage(c.tmem_base + nc * kNch, sbase + as * kASlotBytes, sbase + kWRingOff + ws * kWSlotBytes,
-                  ptx::make_idesc_f16(kTileM, ncols), kc == 0);
-        ptx::umma_commit(&c.w_empty[ws]);     // frees the W slot when these MMAs retire
+                  ptx::make_idesc_f16(c.cg2 ? 2 * kTileM : kTileM, ncols), kc == 0, c.cg2 != 0);
+        if (c.cg2) ptx::umma_commit_2sm(&c.w_empty[ws]);
+        else ptx::umma_commit(&c.w_empty[ws]);     // frees the W slot when these MMAs retire
         ++c.mw_it;
       }
-      ptx::umma_commit(&c.a_empty[as]);
+      if (c.cg2) ptx::umma_commit_2sm(&c.a_empty[as]);
+      else ptx::umma_commit(&c.a_empty[as]);
       ++c.ma_it;
     }
-    ptx::umma_commit(&c.facc[0]);
+    if (c.cg2) ptx::umma_commit_2sm(&c.facc[0]);
+    else ptx::umma_commit(&c.facc[0]);
     TDMPC2_TRACE(P, c, 3);
   } else {
     for (int nc = 0; nc < nnc; ++nc) {
@@ -414,7 +440,7 @@ __device__ __forceinline__ void tc_mma(const PlanParams& P, Ctx& c, const LayerD
         const uint32_t as = mma_wait_a(c);
         const uint32_t ws = mma_wait_w(c);
         ptx::tc_fence_after();
-        mma_stage(c.tmem_base + slot * kNch, sbase + as * kASlotBytes, sbase + kWRingOff + ws * kWSlotBytes, idesc, kc == 0);
+        mma_stage(c.tmem_base + slot * kNch, sbase + as * kASlotBytes, sbase + kWRingOff + ws * kWSlotBytes, idesc, kc == 0, false);
         ptx::umma_commit(&c.w_empty[ws]);
         ptx::umma_commit(&c.a_empty[as]);
         ++c.mw_it; ++c.ma_it;
@@ -887,7 +913,9 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
   if (tr0) TDMPC2_TRACE(P, c, 8);
 }
 
-// Head epilogues (plain Linear outputs, Npad <= 256 so chunk 0 only).  Column group 0 (warps 4..7) works.
+// Head epilogues (plain Linear outputs, Npad <= 256 so the accumulator is chunk 0 only).
+// Two-hot heads with <= 128 bins and pi heads with <= 64 action dims are spread over all four column groups
+// (32 bins / 16 action dims per group); anything larger runs on column group 0 alone.
 __device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, const LayerDev& ly, const EpiArgs& ea) {
   const EpiThread et = epi_thread(c);
   const float inv_scale = ly.inv_scale;
@@ -898,14 +926,52 @@ __device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, cons
     for (int i = threadIdx.x - kEpiWarp0 * 32; i < P.B; i += kEpiThreads) c.vec[kFusedMaxN + i] = P.bins[i];
     epi_bar_sync();
   }
-  if (et.grp != 0) return;
+  const bool wide_twohot = (ea.kind == EPI_TWOHOT) && (P.B <= 32 * kEpiGroups);
+  const bool wide_pi = (ea.kind == EPI_PI) && (P.A <= 16 * kEpiGroups);
+  if (!wide_twohot && !wide_pi && et.grp != 0) return;
   {
     const long long tw = clock64();
     ptx::mbar_wait(&c.facc[0], c.fph0);
     c.pf2 += clock64() - tw;
   }
   ptx::tc_fence_after();
-  if (ea.kind == EPI_TWOHOT) {
+  if (wide_twohot) {
+    // two_hot_inv (math.py:74-83) with the 4 groups each owning 32 bins: max, then exp-sum and bin-weighted sum,
+    // exchanged through smem (part: [0,4) max, [4,8) sum; third array in the unused LN-beta vector slot).
+    const float* bins = c.vec + kFusedMaxN;
+    float* xch = c.vec + 2 * kFusedMaxN;                // [kEpiGroups][128]
+    const int B = P.B, c0 = 32 * et.grp;
+    uint32_t v[32];
+    ptx::tmem_ld_32x32(et.taddr + c0, v);
+    ptx::tmem_ld_wait();
+    float x[32];
+    float m = -CUDART_INF_F;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      x[i] = (c0 + i < B) ? fmaf(__uint_as_float(v[i]), inv_scale, sb[min(c0 + i, B - 1)]) : -CUDART_INF_F;
+      m = fmaxf(m, x[i]);
+    }
+    c.part[et.grp * kTileM + et.row] = m;
+    epi_bar_sync();
+#pragma unroll
+    for (int g = 0; g < kEpiGroups; ++g) m = fmaxf(m, c.part[g * kTileM + et.row]);
+    float ssum = 0.f, acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float e = (c0 + i < B) ? exp_fast(x[i] - m) : 0.f;     // exp(-inf - m) would be 0 as well; keep NaN rows NaN
+      ssum += e;
+      acc = fmaf(e, bins[min(c0 + i, B - 1)], acc);
+    }
+    c.part[(kEpiGroups + et.grp) * kTileM + et.row] = ssum;
+    xch[et.grp * kTileM + et.row] = acc;
+    epi_bar_sync();
+    if (et.grp == 0) {
+      float S = 0.f, Acc = 0.f;
+#pragma unroll
+      for (int g = 0; g < kEpiGroups; ++g) { S += c.part[(kEpiGroups + g) * kTileM + et.row]; Acc += xch[g * kTileM + et.row]; }
+      head_commit(P, c, ea, et.row, symexp_f(__fdiv_rn(Acc, S)));
+    }
+  } else if (ea.kind == EPI_TWOHOT) {
     const float* bins = c.vec + kFusedMaxN;
     const int B = P.B;
     float m = -CUDART_INF_F;
@@ -925,7 +991,7 @@ __device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, cons
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         if (c0 + i < B) {
-          const float e = __expf(fmaf(__uint_as_float(v[i]), inv_scale, sb[c0 + i]) - m);
+          const float e = exp_fast(fmaf(__uint_as_float(v[i]), inv_scale, sb[c0 + i]) - m);
           ssum += e;
           acc = fmaf(e, bins[c0 + i], acc);
         }
@@ -938,21 +1004,44 @@ __device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, cons
     __half* xhi = plane_ptr(P, c.slot, BUF_X, 0) + static_cast<size_t>(et.row) * P.KpadX + P.L + P.T;
     __half* xlo = plane_ptr(P, c.slot, BUF_X, 1) + static_cast<size_t>(et.row) * P.KpadX + P.L + P.T;
     const float* eps = ea.eps_base + (static_cast<size_t>(e) * ea.eps_rows + idx) * P.A;
-    for (int a0 = 0; a0 < P.A; a0 += 16) {
+    const int a_begin = wide_pi ? 16 * et.grp : 0;
+    const int a_end = wide_pi ? min(P.A, a_begin + 16) : P.A;
+    for (int a0 = a_begin; a0 < a_end; a0 += 16) {
       uint32_t vm[16], vs[16];
       ptx::tmem_ld_32x16(et.taddr + a0, vm);            // mean logits, columns [a0, a0+16)
       ptx::tmem_ld_32x16(et.taddr + P.Apad + a0, vs);   // log_std logits, columns [Apad+a0, Apad+a0+16) (aligned)
       ptx::tmem_ld_wait();
+      // 16 action columns = 32 B per plane: two 16-byte stores when the whole span lies inside the row
+      // (columns past A are zero-weight padding of X, so writing zeros there is harmless)
+      const bool vec = (((P.L + P.T) & 7) == 0) && (P.L + P.T + a0 + 16 <= P.KpadX);
+      uint32_t hw[8], lw[8];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int a = a0 + i;
-        if (a < P.A) {
-          const float mu = fmaf(__uint_as_float(vm[i]), inv_scale, sb[a]);
-          const float ls = fmaf(__uint_as_float(vs[i]), inv_scale, sb[P.Apad + a]);
-          const float act = pi_action(P, mu, ls, eps[a], task, a);
-          split_store(xhi + a, xlo + a, act);
-          if (ea.act_out && rm.env >= 0)
-            ea.act_out[((static_cast<size_t>(e) * P.H + ea.t_out) * P.P + idx) * P.A + a] = act;
+      for (int i = 0; i < 16; i += 2) {
+        float act2[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int a = a0 + i + u;
+          act2[u] = 0.f;
+          if (a < a_end) {
+            const float mu = fmaf(__uint_as_float(vm[i + u]), inv_scale, sb[a]);
+            const float ls = fmaf(__uint_as_float(vs[i + u]), inv_scale, sb[P.Apad + a]);
+            act2[u] = pi_action(P, mu, ls, eps[a], task, a);
+            if (!vec) split_store(xhi + a, xlo + a, act2[u]);
+            if (ea.act_out && rm.env >= 0)
+              ea.act_out[((static_cast<size_t>(e) * P.H + ea.t_out) * P.P + idx) * P.A + a] = act2[u];
+          }
+        }
+        __half h0, l0, h1, l1;
+        split_f(act2[0], h0, l0);
+        split_f(act2[1], h1, l1);
+        hw[i >> 1] = static_cast<uint32_t>(__half_as_ushort(h0)) | (static_cast<uint32_t>(__half_as_ushort(h1)) << 16);
+        lw[i >> 1] = static_cast<uint32_t>(__half_as_ushort(l0)) | (static_cast<uint32_t>(__half_as_ushort(l1)) << 16);
+      }
+      if (vec) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          __stcg(reinterpret_cast<uint4*>(xhi + a0) + i, make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]));
+          __stcg(reinterpret_cast<uint4*>(xlo + a0) + i, make_uint4(lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]));
         }
       }
     }
@@ -993,7 +1082,7 @@ __device__ __forceinline__ void run_layer(const PlanParams& P, Ctx& c, const Lay
     if (c.warp == 0) {
       if (c.lane == 0) tc_producer<true>(P, c, ly, srcbuf);
     } else if (c.warp == 1) {
-      if (c.lane == 0) tc_mma<true>(P, c, ly);
+      if (c.lane == 0 && (!c.cg2 || c.rank == 0)) tc_mma<true>(P, c, ly);
     } else if (c.warp >= kEpiWarp0) {
       if (is_ln) epi_ln_fused(P, c, ly, ea);
       else epi_head_fused(P, c, ly, ea);
@@ -1116,7 +1205,10 @@ __device__ __forceinline__ void refit_env(const PlanParams& P, Ctx& c, int e, in
 }
 
 // ------------------------------------------------------------------------------------ the kernel
-template <int ENGINE>
+// CG2: CTA pairs (cluster of 2) run the GEMMs as tcgen05 cta_group::2 MMAs (M = 256: 128 rows of each CTA's own
+// tile; each CTA streams only half of every weight tile).  Only MODE_ITER with an even number of tiles per
+// environment and every layer on the fused path is launched this way.
+template <int ENGINE, bool CG2 = false>
 __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant__ PlanParams P) {
   extern __shared__ uint8_t smem_raw[];
   Ctx c;
@@ -1141,6 +1233,8 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
     c.part = c.vec + 3 * kFusedMaxN;
   }
   c.slot = blockIdx.x;
+  c.cg2 = CG2 ? 1 : 0;
+  c.rank = CG2 ? static_cast<int>(ptx::cluster_ctarank()) : 0;
   c.warp = threadIdx.x >> 5;
   c.lane = threadIdx.x & 31;
   c.pa_it = c.pw_it = c.ma_it = c.mw_it = c.a_it = c.d_it = 0;
@@ -1164,7 +1258,8 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
       ptx::prefetch_tensormap(&P.tmX);
       ptx::prefetch_tensormap(&P.tmH);
     }
-    if (c.warp == 2) ptx::tmem_alloc(c.tmem_ptr, 512);
+    if (CG2) ptx::cluster_sync();          // the peer's barriers are initialised before anything can signal them
+    if (c.warp == 2) { if (CG2) ptx::tmem_alloc_2sm(c.tmem_ptr, 512); else ptx::tmem_alloc(c.tmem_ptr, 512); }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -1173,7 +1268,9 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
 
   const LayerDev* LY = P.layers;
 
-  for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+  // pair mode: the two CTAs of a pair take tiles (2p, 2p+1) and run the same number of loop trips
+  for (int tile = CG2 ? 2 * (static_cast<int>(blockIdx.x) >> 1) + c.rank : static_cast<int>(blockIdx.x); tile < P.ntiles;
+       tile += gridDim.x) {
     // ---------------- tile set-up: fill the input planes of X ----------------
     const long long t_setup = clock64();
     for (int r = threadIdx.x; r < kTileM; r += kThreads) { rowenv[r] = map_row(P, tile, r).env; c.G[r] = 0.f; c.q1[r] = 0.f; }
@@ -1352,7 +1449,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
           ea.kind = EPI_TWOHOT; ea.head = (mlp == 3) ? HEAD_Q1 : HEAD_Q2; ea.disc = dpow[P.H];
         }
       }
-      c.trace_step = (tile == blockIdx.x) ? sidx : (1 << 30);
+      c.trace_step = (tile == static_cast<int>(blockIdx.x)) ? sidx : (1 << 30);
       run_layer<ENGINE>(P, c, LY[li], src, ea);
     }
 
@@ -1390,7 +1487,8 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
   if (ENGINE == ENGINE_TC) {
     ptx::tc_fence_before();
     __syncthreads();
-    if (c.warp == 2) ptx::tmem_dealloc(c.tmem_base, 512);
+    if (CG2) ptx::cluster_sync();          // neither CTA may retire while the pair's MMAs / barriers are in use
+    if (c.warp == 2) { if (CG2) ptx::tmem_dealloc_2sm(c.tmem_base, 512); else ptx::tmem_dealloc(c.tmem_base, 512); }
   }
 }
 

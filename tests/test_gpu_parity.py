@@ -186,3 +186,25 @@ def test_estimate_value_matches_oracle(engine):
     got = pl.estimate_value(z.cuda().contiguous(), actions.cuda().contiguous(), torch.tensor(task, dtype=torch.int32).cuda(),
                             eps.cuda().contiguous(), qidx.to(torch.int32).cuda().contiguous()).cpu()
     assert torch.allclose(got, want, atol=5e-5, rtol=1e-5), (got - want).abs().max()
+
+
+def test_cta_pair_engine_is_bit_identical_to_single_cta():
+    """tcgen05x2 runs the CEM iterations on CTA pairs (cta_group::2, M = 256).  Each row still sees exactly the same
+    products in the same order, so the trajectory values must be BIT-identical to the single-CTA engine."""
+    from oracle.plan_oracle import draw_noise as oracle_noise
+    cfg = workload("c1", num_envs=3)                     # 4 tiles per environment -> pairs (0,1), (2,3)
+    sd = synth_state_dict(cfg, seed=7)
+    E = 3
+    g = torch.Generator().manual_seed(5)
+    obs = torch.randn(E, cfg.obs_shape["state"][0], generator=g).cuda()
+    prev = (0.3 * torch.randn(E, cfg.horizon, cfg.action_dim, generator=g)).cuda()
+    t0 = torch.tensor([1, 0, 0], dtype=torch.uint8).cuda()
+    noise = _to_gpu_noise(oracle_noise(cfg, 41, E), False)
+    out = {}
+    for engine in ("tcgen05", "tcgen05x2"):
+        pl = _planner(cfg, E, engine, sd)
+        a, m, tr = pl.plan(obs, None, t0, prev, noise, trace=True)
+        torch.cuda.synchronize()
+        out[engine] = (a.cpu(), m.cpu(), tr["values"].cpu(), tr["elite_idx"].cpu())
+    for x, y in zip(out["tcgen05"], out["tcgen05x2"]):
+        assert torch.equal(x, y)
