@@ -49,6 +49,7 @@ constexpr int kStageBytes = 2 * kAPlane + 2 * kWPlane;   // 96 KiB (the operand 
 constexpr int kASlotBytes = 2 * kAPlane;                  // 32 KiB
 constexpr int kWSlotBytes = 2 * kWPlane;                  // 64 KiB
 constexpr int kARing = 2, kWRing = 2;
+constexpr int kWRingPair = 4;                            // pair mode: 4 half-size W slots (hi 16 KiB | lo 16 KiB) in the same 128 KiB
 constexpr int kWRingOff = kARing * kASlotBytes;           // 64 KiB
 static_assert(kARing * kASlotBytes + kWRing * kWSlotBytes == kStages * kStageBytes, "operand smem layout");
 // Fused-epilogue staging for TMA stores: per column group 2 buffers x (hi 8 KiB | lo 8 KiB) = one 32-column block
@@ -215,6 +216,7 @@ struct Ctx {
   uint32_t tmem_base;
   int slot, warp, lane;
   int cg2, rank;             // CTA-pair mode (tcgen05 cta_group::2): pair rank 0 = leader issues the MMAs
+  uint32_t w_ring, w_stride, w_lo_off;   // W ring geometry: 2 x 64 KiB (lo plane at +32 KiB) or, in pair mode, 4 x 32 KiB (+16 KiB)
   // pipeline counters (each role keeps its own; persist across layers / tiles)
   uint32_t pa_it, pw_it, ma_it, mw_it, a_it, d_it;
   uint32_t fph0, fph1;      // fused path: phase parity of facc[0|1] (tracked identically by every thread)
@@ -324,18 +326,18 @@ __device__ __forceinline__ void prod_load_a(const PlanParams& P, Ctx& c, const C
 }
 __device__ __forceinline__ void prod_load_w(Ctx& c, const CUtensorMap* tmW, const LayerDev& ly, int kc, int nc) {
   const int ncols = min(kNch, ly.Npad - nc * kNch);   // 128 or 256
-  const uint32_t s = c.pw_it % kWRing, ph = (c.pw_it / kWRing) & 1;
+  const uint32_t s = c.pw_it % c.w_ring, ph = (c.pw_it / c.w_ring) & 1;
   const long long tw = clock64();
   ptx::mbar_wait(&c.w_empty[s], ph ^ 1);
   c.pf0 += clock64() - tw;
-  uint8_t* st = c.stage_base + kWRingOff + s * kWSlotBytes;
+  uint8_t* st = c.stage_base + kWRingOff + s * c.w_stride;
   if (c.cg2) {
     // each CTA streams HALF of the N-chunk's weight rows (one 128-row box per plane; for a 128-column chunk only
     // its first 64 rows are consumed): the pair MMA reads B rows [0, N/2) from the leader and [N/2, N) from the peer
     if (c.rank == 0) ptx::mbar_expect_tx(&c.w_full[s], 2 * (2 * 128 * 128));
     const int wr = ly.wrow + nc * kNch + c.rank * (ncols / 2);
     ptx::tma_load_2d_2sm(tmW, &c.w_full[s], st, kc * kKch, wr);
-    ptx::tma_load_2d_2sm(tmW, &c.w_full[s], st + kWPlane, kc * kKch, wr + ly.Npad);
+    ptx::tma_load_2d_2sm(tmW, &c.w_full[s], st + c.w_lo_off, kc * kKch, wr + ly.Npad);
   } else {
     ptx::mbar_expect_tx(&c.w_full[s], 2 * ncols * 128);
     for (int b = 0; b < ncols / 128; ++b) {
@@ -370,13 +372,13 @@ __device__ __forceinline__ void tc_producer(const PlanParams& P, Ctx& c, const L
 }
 
 // 12 MMAs of one (A K-chunk, W K-chunk x N-chunk) pair: A_lo*W_hi + A_hi*W_lo + A_hi*W_hi, 4 K-steps of 16.
-__device__ __forceinline__ void mma_stage(uint32_t d, uint32_t sa, uint32_t sw, uint32_t idesc, bool first, bool cg2) {
+__device__ __forceinline__ void mma_stage(uint32_t d, uint32_t sa, uint32_t sw, uint32_t w_lo_off, uint32_t idesc, bool first, bool cg2) {
 #pragma unroll
   for (int ks = 0; ks < kKch / 16; ++ks) {
     const uint64_t a_hi = ptx::make_sw128_kmajor_desc(sa + ks * 32);
     const uint64_t a_lo = ptx::make_sw128_kmajor_desc(sa + kAPlane + ks * 32);
     const uint64_t w_hi = ptx::make_sw128_kmajor_desc(sw + ks * 32);
-    const uint64_t w_lo = ptx::make_sw128_kmajor_desc(sw + kWPlane + ks * 32);
+    const uint64_t w_lo = ptx::make_sw128_kmajor_desc(sw + w_lo_off + ks * 32);
     if (cg2) {
       ptx::umma_f16_2sm(d, a_lo, w_hi, idesc, !(first && ks == 0));
       ptx::umma_f16_2sm(d, a_hi, w_lo, idesc, 1);
@@ -396,7 +398,7 @@ __device__ __forceinline__ uint32_t mma_wait_a(Ctx& c) {
   return s;
 }
 __device__ __forceinline__ uint32_t mma_wait_w(Ctx& c) {
-  const uint32_t s = c.mw_it % kWRing, ph = (c.mw_it / kWRing) & 1;
+  const uint32_t s = c.mw_it % c.w_ring, ph = (c.mw_it / c.w_ring) & 1;
   const long long tw = clock64();
   ptx::mbar_wait(&c.w_full[s], ph);
   c.pf0 += clock64() - tw;
@@ -416,7 +418,7 @@ __device__ __forceinline__ void tc_mma(const PlanParams& P, Ctx& c, const LayerD
         const uint32_t ws = mma_wait_w(c);
         ptx::tc_fence_after();
         const int ncols = min(kNch, ly.Npad - nc * kNch);
-        mma_stage(c.tmem_base + nc * kNch, sbase + as * kASlotBytes, sbase + kWRingOff + ws * kWSlotBytes,
+        mma_stage(c.tmem_base + nc * kNch, sbase + as * kASlotBytes, sbase + kWRingOff + ws * c.w_stride, c.w_lo_off,
                   ptx::make_idesc_f16(c.cg2 ? 2 * kTileM : kTileM, ncols), kc == 0, c.cg2 != 0);
         if (c.cg2) ptx::umma_commit_2sm(&c.w_empty[ws]);
         else ptx::umma_commit(&c.w_empty[ws]);     // frees the W slot when these MMAs retire
@@ -440,7 +442,7 @@ __device__ __forceinline__ void tc_mma(const PlanParams& P, Ctx& c, const LayerD
         const uint32_t as = mma_wait_a(c);
         const uint32_t ws = mma_wait_w(c);
         ptx::tc_fence_after();
-        mma_stage(c.tmem_base + slot * kNch, sbase + as * kASlotBytes, sbase + kWRingOff + ws * kWSlotBytes, idesc, kc == 0, false);
+        mma_stage(c.tmem_base + slot * kNch, sbase + as * kASlotBytes, sbase + kWRingOff + ws * c.w_stride, c.w_lo_off, idesc, kc == 0, false);
         ptx::umma_commit(&c.w_empty[ws]);
         ptx::umma_commit(&c.a_empty[as]);
         ++c.mw_it; ++c.ma_it;
@@ -706,6 +708,93 @@ __device__ __forceinline__ float mish_fast(float x) {
   return x * (n * rcp_ftz(n + 2.f));
 }
 
+// Pass 2 of the fused LayerNorm epilogue, specialised for the common case (whole 32-column blocks, planes out
+// through TMA stores, no fp32 side output): one block = two x16 TMEM loads, packed fp32x2 math, four 16-byte
+// swizzled smem stores per plane, then the block is handed to the TMA unit.
+template <int KIND>
+__device__ __forceinline__ void epi_pass2_fast(const PlanParams& P, Ctx& c, const EpiThread& et, const EpiArgs& ea, int cb,
+                                               int nvalid, float inv_scale, float rstd, float nmr) {
+  const float* sb = c.vec; const float* sg = c.vec + kFusedMaxN; const float* sbe = c.vec + 2 * kFusedMaxN;
+  uint8_t* stg = c.stage_base + kWRingOff + et.grp * (2 * kStgBuf);
+  const bool leader = (et.q == 0) && (c.lane == 0);
+  const CUtensorMap* tmD = (ea.dstbuf == BUF_X) ? &P.tmXs : &P.tmHs;
+  const uint32_t swz = static_cast<uint32_t>((et.row >> 1) & 3);
+  const int row_hi = plane_row0(P, c.slot, ea.dstbuf, 0), row_lo = plane_row0(P, c.slot, ea.dstbuf, 1);
+  const float2 inv2 = f2s(inv_scale), rstd2 = f2s(rstd), nmr2 = f2s(nmr);
+  const int nblk = nvalid >> 5;
+  for (int blk = 0; blk < nblk; ++blk) {
+    const int c0 = cb + (blk << 5);
+    uint8_t* buf = stg + (blk & 1) * kStgBuf;
+    const uint32_t rowaddr = ptx::smem_u32(buf) + static_cast<uint32_t>(et.row) * 64u;
+    if (blk >= 2) {                                               // buffer reuse: its previous store must have read it
+      if (leader) ptx::bulk_wait_read<1>();
+      group_bar_sync(et.grp);
+    }
+#pragma unroll
+    for (int sub = 0; sub < 32; sub += 16) {
+      uint32_t v[16];
+      ptx::tmem_ld_32x16(et.taddr + c0 + sub, v);
+      ptx::tmem_ld_wait();
+      uint32_t hw[8], lw[8];
+#pragma unroll
+      for (int i4 = 0; i4 < 16; i4 += 4) {
+        const float4 b4 = lds128(sb + c0 + sub + i4);
+        const float4 g4 = lds128(sg + c0 + sub + i4);
+        const float4 e4 = lds128(sbe + c0 + sub + i4);
+        float2 t0 = __ffma2_rn(__ffma2_rn(__ffma2_rn(f2(__uint_as_float(v[i4]), __uint_as_float(v[i4 + 1])), inv2, f2(b4.x, b4.y)),
+                                          rstd2, nmr2), f2(g4.x, g4.y), f2(e4.x, e4.y));
+        float2 t1 = __ffma2_rn(__ffma2_rn(__ffma2_rn(f2(__uint_as_float(v[i4 + 2]), __uint_as_float(v[i4 + 3])), inv2, f2(b4.z, b4.w)),
+                                          rstd2, nmr2), f2(g4.z, g4.w), f2(e4.z, e4.w));
+        if (KIND == EPI_LN_MISH) { t0 = mish_fast2(t0); t1 = mish_fast2(t1); }
+        v[i4] = __float_as_uint(t0.x); v[i4 + 1] = __float_as_uint(t0.y);
+        v[i4 + 2] = __float_as_uint(t1.x); v[i4 + 3] = __float_as_uint(t1.y);
+      }
+      if (KIND == EPI_LN_SIMNORM) {
+        // SimNorm: softmax over groups of 8 consecutive columns (layers.py:84-88)
+#pragma unroll
+        for (int g0 = 0; g0 < 16; g0 += 8) {
+          float y[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(v[g0 + i]);
+          float m = y[0];
+#pragma unroll
+          for (int i = 1; i < 8; ++i) m = fmaxf(m, y[i]);
+          float t = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { y[i] = exp_fast(y[i] - m); t += y[i]; }
+          const float rt = rcp_ftz(t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[g0 + i] = __float_as_uint(y[i] * rt);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float a0 = __uint_as_float(v[2 * i]), a1 = __uint_as_float(v[2 * i + 1]);
+        const __half2 h2 = __floats2half2_rn(a0, a1);
+        const float2 hf = __half22float2(h2);
+        const float2 df = __fadd2_rn(f2(a0, a1), f2(-hf.x, -hf.y));
+        const __half2 l2 = __floats2half2_rn(df.x, df.y);
+        hw[i] = *reinterpret_cast<const uint32_t*>(&h2);
+        lw[i] = *reinterpret_cast<const uint32_t*>(&l2);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const uint32_t off = ((static_cast<uint32_t>((sub >> 3) + i) ^ swz) << 4);
+        ptx::st_shared_v4(rowaddr + off, hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
+        ptx::st_shared_v4(rowaddr + kStgPlane + off, lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]);
+      }
+    }
+    ptx::fence_proxy_async_smem();
+    group_bar_sync(et.grp);
+    if (leader) {
+      ptx::tma_store_2d(tmD, buf, ea.dst_col0 + c0, row_hi);
+      ptx::tma_store_2d(tmD, buf + kStgPlane, ea.dst_col0 + c0, row_lo);
+      ptx::bulk_commit();
+    }
+  }
+  if (leader) ptx::bulk_wait<0>();                               // stores performed before the layer is published
+}
+
 // bias + LayerNorm + (Mish | SimNorm); planes and/or fp32 rows out.  16 epilogue warps: 4 lane quarters x 4
 // column groups; a group owns whole 64-column blocks (the TMA-store granule).
 // Pass 1 reads the accumulator row once for shifted first/second moments (groups merged with Chan's
@@ -733,7 +822,29 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
   // ---- pass 1: shifted moments of this group's columns
   float x0 = 0.f, s = 0.f, q = 0.f;
   float2 s2 = f2s(0.f), q2 = f2s(0.f);
-  for (int c0 = cb; c0 < cb + nvalid; c0 += 16) {
+  const bool p1_fast = (nvalid > 0) && ((nvalid & 31) == 0);
+  if (p1_fast) {
+    // whole 32-column chunks: x32 loads, four independent packed accumulator chains
+    float2 sa = f2s(0.f), sbb = f2s(0.f), qa = f2s(0.f), qb = f2s(0.f);
+    const float2 inv2 = f2s(inv_scale);
+    for (int c0 = cb; c0 < cb + nvalid; c0 += 32) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(et.taddr + c0, v);
+      ptx::tmem_ld_wait();
+      if (c0 == cb) x0 = fmaf(__uint_as_float(v[0]), inv_scale, sb[c0]);
+      const float2 nx0 = f2s(-x0);
+#pragma unroll
+      for (int i4 = 0; i4 < 32; i4 += 4) {
+        const float4 b4 = lds128(sb + c0 + i4);
+        const float2 xa = __ffma2_rn(f2(__uint_as_float(v[i4]), __uint_as_float(v[i4 + 1])), inv2, __fadd2_rn(f2(b4.x, b4.y), nx0));
+        const float2 xb = __ffma2_rn(f2(__uint_as_float(v[i4 + 2]), __uint_as_float(v[i4 + 3])), inv2, __fadd2_rn(f2(b4.z, b4.w), nx0));
+        sa = __fadd2_rn(sa, xa); qa = __ffma2_rn(xa, xa, qa);
+        sbb = __fadd2_rn(sbb, xb); qb = __ffma2_rn(xb, xb, qb);
+      }
+    }
+    s2 = __fadd2_rn(sa, sbb); q2 = __fadd2_rn(qa, qb);
+  }
+  for (int c0 = cb; c0 < cb + (p1_fast ? 0 : nvalid); c0 += 16) {
     uint32_t v[16];
     ptx::tmem_ld_32x16(et.taddr + c0, v);
     ptx::tmem_ld_wait();
@@ -788,7 +899,12 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
     rstd = rsqrtf(m2 / static_cast<float>(N) + 1e-5f);            // nn.LayerNorm eps (layers.py:101), biased variance
   }
   const float nmr = -mean * rstd;
-  // ---- pass 2: normalise, activate, emit
+  if (ea.dstbuf >= 0 && !ea.out_f32 && (N % 32 == 0) && (ea.dst_col0 % 32 == 0)) {
+    if (ea.kind == EPI_LN_MISH) epi_pass2_fast<EPI_LN_MISH>(P, c, et, ea, cb, nvalid, inv_scale, rstd, nmr);
+    else epi_pass2_fast<EPI_LN_SIMNORM>(P, c, et, ea, cb, nvalid, inv_scale, rstd, nmr);
+    return;
+  }
+  // ---- pass 2 (general path): normalise, activate, emit
   __half* dhi = ea.dstbuf >= 0 ? plane_ptr(P, c.slot, ea.dstbuf, 0) : nullptr;
   __half* dlo = ea.dstbuf >= 0 ? plane_ptr(P, c.slot, ea.dstbuf, 1) : nullptr;
   const int pitch = ea.dstbuf >= 0 ? plane_pitch(P, ea.dstbuf) : 0;
@@ -1219,14 +1335,14 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
     c.a_full = reinterpret_cast<uint64_t*>(ctrl);
     c.a_empty = c.a_full + kARing;
     c.w_full = c.a_empty + kARing;
-    c.w_empty = c.w_full + kWRing;
-    c.acc_full = c.w_empty + kWRing;
+    c.w_empty = c.w_full + kWRingPair;
+    c.acc_full = c.w_empty + kWRingPair;
     c.acc_empty = c.acc_full + 2;
     c.facc = c.acc_empty + 2;
     c.tmem_ptr = reinterpret_cast<uint32_t*>(c.facc + 2);
     c.flags = reinterpret_cast<int*>(c.tmem_ptr + 1);          // [8]
-    c.G = reinterpret_cast<float*>(ctrl + 128);                 // [128]
-    c.q1 = c.G + kTileM;                                        // [128]  (ends at ctrl + 1152 <= kSmemCtrl)
+    c.G = reinterpret_cast<float*>(ctrl + 256);                 // [128]  (18 mbarriers + tmem ptr + flags live below 256)
+    c.q1 = c.G + kTileM;                                        // [128]  (ends at ctrl + 1280 <= kSmemCtrl)
     c.rowbuf = reinterpret_cast<float*>(ctrl + kSmemCtrl);
     c.rowenv = reinterpret_cast<int*>(ctrl + kSmemCtrl + kSmemRowBuf);
     c.vec = reinterpret_cast<float*>(ctrl + kSmemCtrl + kSmemRowBuf + kSmemRowEnv);
@@ -1234,6 +1350,9 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
   }
   c.slot = blockIdx.x;
   c.cg2 = CG2 ? 1 : 0;
+  c.w_ring = CG2 ? kWRingPair : kWRing;
+  c.w_stride = CG2 ? kWSlotBytes / 2 : kWSlotBytes;
+  c.w_lo_off = CG2 ? kAPlane : kWPlane;
   c.rank = CG2 ? static_cast<int>(ptx::cluster_ctarank()) : 0;
   c.warp = threadIdx.x >> 5;
   c.lane = threadIdx.x & 31;
@@ -1248,7 +1367,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
   if (ENGINE == ENGINE_TC) {
     if (threadIdx.x == 0) {
       for (int s = 0; s < kARing; ++s) { ptx::mbar_init(&c.a_full[s], 1); ptx::mbar_init(&c.a_empty[s], 1); }
-      for (int s = 0; s < kWRing; ++s) { ptx::mbar_init(&c.w_full[s], 1); ptx::mbar_init(&c.w_empty[s], 1); }
+      for (int s = 0; s < kWRingPair; ++s) { ptx::mbar_init(&c.w_full[s], 1); ptx::mbar_init(&c.w_empty[s], 1); }
       for (int s = 0; s < 2; ++s) {
         ptx::mbar_init(&c.acc_full[s], 1);
         ptx::mbar_init(&c.acc_empty[s], 4 * 32);

@@ -98,7 +98,7 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 class Planner:
     """Owns one tdmpc2_planner handle plus its packed weights and workspace."""
 
-    def __init__(self, cfg: Config, num_envs: int, device, engine: str = "tcgen05"):
+    def __init__(self, cfg: Config, num_envs: int, device, engine: str = "tcgen05x2"):
         self.lib = _cabi.load()                         # raises if the .so is missing
         self.cfg, self.E = cfg, int(num_envs)
         self.device = torch.device(device)
