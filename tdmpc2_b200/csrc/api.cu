@@ -253,7 +253,7 @@ extern "C" int tdmpc2_planner_create(const tdmpc2_dims* dims, tdmpc2_planner** o
   const size_t E = d.num_envs, H = d.horizon, N = d.num_samples, K = d.num_elites, P = d.num_pi_trajs;
   off = 0;
   p->off_X = off; off = align_up(off + static_cast<size_t>(p->nslots) * 2 * kTileM * p->KpadX * 2, 1024);
-  p->off_H = off; off = align_up(off + static_cast<size_t>(p->nslots) * 4 * kTileM * p->KpadH * 2, 1024);
+  p->off_H = off; off = align_up(off + static_cast<size_t>(p->nslots) * 2 * kTileM * p->KpadH * 2, 1024);
   p->off_raw = off; off = align_up(off + static_cast<size_t>(p->nslots) * kTileM * p->NpadMax * 4, 1024);
   p->off_z = off; off = align_up(off + E * L * 4, 256);
   p->off_pia = off; off = align_up(off + E * H * std::max<size_t>(P, 1) * A * 4, 256);
@@ -330,9 +330,9 @@ extern "C" int tdmpc2_planner_bind(tdmpc2_planner* p, void* packed, void* worksp
   memset(&B, 0, sizeof(B));
   int rc;
   if ((rc = make_map(enc, &B.tmX, p->ws + p->off_X, p->KpadX, static_cast<uint64_t>(p->nslots) * 2 * kTileM))) return rc;
-  if ((rc = make_map(enc, &B.tmH, p->ws + p->off_H, p->KpadH, static_cast<uint64_t>(p->nslots) * 4 * kTileM))) return rc;
+  if ((rc = make_map(enc, &B.tmH, p->ws + p->off_H, p->KpadH, static_cast<uint64_t>(p->nslots) * 2 * kTileM))) return rc;
   if ((rc = make_map(enc, &B.tmXs, p->ws + p->off_X, p->KpadX, static_cast<uint64_t>(p->nslots) * 2 * kTileM, 32))) return rc;
-  if ((rc = make_map(enc, &B.tmHs, p->ws + p->off_H, p->KpadH, static_cast<uint64_t>(p->nslots) * 4 * kTileM, 32))) return rc;
+  if ((rc = make_map(enc, &B.tmHs, p->ws + p->off_H, p->KpadH, static_cast<uint64_t>(p->nslots) * 2 * kTileM, 32))) return rc;
   for (int m = 0; m < p->nmaps; ++m)
     if ((rc = make_map(enc, &B.tmW[m], p->packed + p->map_off[m], p->map_kpad[m], p->map_rows[m]))) return rc;
 

@@ -74,7 +74,9 @@ constexpr int kSmemBytes = kStages * kStageBytes + kSmemCtrl + kSmemRowBuf + kSm
 
 enum Mode { MODE_ENCODE = 0, MODE_PRIOR = 1, MODE_ITER = 2, MODE_VALUE = 3, MODE_LAYER = 4 };
 enum Engine { ENGINE_TC = 0, ENGINE_SIMT = 1 };
-enum Buf { BUF_X = 0, BUF_H1 = 1, BUF_H2 = 2 };
+// X = [z | emb | a] input planes; H = hidden planes.  ONE hidden buffer is enough: a layer's epilogue only runs after
+// every MMA of its GEMM has consumed the A operand, so layer 1 overwrites its own input in place.
+enum Buf { BUF_X = 0, BUF_H1 = 1 };
 enum Epi { EPI_LN_MISH = 0, EPI_LN_SIMNORM = 1, EPI_TWOHOT = 2, EPI_PI = 3, EPI_RAW = 4 };
 enum HeadKind { HEAD_REWARD = 0, HEAD_Q1 = 1, HEAD_Q2 = 2 };
 
@@ -93,7 +95,7 @@ struct LayerDev {
 
 struct PlanParams {
   CUtensorMap tmX;                 // [slots*2*128, KpadX] fp16, box 64 x 128
-  CUtensorMap tmH;                 // [slots*4*128, KpadH]
+  CUtensorMap tmH;                 // [slots*2*128, KpadH]
   CUtensorMap tmXs, tmHs;          // same tensors, box 32 x 128, 64-byte swizzle: the epilogue's TMA stores
   CUtensorMap tmW[kMaxWMaps];      // weights, one map per Kpad class, box 64 x 128
   const LayerDev* layers;
@@ -226,12 +228,12 @@ struct Ctx {
 
 __device__ __forceinline__ __half* plane_ptr(const PlanParams& P, int slot, int buf, int plane) {
   if (buf == BUF_X) return P.X + (static_cast<size_t>(slot) * 2 + plane) * kTileM * P.KpadX;
-  return P.Hb + ((static_cast<size_t>(slot) * 2 + (buf - BUF_H1)) * 2 + plane) * kTileM * P.KpadH;
+  return P.Hb + (static_cast<size_t>(slot) * 2 + plane) * kTileM * P.KpadH;
 }
 __device__ __forceinline__ int plane_pitch(const PlanParams& P, int buf) { return buf == BUF_X ? P.KpadX : P.KpadH; }
 __device__ __forceinline__ int plane_row0(const PlanParams& P, int slot, int buf, int plane) {  // TMA row coord
   if (buf == BUF_X) return (slot * 2 + plane) * kTileM;
-  return ((slot * 2 + (buf - BUF_H1)) * 2 + plane) * kTileM;
+  return (slot * 2 + plane) * kTileM;
 }
 __device__ __forceinline__ float* raw_ptr(const PlanParams& P, int slot) {
   return P.raw + static_cast<size_t>(slot) * kTileM * P.NpadMax;
@@ -1490,9 +1492,9 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
         ea.out_f32 = P.dbg_y; ea.out_pitch = LY[li].N; ea.rowmap = rowenv;
       } else if (P.mode == MODE_ENCODE) {
         li = P.li_enc + sidx;
-        src = sidx == 0 ? BUF_X : ((sidx & 1) ? BUF_H1 : BUF_H2);
+        src = sidx == 0 ? BUF_X : BUF_H1;
         if (sidx == P.num_enc - 1) { ea.kind = EPI_LN_SIMNORM; ea.out_f32 = P.z; ea.out_pitch = P.L; ea.rowmap = rowenv; }
-        else { ea.kind = EPI_LN_MISH; ea.dstbuf = (sidx & 1) ? BUF_H2 : BUF_H1; }
+        else { ea.kind = EPI_LN_MISH; ea.dstbuf = BUF_H1; }
       } else {
         // which MLP, which of its 3 layers
         int mlp, l, t = 0;       // mlp: 0 reward, 1 dynamics, 2 pi, 3 q_a, 4 q_b
@@ -1547,11 +1549,11 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
           const int u = sidx - 6 * P.H;
           mlp = 2 + u / 3; l = u % 3;
         }
-        src = l == 0 ? BUF_X : (l == 1 ? BUF_H1 : BUF_H2);
+        src = l == 0 ? BUF_X : BUF_H1;
         const int base = mlp == 0 ? P.li_rew : mlp == 1 ? P.li_dyn : mlp == 2 ? P.li_pi : P.li_q + 3 * qi[mlp - 3];
         li = base + l;
         if (l < 2) {
-          ea.kind = EPI_LN_MISH; ea.dstbuf = l == 0 ? BUF_H1 : BUF_H2;
+          ea.kind = EPI_LN_MISH; ea.dstbuf = BUF_H1;
         } else if (mlp == 0) {                 // reward (world_model.py:123-130) + two_hot_inv
           ea.kind = EPI_TWOHOT; ea.head = HEAD_REWARD; ea.disc = dpow[t];
         } else if (mlp == 1) {                 // z <- next(z, a)  (world_model.py:114-121)
