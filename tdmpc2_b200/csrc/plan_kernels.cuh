@@ -14,18 +14,23 @@
 // Every dense layer is `acc = A[128, Kpad] * W[Npad, Kpad]^T` with both operands
 // stored as two fp16 planes (hi, lo; x ~= hi + lo to ~22 bits).  The tcgen05
 // engine accumulates A_lo*W_hi + A_hi*W_lo + A_hi*W_hi in fp32 in TMEM
-// (kind::f16, M=128, N<=256, K=16), operands staged by TMA (128-byte swizzle)
-// through a 2-stage mbarrier pipeline: warp 0 = TMA producer, warp 1 = MMA
-// issuer, warps 4-11 = epilogue.
+// (kind::f16, K=16), operands staged by TMA (128-byte swizzle) through two
+// mbarrier rings (A: 2 x 32 KiB, W: 2 x 64 KiB | 4 x 32 KiB) so that an A K-chunk
+// is streamed once per layer: warp 0 = TMA producer, warp 1 = MMA issuer,
+// warps 4-19 = epilogue (4 TMEM lane quarters x 4 column groups).
 //
+//   * PAIR mode (CEM iterations): clusters of two CTAs issue cta_group::2 MMAs with
+//     M = 256 (each CTA's own 128-row tile); each CTA streams half of every W tile.
 //   * Layers with Npad <= 512 (the whole accumulator fits TMEM) use the FUSED
 //     epilogue: one thread per row reads its accumulator row straight from TMEM
 //     (tcgen05.ld), applies bias + LayerNorm + Mish / SimNorm / two-hot-inverse /
-//     tanh-Gaussian sampling, and writes the next layer's fp16 planes.
+//     tanh-Gaussian sampling in packed fp32x2 math, and emits the next layer's fp16
+//     planes as swizzled smem tiles that leave through TMA stores.
 //   * Wider layers (48M / 317M presets) drain N-chunks of 256 columns to an fp32
 //     scratch row buffer and run the same math warp-per-row afterwards.
 //
-// Activations live in a per-CTA scratch slot (global memory, L2-resident).
+// Activations live in a per-CTA scratch slot (global memory, L2-resident: X planes +
+// one in-place hidden buffer, 0.56 MB per slot for the 5M model).
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
