@@ -51,9 +51,13 @@ typedef enum tdmpc2_status {
 typedef enum tdmpc2_engine {
   TDMPC2_ENGINE_TCGEN05 = 0,   /* TMA + tcgen05.mma (3x fp16-split, fp32 TMEM accumulate): the product path */
   TDMPC2_ENGINE_SIMT = 1,      /* CUDA-core fp32 FFMA over the same packed operands: bring-up / diagnostics  */
-  TDMPC2_ENGINE_TCGEN05_2SM = 2 /* as 0, but CEM iterations run on CTA pairs (tcgen05 cta_group::2, M = 256):
+  TDMPC2_ENGINE_TCGEN05_2SM = 2, /* as 0, but CEM iterations run on CTA pairs (tcgen05 cta_group::2, M = 256):
                                   each CTA streams half of every weight tile.  Falls back to 0 when a model has
                                   layers wider than TMEM or an odd number of 128-row tiles per environment */
+  TDMPC2_ENGINE_TCGEN05_PP = 3 /* as 2, but every CTA splits its tile into two 64-row halves (cta_group::2, M = 128)
+                                  whose accumulators sit side by side in TMEM: the GEMM of one half overlaps the
+                                  LayerNorm / head epilogue of the other.  Trunk layers must be 256 or 512 wide and
+                                  heads at most 128 (the 5M preset); anything else runs as engine 2 */
 } tdmpc2_engine;
 
 /* Planner + model dimensions.  Mirrors the keys the reference reads from cfg:

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtdmpc2_b200.so")
 STAMP = LIB + ".stamp"
-SOURCES = ["api.cu", "plan_kernels.cuh", "ptx.cuh", os.path.join("..", "..", "include", "tdmpc2_b200.h")]
+SOURCES = ["api.cu", "plan_kernels.cuh", "plan_pp.cuh", "ptx.cuh", os.path.join("..", "..", "include", "tdmpc2_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 

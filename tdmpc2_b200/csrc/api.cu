@@ -14,6 +14,7 @@
 
 #include "../../include/tdmpc2_b200.h"
 #include "plan_kernels.cuh"
+#include "plan_pp.cuh"
 
 using namespace tdmpc2;
 
@@ -126,7 +127,7 @@ struct tdmpc2_planner {
   uint8_t* ws = nullptr;
   PlanParams base;
   int engine = TDMPC2_ENGINE_TCGEN05;
-  bool bound = false, weights_ok = false, smem_attr_set[2] = {false, false}, smem_attr_pair = false, all_fused = true;
+  bool bound = false, weights_ok = false, smem_attr_set[2] = {false, false}, smem_attr_pair = false, smem_attr_pp = false, all_fused = true;
   int64_t launches = 0;
   const int32_t* cur_task = nullptr;
   long long* prof = nullptr;
@@ -288,7 +289,8 @@ extern "C" int tdmpc2_planner_set_profile(tdmpc2_planner* p, long long* device_b
   return 0;
 }
 extern "C" int tdmpc2_planner_set_engine(tdmpc2_planner* p, int engine) {
-  if (!p || (engine != TDMPC2_ENGINE_TCGEN05 && engine != TDMPC2_ENGINE_SIMT && engine != TDMPC2_ENGINE_TCGEN05_2SM))
+  if (!p || (engine != TDMPC2_ENGINE_TCGEN05 && engine != TDMPC2_ENGINE_SIMT && engine != TDMPC2_ENGINE_TCGEN05_2SM &&
+             engine != TDMPC2_ENGINE_TCGEN05_PP))
     return fail(TDMPC2_ERR_INVALID, "bad engine");
   p->engine = engine;
   return 0;
@@ -298,10 +300,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_map(EncodeTiledFn enc, CUtensorMap* m, void* base, uint64_t kpad, uint64_t rows, int box_cols = kKch) {
+static int make_map(EncodeTiledFn enc, CUtensorMap* m, void* base, uint64_t kpad, uint64_t rows, int box_cols = kKch,
+                    int box_rows = 128) {
   cuuint64_t dims[2] = {kpad, rows};
   cuuint64_t strides[1] = {kpad * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), 128};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   // 64-column boxes (operand loads): 128-byte rows, 128B swizzle; 32-column boxes (epilogue stores): 64B swizzle
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -333,6 +336,13 @@ extern "C" int tdmpc2_planner_bind(tdmpc2_planner* p, void* packed, void* worksp
   if ((rc = make_map(enc, &B.tmH, p->ws + p->off_H, p->KpadH, static_cast<uint64_t>(p->nslots) * 2 * kTileM))) return rc;
   if ((rc = make_map(enc, &B.tmXs, p->ws + p->off_X, p->KpadX, static_cast<uint64_t>(p->nslots) * 2 * kTileM, 32))) return rc;
   if ((rc = make_map(enc, &B.tmHs, p->ws + p->off_H, p->KpadH, static_cast<uint64_t>(p->nslots) * 2 * kTileM, 32))) return rc;
+  {
+    const uint64_t rows = static_cast<uint64_t>(p->nslots) * 2 * kTileM;
+    if ((rc = make_map(enc, &B.tmX64, p->ws + p->off_X, p->KpadX, rows, kKch, kPPHalf))) return rc;
+    if ((rc = make_map(enc, &B.tmH64, p->ws + p->off_H, p->KpadH, rows, kKch, kPPHalf))) return rc;
+    if ((rc = make_map(enc, &B.tmXs64, p->ws + p->off_X, p->KpadX, rows, 32, kPPHalf))) return rc;
+    if ((rc = make_map(enc, &B.tmHs64, p->ws + p->off_H, p->KpadH, rows, 32, kPPHalf))) return rc;
+  }
   for (int m = 0; m < p->nmaps; ++m)
     if ((rc = make_map(enc, &B.tmW[m], p->packed + p->map_off[m], p->map_kpad[m], p->map_rows[m]))) return rc;
 
@@ -439,6 +449,20 @@ extern "C" int tdmpc2_pack_weights(tdmpc2_planner* p, const tdmpc2_weights* w, v
 }
 
 // ------------------------------------------------------------------------------------ launches
+// plan_pp.cuh covers models whose trunk layers are 256 / 512 wide and whose heads fit one 128-column chunk
+static bool pp_eligible(const tdmpc2_planner* p) {
+  const tdmpc2_dims& d = p->d;
+  if (!p->all_fused || d.action_dim > 64 || d.num_bins > 128 || d.num_bins < 1 || 6 * d.horizon + 9 > kPPMaxSteps) return false;
+  if (d.num_samples % kTileM != 0 || (d.latent_dim + d.task_dim) % 8 != 0 || (d.latent_dim + d.task_dim) / 8 > kEpiThreads) return false;
+  if (d.simnorm_dim != 8) return false;
+  for (size_t i = static_cast<size_t>(p->li_dyn); i < p->layers.size(); ++i) {
+    const LayerHost& l = p->layers[i];
+    if (l.has_ln) { if (l.N != l.Npad || (l.Npad != 256 && l.Npad != 512)) return false; }
+    else if (l.Npad != 128) return false;
+  }
+  return true;
+}
+
 static int launch_plan(tdmpc2_planner* p, const PlanParams& prm, int ntiles, cudaStream_t st) {
   const int eng = p->engine == TDMPC2_ENGINE_SIMT ? 1 : 0;
   if (!p->smem_attr_set[eng]) {
@@ -450,7 +474,27 @@ static int launch_plan(tdmpc2_planner* p, const PlanParams& prm, int ntiles, cud
   PlanParams prm2 = prm;
   prm2.prof = p->prof;
   // CTA-pair (cta_group::2) launch: CEM iterations only, whole pairs of tiles of one environment, fused layers only
-  bool pair = (p->engine == TDMPC2_ENGINE_TCGEN05_2SM) && prm.mode == MODE_ITER && (p->tiles_per_env % 2 == 0) &&
+  const bool pair_engine = (p->engine == TDMPC2_ENGINE_TCGEN05_2SM || p->engine == TDMPC2_ENGINE_TCGEN05_PP);
+  if (p->engine == TDMPC2_ENGINE_TCGEN05_PP && prm.mode == MODE_ITER && (p->tiles_per_env % 2 == 0) && (ntiles % 2 == 0) &&
+      pp_eligible(p)) {
+    // ping-pong kernel (plan_pp.cuh): GEMM of one 64-row half overlaps the epilogue of the other
+    if (!p->smem_attr_pp) {
+      CUDA_TRY(cudaFuncSetAttribute(plan_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPPSmemBytes));
+      p->smem_attr_pp = true;
+    }
+    grid &= ~1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kPPSmemBytes; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, plan_pp_kernel, prm2));
+    CUDA_TRY(cudaGetLastError());
+    p->launches += 1;
+    return 0;
+  }
+  bool pair = pair_engine && prm.mode == MODE_ITER && (p->tiles_per_env % 2 == 0) &&
               (ntiles % 2 == 0) && p->all_fused;
   if (pair) {
     if (!p->smem_attr_pair) {

@@ -102,6 +102,8 @@ struct PlanParams {
   CUtensorMap tmX;                 // [slots*2*128, KpadX] fp16, box 64 x 128
   CUtensorMap tmH;                 // [slots*2*128, KpadH]
   CUtensorMap tmXs, tmHs;          // same tensors, box 32 x 128, 64-byte swizzle: the epilogue's TMA stores
+  CUtensorMap tmX64, tmH64;        // 64-row boxes (ping-pong engine, plan_pp.cuh): loads 64 x 64, 128-byte swizzle
+  CUtensorMap tmXs64, tmHs64;      //                                             : stores 32 x 64, 64-byte swizzle
   CUtensorMap tmW[kMaxWMaps];      // weights, one map per Kpad class, box 64 x 128
   const LayerDev* layers;
   int E, N, P, Ppad, K, H, obs_dim, A, Apad, L, M, T, B, num_q, simnorm, num_enc;   // Apad = pad32(A): the pi head's
@@ -1232,12 +1234,17 @@ __device__ __forceinline__ void run_layer(const PlanParams& P, Ctx& c, const Lay
 
 // ------------------------------------------------------------------------------------ top-k + MPPI refit
 // Runs in the LAST CTA to finish a tile of environment e (tdmpc2.py:184-197).
-__device__ __forceinline__ void refit_env(const PlanParams& P, Ctx& c, int e, int task) {
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(c.stage_base);
+// Thread groups that can run the CTA-wide glue phases: the whole CTA (bar 0) or only the 16 epilogue warps (bar 1).
+struct GroupAll { static constexpr int N = kThreads; __device__ static int tid() { return threadIdx.x; } __device__ static void sync() { __syncthreads(); } };
+struct GroupEpi { static constexpr int N = kEpiThreads; __device__ static int tid() { return threadIdx.x - kEpiWarp0 * 32; } __device__ static void sync() { epi_bar_sync(); } };
+
+template <class G>
+__device__ __forceinline__ void refit_env(const PlanParams& P, uint8_t* scratch, size_t scratch_bytes, int e, int task) {
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(scratch);
   int nsort = 1;
   while (nsort < P.N) nsort <<= 1;
   const float* vals = P.values + static_cast<size_t>(e) * P.N;
-  for (int i = threadIdx.x; i < nsort; i += kThreads) {
+  for (int i = G::tid(); i < nsort; i += G::N) {
     unsigned long long k = 0ull;   // sentinel: sorts last
     if (i < P.N) {
       const float v = __ldcg(vals + i);
@@ -1248,11 +1255,11 @@ __device__ __forceinline__ void refit_env(const PlanParams& P, Ctx& c, int e, in
     }
     keys[i] = k;
   }
-  __syncthreads();
+  G::sync();
   // bitonic sort, descending (value desc, index asc on ties)
   for (int k2 = 2; k2 <= nsort; k2 <<= 1) {
     for (int j = k2 >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < nsort; i += kThreads) {
+      for (int i = G::tid(); i < nsort; i += G::N) {
         const int ixj = i ^ j;
         if (ixj > i) {
           const unsigned long long a = keys[i], b = keys[ixj];
@@ -1260,50 +1267,50 @@ __device__ __forceinline__ void refit_env(const PlanParams& P, Ctx& c, int e, in
           if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[ixj] = a; }
         }
       }
-      __syncthreads();
+      G::sync();
     }
   }
   float* escore = reinterpret_cast<float*>(keys + nsort);     // [K]
   int* eidx = reinterpret_cast<int*>(escore + P.K);           // [K]
   float* red = reinterpret_cast<float*>(eidx + P.K);          // [2]
   const float vmax = __ldcg(vals + (0xFFFFFFFFu - static_cast<unsigned>(keys[0] & 0xFFFFFFFFull)));
-  for (int k = threadIdx.x; k < P.K; k += kThreads) {
+  for (int k = G::tid(); k < P.K; k += G::N) {
     const int idx = static_cast<int>(0xFFFFFFFFu - static_cast<unsigned>(keys[k] & 0xFFFFFFFFull));
     eidx[k] = idx;
     escore[k] = expf(__fmul_rn(P.temperature, __ldcg(vals + idx) - vmax));   // exp(T * (v - max))
     P.elite_idx32[static_cast<size_t>(e) * P.K + k] = idx;
     if (P.elite_idx_out) P.elite_idx_out[static_cast<size_t>(e) * P.K + k] = idx;
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  G::sync();
+  if (G::tid() == 0) {
     float s = 0.f;
     for (int k = 0; k < P.K; ++k) s += escore[k];
     red[0] = s;
   }
-  __syncthreads();
-  for (int k = threadIdx.x; k < P.K; k += kThreads) escore[k] = __fdiv_rn(escore[k], red[0]);   // score /= score.sum(0)
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  G::sync();
+  for (int k = G::tid(); k < P.K; k += G::N) escore[k] = __fdiv_rn(escore[k], red[0]);   // score /= score.sum(0)
+  G::sync();
+  if (G::tid() == 0) {
     float s = 0.f;
     for (int k = 0; k < P.K; ++k) s += escore[k];
     red[1] = s + 1e-9f;                                        // score.sum(0) + 1e-9
   }
-  __syncthreads();
+  G::sync();
   const float denom = red[1];
-  for (int k = threadIdx.x; k < P.K; k += kThreads) P.score[static_cast<size_t>(e) * P.K + k] = escore[k];
+  for (int k = G::tid(); k < P.K; k += G::N) P.score[static_cast<size_t>(e) * P.K + k] = escore[k];
   // Gather the elites' actions once, all loads independent (the weighted sums below then run out of smem).
   const int HA = P.H * P.A;
-  float* eact = reinterpret_cast<float*>(c.stage_base + 65536);          // [K][H*A]; keys/score/idx stay below 64 KiB
-  const bool staged = static_cast<size_t>(P.K) * HA * 4 <= static_cast<size_t>(kStages * kStageBytes - 65536) &&
+  float* eact = reinterpret_cast<float*>(scratch + 65536);          // [K][H*A]; keys/score/idx stay below 64 KiB
+  const bool staged = static_cast<size_t>(P.K) * HA * 4 <= (scratch_bytes - 65536) &&
                       static_cast<size_t>(nsort) * 8 + static_cast<size_t>(P.K) * 8 + 16 <= 65536;
   if (staged) {
-    for (int i = threadIdx.x; i < P.K * HA; i += kThreads) {
+    for (int i = G::tid(); i < P.K * HA; i += G::N) {
       const int k = i / HA, ta = i % HA;
       eact[i] = sample_action(P, e, ta / P.A, eidx[k], ta % P.A, task);
     }
-    __syncthreads();
+    G::sync();
   }
-  for (int i = threadIdx.x; i < HA; i += kThreads) {
+  for (int i = G::tid(); i < HA; i += G::N) {
     const int t = i / P.A, a = i % P.A;
     float m = 0.f;
     for (int k = 0; k < P.K; ++k) m = fmaf(escore[k], staged ? eact[k * HA + i] : sample_action(P, e, t, eidx[k], a, task), m);
@@ -1324,7 +1331,7 @@ __device__ __forceinline__ void refit_env(const PlanParams& P, Ctx& c, int e, in
     P.mean[sa] = m;
     P.std[sa] = sd;
   }
-  __syncthreads();
+  G::sync();
 }
 
 // ------------------------------------------------------------------------------------ the kernel
@@ -1592,7 +1599,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
       __syncthreads();
       if (c.flags[0]) {
         __threadfence();
-        refit_env(P, c, env_tile, task_tile);
+        refit_env<GroupAll>(P, c.stage_base, static_cast<size_t>(kStages) * kStageBytes, env_tile, task_tile);
       }
       publish_planes();     // refit_env wrote the stage smem through the generic proxy; TMA reuses it next tile
     }

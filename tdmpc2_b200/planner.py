@@ -137,7 +137,8 @@ class Planner:
             pass
 
     def set_engine(self, engine: str) -> None:
-        code = {"tcgen05": _cabi.ENGINE_TCGEN05, "simt": _cabi.ENGINE_SIMT, "tcgen05x2": _cabi.ENGINE_TCGEN05_2SM}[engine]
+        code = {"tcgen05": _cabi.ENGINE_TCGEN05, "simt": _cabi.ENGINE_SIMT, "tcgen05x2": _cabi.ENGINE_TCGEN05_2SM,
+                "tcgen05pp": _cabi.ENGINE_TCGEN05_PP}[engine]
         _cabi.check(self.lib.tdmpc2_planner_set_engine(self.h, code))
         self.engine = engine
 
