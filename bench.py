@@ -154,7 +154,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default="tcgen05x2", choices=["tcgen05x2", "tcgen05", "simt"])
+    ap.add_argument("--engine", default=None, choices=["tcgen05pp", "tcgen05x2", "tcgen05", "simt"])
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--envs", type=int, default=None, help="environments per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -301,7 +301,7 @@ def main():
         "config": {"workload": f"{args.workload}: dog-run 5M model, {E_local} envs/GPU, num_samples={cfg.num_samples}, "
                                f"horizon={cfg.horizon}, iterations={cfg.iterations}" if args.workload == "c2"
                    else f"{args.workload}: {E_local} envs/GPU",
-                   "global_envs": E_total, "parallelism": f"env-shard x{world}", "engine": args.engine,
+                   "global_envs": E_total, "parallelism": f"env-shard x{world}", "engine": agent.planner.engine_name,
                    "arithmetic": "3-pass fp16-split operands on tcgen05 kind::f16, fp32 accumulate (fp32-parity mode)",
                    "l2": "no flush: per-step inputs exceed L2 (fresh noise tensors, "
                          f"{4 * E_local * cfg.iterations * (cfg.horizon * (cfg.num_samples - cfg.num_pi_trajs) + cfg.num_samples) * A_ / 1e6:.0f} MB/step/GPU)",

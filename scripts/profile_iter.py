@@ -38,7 +38,13 @@ if os.environ.get("TDMPC2_PHASE_PROF"):
     for r in range(4):
         print(names[r].ljust(10), "  ".join(f"{cols[k]}={m[r, k] / 1e3:9.1f}k" for k in range(9)))
 
-    if os.environ.get("TDMPC2_TRACE"):
+    if os.environ.get("TDMPC2_TRACE") == "pp":
+        ev = ["start", "gA0", "gA1", "gB0", "gB1", "accA", "eA", "eAend", "accB", "eB", "eBend"]
+        t00 = int(tr[0, 0])
+        for st in range(27):
+            t0 = int(tr[st, 0])
+            print(f"step {st:2d} @{(t0 - t00) / 1e3:8.1f}k  " + " ".join(f"{ev[k]}={(int(tr[st, k]) - t0) / 1e3:6.1f}" for k in range(1, 11) if int(tr[st, k]) > 0))
+    elif os.environ.get("TDMPC2_TRACE"):
         ev = ["start", "tma0", "mma0", "mmaL", "e0acc", "e0p1", "e0bar", "e0p2", "e0bw", "end", "e3acc", "e3p2"]
         t00 = int(tr[0, 0])
         for st in range(27):

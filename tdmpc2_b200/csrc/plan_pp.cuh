@@ -46,6 +46,12 @@ constexpr int kPPProg = 2 * kPPMaxSteps * 32;          // double-buffered layer 
 constexpr int kPPSmemBytes = kPPOperandBytes + kPPCtrl + kPPVec + kPPPart + kPPAct + kPPProg + 1024;
 static_assert(kPPSmemBytes <= 232448, "ping-pong kernel shared memory");
 
+// Diagnostics: clock stamps of CTA 0's first tile, [step][event] after the per-CTA counters (see TDMPC2_TRACE).
+#define PP_TRACE(P_, on_, s_, ev_)                                                           \
+  do {                                                                                      \
+    if ((P_).prof && (on_) && (s_) < 32) (P_).prof[148 * 4 * 12 + (s_) * 16 + (ev_)] = clock64(); \
+  } while (0)
+
 struct PPStep {
   int li, src, kind, dstbuf, head, t_act;   // t_act >= 0: X action columns must hold a_t before this step's GEMM
   float disc;
@@ -455,6 +461,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_pp_kernel(const __grid_const
             ptx::mbar_wait(&c.acc_free[h], (free_it[h] & 1) ^ 1);    // both CTAs drained the previous accumulator of h
             ++free_it[h];
             ptx::tc_fence_after();
+            PP_TRACE(P, blockIdx.x == 0 && tcount == 0, s, 1 + 2 * h);
             for (int kc = 0; kc < nkc; ++kc) {
               const uint32_t as = ma_it % kPPARing, aph = (ma_it / kPPARing) & 1;
               ptx::mbar_wait(&c.a_full[as], aph);
@@ -483,6 +490,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_pp_kernel(const __grid_const
               ++ma_it;
             }
             ptx::umma_commit_2sm(&c.facc[h]);
+            PP_TRACE(P, blockIdx.x == 0 && tcount == 0, s, 2 + 2 * h);
           }
         }
       }
@@ -572,15 +580,19 @@ __global__ void __launch_bounds__(kThreads, 1) plan_pp_kernel(const __grid_const
         if (st.kind == EPI_TWOHOT) for (int i = tid; i < P.B; i += kEpiThreads) c.vec[kFusedMaxN + i] = P.bins[i];
         const int t_next = (s + 1 < nsteps) ? prog[s + 1].t_act : -1;
         epi_bar_sync();
+        const bool tr_on = (blockIdx.x == 0 && tcount == 0 && tid == 0);
+        PP_TRACE(P, tr_on, s, 0);
         for (int h = 0; h < 2; ++h) {
           ptx::mbar_wait(&c.facc[h], fph[h]);
           fph[h] ^= 1;
           ptx::tc_fence_after();
+          PP_TRACE(P, tr_on, s, 5 + 3 * h);
           if (st.kind == EPI_LN_MISH) pp_epi_ln<EPI_LN_MISH>(P, c, et, ly, st, h);
           else if (st.kind == EPI_LN_SIMNORM) pp_epi_ln<EPI_LN_SIMNORM>(P, c, et, ly, st, h);
           else if (st.kind == EPI_TWOHOT) pp_epi_twohot(P, c, et, ly, st, h, tile);
           else pp_epi_pi(P, c, et, ly, h, tile, env, task);
           ptx::tc_fence_before();
+          PP_TRACE(P, tr_on, s, 6 + 3 * h);
           if (t_next >= 0) pp_write_actions(P, c, tile, env, task, t_next, h * kPPHalf, kPPHalf, h == 0);
           if (is_ln && ((et.q & 1) == 0) && c.lane == 0) ptx::bulk_wait<0>();      // this block group's stores are performed
           __threadfence();
@@ -590,6 +602,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_pp_kernel(const __grid_const
             pp_arrive_leader(&c.acc_free[h], c.rank);                 // TMEM of half h may be overwritten
             if (s + 1 < nsteps) ptx::mbar_arrive(&c.act_ready[h]);    // planes of (h, s+1) are published
           }
+          PP_TRACE(P, tr_on, s, 7 + 3 * h);
         }
       }
 

@@ -9,6 +9,8 @@ Call sequence of one `plan()` (reference tdmpc2.py:138-206):
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from dataclasses import dataclass
 from typing import Dict, Optional
@@ -17,6 +19,11 @@ import torch
 
 from . import _cabi
 from .config import Config, get_discount
+
+
+# GEMM engine of the CEM-iteration kernel (include/tdmpc2_b200.h, tdmpc2_engine).  "tcgen05pp" falls back to
+# "tcgen05x2" and that to "tcgen05" inside the library when a model / shape does not fit; TDMPC2_B200_ENGINE overrides.
+DEFAULT_ENGINE = os.environ.get("TDMPC2_B200_ENGINE", "tcgen05x2")
 
 
 @dataclass
@@ -98,7 +105,7 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 class Planner:
     """Owns one tdmpc2_planner handle plus its packed weights and workspace."""
 
-    def __init__(self, cfg: Config, num_envs: int, device, engine: str = "tcgen05x2"):
+    def __init__(self, cfg: Config, num_envs: int, device, engine: Optional[str] = None):
         self.lib = _cabi.load()                         # raises if the .so is missing
         self.cfg, self.E = cfg, int(num_envs)
         self.device = torch.device(device)
@@ -137,6 +144,8 @@ class Planner:
             pass
 
     def set_engine(self, engine: str) -> None:
+        engine = engine or DEFAULT_ENGINE
+        self.engine_name = engine
         code = {"tcgen05": _cabi.ENGINE_TCGEN05, "simt": _cabi.ENGINE_SIMT, "tcgen05x2": _cabi.ENGINE_TCGEN05_2SM,
                 "tcgen05pp": _cabi.ENGINE_TCGEN05_PP}[engine]
         _cabi.check(self.lib.tdmpc2_planner_set_engine(self.h, code))

@@ -22,7 +22,7 @@ from .world_model import WorldModel, convert_legacy_checkpoint
 
 
 class TDMPC2(torch.nn.Module):
-    def __init__(self, cfg: Config, device: Union[str, torch.device, None] = None, engine: str = "tcgen05x2"):
+    def __init__(self, cfg: Config, device: Union[str, torch.device, None] = None, engine: Optional[str] = None):
         super().__init__()
         self.cfg = cfg
         self.device = torch.device("cuda:0" if device is None else device)      # tdmpc2.py:20
