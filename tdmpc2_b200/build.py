@@ -57,5 +57,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defines: list[str]) -> str:
+    """Experiment build: libtdmpc2_b200_<name>.so with extra -D flags; load it through TDMPC2_B200_LIB."""
+    out = os.path.join(HERE, f"libtdmpc2_b200_{name}.so")
+    cmd = [find_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["api.cu", "-o", out]
+    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -42,6 +42,10 @@
 
 namespace tdmpc2 {
 
+#ifndef TDMPC2_POLL_ONE
+#define TDMPC2_POLL_ONE 0     // 1: a single epilogue warp polls the accumulator-complete mbarrier (scripts/micro/tma_bw.cu)
+#endif
+
 constexpr int kTileM = 128;       // rows per tile (UMMA M)
 constexpr int kKch = 64;          // K elements per pipeline stage (128 B of fp16: one swizzle row)
 constexpr int kNch = 256;         // N columns per accumulator chunk (UMMA N max)
@@ -819,11 +823,21 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
   const float inv_scale = ly.inv_scale;
   epi_stage_vectors(c, ly, true);
   const float* sb = c.vec; const float* sg = c.vec + kFusedMaxN; const float* sbe = c.vec + 2 * kFusedMaxN;
+#if TDMPC2_POLL_ONE
+  {
+    // one warp polls the accumulator barrier, the other 15 block on a hardware barrier: pollers cost TMA throughput
+    const long long tw = clock64();
+    if (c.warp == kEpiWarp0) ptx::mbar_wait(&c.facc[0], c.fph0);
+    epi_bar_sync();
+    c.pf2 += clock64() - tw;
+  }
+#else
   if (nvalid > 0) {
     const long long tw = clock64();
     ptx::mbar_wait(&c.facc[0], c.fph0);
     c.pf2 += clock64() - tw;
   }
+#endif
   const bool tr0 = (et.grp == 0 && et.q == 0 && c.lane == 0), tr3 = (et.grp == 3 && et.q == 0 && c.lane == 0);
   if (tr0) TDMPC2_TRACE(P, c, 4);
   if (tr3) TDMPC2_TRACE(P, c, 10);
