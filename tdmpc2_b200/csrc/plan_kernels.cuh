@@ -42,10 +42,6 @@
 
 namespace tdmpc2 {
 
-#ifndef TDMPC2_POLL_ONE
-#define TDMPC2_POLL_ONE 0     // 1: a single epilogue warp polls the accumulator-complete mbarrier (scripts/micro/tma_bw.cu)
-#endif
-
 constexpr int kTileM = 128;       // rows per tile (UMMA M)
 constexpr int kKch = 64;          // K elements per pipeline stage (128 B of fp16: one swizzle row)
 constexpr int kNch = 256;         // N columns per accumulator chunk (UMMA N max)
@@ -706,13 +702,27 @@ __device__ __forceinline__ float exp_fast(float x) { return ex2_ftz(x * 1.442695
 // which is what bounds the fused epilogue.
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
+#ifndef TDMPC2_MISH_SHARED_RCP
+#define TDMPC2_MISH_SHARED_RCP 1
+#endif
+// Two Mish values.  The MUFU pipe (16 lanes / clk / SM) co-limits pass 2 of the epilogue, so the two divisions share
+// one reciprocal: 1/d.x = d.y / (d.x d.y).  x is clamped at 10 (n/(n+2) already rounds to 1 there), which keeps
+// d.x * d.y < 2.4e17.
 __device__ __forceinline__ float2 mish_fast2(float2 x) {
+#if TDMPC2_MISH_SHARED_RCP
+  const float2 a = f2(fminf(x.x, 10.f), fminf(x.y, 10.f));
+#else
   const float2 a = f2(fminf(x.x, 30.f), fminf(x.y, 30.f));
+#endif
   const float2 z = __fmul2_rn(a, f2s(1.4426950408889634f));
   const float2 e = f2(ex2_ftz(z.x), ex2_ftz(z.y));
   const float2 n = __fmul2_rn(e, __fadd2_rn(e, f2s(2.f)));
   const float2 d = __fadd2_rn(n, f2s(2.f));
+#if TDMPC2_MISH_SHARED_RCP
+  const float2 r = __fmul2_rn(f2s(rcp_ftz(d.x * d.y)), f2(d.y, d.x));
+#else
   const float2 r = f2(rcp_ftz(d.x), rcp_ftz(d.y));
+#endif
   return __fmul2_rn(x, __fmul2_rn(n, r));
 }
 __device__ __forceinline__ float mish_fast(float x) {
@@ -823,21 +833,11 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
   const float inv_scale = ly.inv_scale;
   epi_stage_vectors(c, ly, true);
   const float* sb = c.vec; const float* sg = c.vec + kFusedMaxN; const float* sbe = c.vec + 2 * kFusedMaxN;
-#if TDMPC2_POLL_ONE
-  {
-    // one warp polls the accumulator barrier, the other 15 block on a hardware barrier: pollers cost TMA throughput
-    const long long tw = clock64();
-    if (c.warp == kEpiWarp0) ptx::mbar_wait(&c.facc[0], c.fph0);
-    epi_bar_sync();
-    c.pf2 += clock64() - tw;
-  }
-#else
   if (nvalid > 0) {
     const long long tw = clock64();
     ptx::mbar_wait(&c.facc[0], c.fph0);
     c.pf2 += clock64() - tw;
   }
-#endif
   const bool tr0 = (et.grp == 0 && et.q == 0 && c.lane == 0), tr3 = (et.grp == 3 && et.q == 0 && c.lane == 0);
   if (tr0) TDMPC2_TRACE(P, c, 4);
   if (tr3) TDMPC2_TRACE(P, c, 10);

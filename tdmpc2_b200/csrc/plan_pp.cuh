@@ -583,12 +583,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_pp_kernel(const __grid_const
         const bool tr_on = (blockIdx.x == 0 && tcount == 0 && tid == 0);
         PP_TRACE(P, tr_on, s, 0);
         for (int h = 0; h < 2; ++h) {
-#if TDMPC2_POLL_ONE
-          if (c.warp == kEpiWarp0) ptx::mbar_wait(&c.facc[h], fph[h]);
-          epi_bar_sync();
-#else
           ptx::mbar_wait(&c.facc[h], fph[h]);
-#endif
           fph[h] ^= 1;
           ptx::tc_fence_after();
           PP_TRACE(P, tr_on, s, 5 + 3 * h);
