@@ -702,27 +702,16 @@ __device__ __forceinline__ float exp_fast(float x) { return ex2_ftz(x * 1.442695
 // which is what bounds the fused epilogue.
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
-#ifndef TDMPC2_MISH_SHARED_RCP
-#define TDMPC2_MISH_SHARED_RCP 1
-#endif
-// Two Mish values.  The MUFU pipe (16 lanes / clk / SM) co-limits pass 2 of the epilogue, so the two divisions share
-// one reciprocal: 1/d.x = d.y / (d.x d.y).  x is clamped at 10 (n/(n+2) already rounds to 1 there), which keeps
-// d.x * d.y < 2.4e17.
+// Two Mish values; the two divisions share one reciprocal, 1/d.x = d.y / (d.x d.y) (halves the MUFU.RCP count; it
+// measured neutral, the epilogue is latency-bound).  x is clamped at 10: n/(n+2) already rounds to 1 there, and
+// d.x * d.y stays below 2.4e17.
 __device__ __forceinline__ float2 mish_fast2(float2 x) {
-#if TDMPC2_MISH_SHARED_RCP
   const float2 a = f2(fminf(x.x, 10.f), fminf(x.y, 10.f));
-#else
-  const float2 a = f2(fminf(x.x, 30.f), fminf(x.y, 30.f));
-#endif
   const float2 z = __fmul2_rn(a, f2s(1.4426950408889634f));
   const float2 e = f2(ex2_ftz(z.x), ex2_ftz(z.y));
   const float2 n = __fmul2_rn(e, __fadd2_rn(e, f2s(2.f)));
   const float2 d = __fadd2_rn(n, f2s(2.f));
-#if TDMPC2_MISH_SHARED_RCP
   const float2 r = __fmul2_rn(f2s(rcp_ftz(d.x * d.y)), f2(d.y, d.x));
-#else
-  const float2 r = f2(rcp_ftz(d.x), rcp_ftz(d.y));
-#endif
   return __fmul2_rn(x, __fmul2_rn(n, r));
 }
 __device__ __forceinline__ float mish_fast(float x) {
