@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define TDMPC2_B200_ABI_VERSION 1
+#define TDMPC2_B200_ABI_VERSION 2   /* 2: tdmpc2_weights.termination, dims.episodic = 1 accepted */
 #define TDMPC2_MAX_ENC_LAYERS 8
 
 typedef enum tdmpc2_status {
@@ -81,7 +81,7 @@ typedef struct tdmpc2_dims {
   int32_t num_q;
   int32_t num_bins;        /* B (two-hot regression bins; must be > 1)                   */
   int32_t simnorm_dim;     /* 8                                                          */
-  int32_t episodic;        /* must be 0 (termination head: SURVEY.md section 8(f))       */
+  int32_t episodic;        /* cfg.episodic: 1 adds the termination head (single-task)    */
   float temperature;       /* cfg.temperature                                            */
   float min_std, max_std;
   float log_std_min, log_std_dif;   /* WorldModel buffers, world_model.py:34-35          */
@@ -110,6 +110,8 @@ typedef struct tdmpc2_weights {
   const float* discount_pow;                    /* [num_tasks, H+1]: gamma_task^t, computed by
                                                    the host the way tdmpc2.py:125-132 does  */
   const float* bins;                            /* torch.linspace(vmin, vmax, B), math.py:80 */
+  tdmpc2_linear termination[3];                 /* _termination.{0,1,2}.* (layer 2: no LN, 1 output), read only
+                                                   when dims.episodic; world_model.py:28,132-141            */
 } tdmpc2_weights;
 
 typedef struct tdmpc2_planner tdmpc2_planner;    /* opaque host-side context */

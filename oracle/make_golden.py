@@ -40,6 +40,11 @@ CASES = {
                           [(True, False, None, 3), (False, False, None, 4)]),
     "c4_mt80_317m_e1": ("c4", {"num_envs": 1}, 1, False, 1.0,
                         [(True, False, 7, 3), (False, False, 41, 4)]),
+    # cfg.episodic: termination head in the rollout (tdmpc2.py:126-136, world_model.py:28,132-141)
+    "tiny_episodic": ("tiny", {"episodic": True}, 13, True, 1.0,
+                      [(True, False, None, 300), (False, False, None, 301), (False, True, None, 302)]),
+    "c1_dog5m_episodic": ("c1", {"episodic": True}, 2, True, 1.0,
+                          [(True, False, None, 6), (False, False, None, 7)]),
 }
 
 
@@ -52,12 +57,18 @@ def main(only=None):
         t = time.time()
         cfg = workload(wl, **over)
         sd = synth_state_dict(cfg, seed=wseed, perturb=perturb, emb_scale=emb_scale)
+        term_bias = None
+        if cfg.episodic:      # synthetic termination logits all share one sign: centre them (see balance_termination)
+            from oracle.plan_oracle import balance_termination
+            term_bias = balance_termination(cfg, sd)
         agent = rh.build_agent(cfg, sd)
         g = torch.Generator().manual_seed(1000 + wseed)
         obs_dim = cfg.obs_shape["state"][0]
         rec = dict(workload=wl, overrides=repr(over), weight_seed=wseed, perturb=perturb, emb_scale=emb_scale,
                    weight_checksum=state_dict_checksum(sd), n_calls=len(calls),
                    torch_version=torch.__version__)
+        if term_bias is not None:
+            rec["term_bias"] = term_bias
         prev_mean = torch.zeros(cfg.horizon, cfg.action_dim)
         for i, (t0, ev, task, seed) in enumerate(calls):
             obs = torch.randn(obs_dim, generator=g)

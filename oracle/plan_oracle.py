@@ -167,6 +167,16 @@ class OracleModel:
             z = self.task_emb(z, task)
         return self._mlp("_reward", torch.cat([z, a], dim=-1), "none")
 
+    def termination_logits(self, z, task):
+        """world_model.py:132-141 with unnormalized=True; the reference asserts `task is None`."""
+        assert task is None
+        if self.cfg.multitask:
+            z = self.task_emb(z, task)
+        return self._mlp("_termination", z, "none")
+
+    def termination(self, z, task):
+        return torch.sigmoid(self.termination_logits(z, task))
+
     def pi(self, z, task, eps):
         """Planner-visible part of WorldModel.pi: the squashed sampled action."""
         if self.cfg.multitask:
@@ -196,20 +206,43 @@ def _discount(cfg, task: Optional[int]) -> float:
     return d(cfg.episode_length)
 
 
-def estimate_value(model: OracleModel, z, actions, task, eps_pi, qidx):
-    """tdmpc2.py:122-136 (non-episodic: termination stays all-zero)."""
+def estimate_value(model: OracleModel, z, actions, task, eps_pi, qidx, info: Optional[dict] = None):
+    """tdmpc2.py:122-136.  `info` (test aid, not in the reference) receives `term_margin` [N]: the smallest
+    |termination logit| a sample saw, so parity tests can skip samples that sit on the 0.5 decision boundary."""
     cfg = model.cfg
-    assert not cfg.episodic, "episodic termination head: SURVEY.md section 8(f) 'next' row"
     G, discount = 0, 1
     termination = torch.zeros(z.shape[0], 1, dtype=torch.float32)
+    margin = torch.full((z.shape[0],), float("inf"))
     gamma = _discount(cfg, task)
     for t in range(cfg.horizon):
         reward = two_hot_inv(model.reward(z, actions[t], task), cfg)
         z = model.next(z, actions[t], task)
         G = G + discount * (1 - termination) * reward
         discount = discount * gamma
+        if cfg.episodic:                                                                    # tdmpc2.py:133-134
+            logits = model.termination_logits(z, task)
+            termination = torch.clip(termination + (torch.sigmoid(logits) > 0.5).float(), max=1.)
+            margin = torch.minimum(margin, logits.abs().squeeze(1))
+    if info is not None:
+        info["term_margin"] = margin
     action = model.pi(z, task, eps_pi)
     return G + discount * (1 - termination) * model.Q_avg(z, action, task, qidx)
+
+
+@torch.no_grad()
+def balance_termination(cfg, sd: Dict[str, torch.Tensor], seed: int = 0, rows: int = 256) -> float:
+    """Test aid for synthetic episodic models: random-init termination logits all share the sign of one
+    common offset, so every sample would (not) terminate at once.  Shifts `_termination.2.bias` in place so
+    that the logits of `rows` probe states (one dynamics step from an encoded random observation) have
+    median 0.3 sigma -- a mix of terminated and live samples at every step.  Returns the new bias."""
+    model = OracleModel(cfg, sd)
+    g = torch.Generator().manual_seed(seed)
+    z = model.encode(torch.randn(1, cfg.obs_shape["state"][0], generator=g), None).repeat(rows, 1)
+    z = model.next(z, torch.rand(rows, cfg.action_dim, generator=g) * 2 - 1, None)
+    lg = model.termination_logits(z, None).squeeze(1)
+    bias = float(sd["_termination.2.bias"].reshape(-1)[0] - lg.median() - 0.3 * lg.std())
+    sd["_termination.2.bias"] = torch.full_like(sd["_termination.2.bias"], bias)
+    return bias
 
 
 @dataclass
@@ -225,6 +258,7 @@ class PlanTrace:
     iter_std: torch.Tensor               # [E, I, H, A]
     score: torch.Tensor                  # [E, K]      (last iteration, normalised)
     pick: torch.Tensor                   # [E] int64   elite position chosen by the gumbel pick
+    term_margin: Optional[torch.Tensor] = None   # [E, I, N] episodic models only: min |termination logit| per sample
     extras: Dict[str, torch.Tensor] = field(default_factory=dict)
 
 
@@ -251,7 +285,7 @@ def plan_one(model: OracleModel, obs, task, t0: bool, prev_mean, noise: PlanNois
     if P > 0:
         actions[:, :P] = pi_actions
     mask = model.sd["_action_masks"][task] if cfg.multitask else None
-    vals, idxs, means, stds = [], [], [], []
+    vals, idxs, means, stds, margins = [], [], [], [], []
     for it in range(cfg.iterations):
         r = noise.r[0, it]
         actions_sample = mean.unsqueeze(1) + std.unsqueeze(1) * r
@@ -259,7 +293,9 @@ def plan_one(model: OracleModel, obs, task, t0: bool, prev_mean, noise: PlanNois
         actions[:, P:] = actions_sample
         if mask is not None:
             actions = actions * mask
-        value = estimate_value(model, z, actions, task, noise.pi[0, it], noise.qidx[0, it]).nan_to_num(0)
+        info = {}
+        value = estimate_value(model, z, actions, task, noise.pi[0, it], noise.qidx[0, it], info).nan_to_num(0)
+        margins.append(info["term_margin"])
         elite_idxs = torch.topk(value.squeeze(1), K, dim=0).indices
         elite_value, elite_actions = value[elite_idxs], actions[:, elite_idxs]
         max_value = elite_value.max(0).values
@@ -281,9 +317,12 @@ def plan_one(model: OracleModel, obs, task, t0: bool, prev_mean, noise: PlanNois
     a = elite_actions[0, rand_idx]
     if not eval_mode:
         a = a + std[0] * noise.final[0]
-    return dict(action=a.clamp(-1, 1), mean=mean, std=std, z=z0[0], pi_actions=pi_actions,
-                values=torch.stack(vals), elite_idx=torch.stack(idxs), iter_mean=torch.stack(means),
-                iter_std=torch.stack(stds), score=score.squeeze(1), pick=rand_idx)
+    out = dict(action=a.clamp(-1, 1), mean=mean, std=std, z=z0[0], pi_actions=pi_actions,
+               values=torch.stack(vals), elite_idx=torch.stack(idxs), iter_mean=torch.stack(means),
+               iter_std=torch.stack(stds), score=score.squeeze(1), pick=rand_idx)
+    if cfg.episodic:
+        out["term_margin"] = torch.stack(margins)
+    return out
 
 
 @torch.no_grad()

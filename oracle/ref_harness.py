@@ -89,7 +89,7 @@ def build_agent(cfg, state_dict: Dict[str, torch.Tensor]):
             self._encoder = layers.enc(cfg, out={})
             self._dynamics = layers.mlp(D, 2 * [cfg.mlp_dim], cfg.latent_dim, act=layers.SimNorm(cfg))
             self._reward = layers.mlp(D, 2 * [cfg.mlp_dim], max(cfg.num_bins, 1))
-            self._termination = None
+            self._termination = layers.mlp(cfg.latent_dim + cfg.task_dim, 2 * [cfg.mlp_dim], 1) if cfg.episodic else None   # world_model.py:28
             self._pi = layers.mlp(cfg.latent_dim + cfg.task_dim, 2 * [cfg.mlp_dim], 2 * cfg.action_dim)
             qs = [layers.mlp(D, 2 * [cfg.mlp_dim], max(cfg.num_bins, 1), dropout=cfg.dropout) for _ in range(cfg.num_q)]
             self._Qs = FuncEnsemble(qs)

@@ -11,6 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TDMPC2_B200_LIB") or os.path.join(HERE, "libtdmpc2_b200.so")
 MAX_ENC_LAYERS = 8
 ENGINE_TCGEN05, ENGINE_SIMT, ENGINE_TCGEN05_2SM, ENGINE_TCGEN05_PP = 0, 1, 2, 3
+ABI_VERSION = 2            # TDMPC2_B200_ABI_VERSION of include/tdmpc2_b200.h this binding was written against
 
 # every symbol include/tdmpc2_b200.h declares
 SYMBOLS = [
@@ -38,7 +39,7 @@ class Weights(C.Structure):
     _fields_ = [("num_enc", C.c_int32), ("enc", Linear * MAX_ENC_LAYERS), ("dynamics", Linear * 3),
                 ("reward", Linear * 3), ("pi", Linear * 3), ("qs", Linear * 3),
                 ("task_emb", C.c_void_p), ("action_masks", C.c_void_p), ("discount_pow", C.c_void_p),
-                ("bins", C.c_void_p)]
+                ("bins", C.c_void_p), ("termination", Linear * 3)]
 
 
 class CabiError(RuntimeError):
@@ -63,6 +64,8 @@ def load():
             raise CabiError(f"{LIB_PATH} does not export {s}")
     vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
     lib.tdmpc2_abi_version.restype = C.c_int
+    if lib.tdmpc2_abi_version() != ABI_VERSION:
+        raise CabiError(f"{LIB_PATH} has ABI version {lib.tdmpc2_abi_version()}, this binding needs {ABI_VERSION}: rebuild it")
     lib.tdmpc2_last_error.restype = C.c_char_p
     lib.tdmpc2_planner_create.argtypes = [C.POINTER(Dims), C.POINTER(vp)]
     lib.tdmpc2_planner_destroy.argtypes = [vp]

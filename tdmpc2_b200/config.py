@@ -181,7 +181,8 @@ def flops_per_env(cfg: Config, heads_used: int = 2) -> float:
     w = lambda i, h, o: i * h + h * h + h * o
     dyn, rew, pi, q = w(D, M, L), w(D, M, B), w(L + T, M, 2 * A), w(D, M, B)
     H, N, P, I = cfg.horizon, cfg.num_samples, cfg.num_pi_trajs, cfg.iterations
-    macs = I * N * (H * (rew + dyn) + pi + heads_used * q) + P * (H * pi + (H - 1) * dyn)
+    term = w(L + T, M, 1) if cfg.episodic else 0          # termination head on z_{t+1} (world_model.py:28)
+    macs = I * N * (H * (rew + dyn + term) + pi + heads_used * q) + P * (H * pi + (H - 1) * dyn)
     enc_in = cfg.obs_shape["state"][0] + T
     n_hidden = max(cfg.num_enc_layers - 1, 1)
     enc = enc_in * cfg.enc_dim + (n_hidden - 1) * cfg.enc_dim ** 2 + cfg.enc_dim * L

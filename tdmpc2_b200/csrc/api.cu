@@ -112,7 +112,7 @@ struct tdmpc2_planner {
   tdmpc2_dims d;
   int num_sms = 0, nslots = 0;
   std::vector<LayerHost> layers;
-  int li_enc = 0, li_dyn = 0, li_rew = 0, li_pi = 0, li_q = 0, num_enc = 0;
+  int li_enc = 0, li_dyn = 0, li_rew = 0, li_pi = 0, li_q = 0, li_term = -1, num_enc = 0;
   int nmaps = 0;
   int map_kpad[kMaxWMaps];
   int map_rows[kMaxWMaps];
@@ -174,7 +174,9 @@ static int check_device(int* num_sms) {
 extern "C" int tdmpc2_planner_create(const tdmpc2_dims* dims, tdmpc2_planner** out) {
   if (!dims || !out) return fail(TDMPC2_ERR_INVALID, "null argument");
   const tdmpc2_dims& d = *dims;
-  if (d.episodic) return fail(TDMPC2_ERR_UNSUPPORTED, "episodic termination head is not built yet (SURVEY.md 8(f))");
+  if (d.episodic != 0 && d.episodic != 1) return fail(TDMPC2_ERR_INVALID, "episodic must be 0 or 1");
+  if (d.episodic && d.task_dim > 0)   // WorldModel.termination asserts task is None (world_model.py:136)
+    return fail(TDMPC2_ERR_UNSUPPORTED, "episodic (termination head) models are single-task in the reference");
   if (d.num_envs < 1 || d.num_samples < 1 || d.horizon < 1 || d.iterations < 1 || d.obs_dim < 1 || d.action_dim < 1 ||
       d.latent_dim < 1 || d.mlp_dim < 1 || d.enc_dim < 1 || d.num_enc_layers < 1 || d.num_q < 2 || d.num_bins < 2 ||
       d.task_dim < 0 || d.num_tasks < 1)
@@ -217,6 +219,9 @@ extern "C" int tdmpc2_planner_create(const tdmpc2_dims* dims, tdmpc2_planner** o
   }
   p->li_q = static_cast<int>(p->layers.size());
   for (int h = 0; h < d.num_q; ++h) { add(D, M, true); add(M, M, true); add(M, B, false); }
+  // termination head: mlp(L+T, 2*[M], 1) on z_{t+1}  (world_model.py:28); appended so the other layer indices stay put
+  p->li_term = -1;
+  if (d.episodic) { p->li_term = static_cast<int>(p->layers.size()); add(L + T, M, true); add(M, M, true); add(M, 1, false); }
   if (!ok) { delete p; return fail(TDMPC2_ERR_INVALID, "more than %d distinct padded input widths", kMaxWMaps); }
 
   p->KpadX = std::max(pad_to(D, kKch), pad_to(d.obs_dim + T, kKch));
@@ -366,7 +371,7 @@ extern "C" int tdmpc2_planner_bind(tdmpc2_planner* p, void* packed, void* worksp
   B.obs_dim = d.obs_dim; B.A = d.action_dim; B.Apad = pad_to(d.action_dim, 32); B.L = d.latent_dim; B.M = d.mlp_dim; B.T = d.task_dim; B.B = d.num_bins;
   B.num_q = d.num_q; B.simnorm = d.simnorm_dim; B.num_enc = p->num_enc;
   B.tiles_per_env = p->tiles_per_env; B.KpadX = p->KpadX; B.KpadH = p->KpadH; B.NpadMax = p->NpadMax;
-  B.li_enc = p->li_enc; B.li_dyn = p->li_dyn; B.li_rew = p->li_rew; B.li_pi = p->li_pi; B.li_q = p->li_q;
+  B.li_enc = p->li_enc; B.li_dyn = p->li_dyn; B.li_rew = p->li_rew; B.li_pi = p->li_pi; B.li_q = p->li_q; B.li_term = p->li_term;
   B.temperature = d.temperature; B.min_std = d.min_std; B.max_std = d.max_std;
   B.log_std_min = d.log_std_min; B.log_std_dif = d.log_std_dif;
   B.X = reinterpret_cast<__half*>(p->ws + p->off_X);
@@ -430,6 +435,7 @@ extern "C" int tdmpc2_pack_weights(tdmpc2_planner* p, const tdmpc2_weights* w, v
     if ((rc = pack_one(p->li_rew + i, w->reward[i], 0))) return rc;
     if ((rc = pack_one(p->li_pi + i, w->pi[i], 0))) return rc;
     for (int h = 0; h < d.num_q; ++h) if ((rc = pack_one(p->li_q + 3 * h + i, w->qs[i], h))) return rc;
+    if (d.episodic && (rc = pack_one(p->li_term + i, w->termination[i], 0))) return rc;
   }
   if (d.task_dim > 0) {
     emb_renorm_kernel<<<d.num_tasks, 32, 0, st>>>(w->task_emb, d.task_dim, reinterpret_cast<float*>(p->packed + p->off_emb));
@@ -452,7 +458,7 @@ extern "C" int tdmpc2_pack_weights(tdmpc2_planner* p, const tdmpc2_weights* w, v
 // plan_pp.cuh covers models whose trunk layers are 256 / 512 wide and whose heads fit one 128-column chunk
 static bool pp_eligible(const tdmpc2_planner* p) {
   const tdmpc2_dims& d = p->d;
-  if (!p->all_fused || d.action_dim > 64 || d.num_bins > 128 || d.num_bins < 1 || 6 * d.horizon + 9 > kPPMaxSteps) return false;
+  if (d.episodic || !p->all_fused || d.action_dim > 64 || d.num_bins > 128 || d.num_bins < 1 || 6 * d.horizon + 9 > kPPMaxSteps) return false;
   if (d.num_samples % kTileM != 0 || (d.latent_dim + d.task_dim) % 8 != 0 || (d.latent_dim + d.task_dim) / 8 > kEpiThreads) return false;
   if (d.simnorm_dim != 8) return false;
   for (size_t i = static_cast<size_t>(p->li_dyn); i < p->layers.size(); ++i) {
@@ -465,9 +471,16 @@ static bool pp_eligible(const tdmpc2_planner* p) {
 
 static int launch_plan(tdmpc2_planner* p, const PlanParams& prm, int ntiles, cudaStream_t st) {
   const int eng = p->engine == TDMPC2_ENGINE_SIMT ? 1 : 0;
+  // episodic models: the rollout modes run the instantiations that carry the termination head
+  const bool epi = p->d.episodic && (prm.mode == MODE_ITER || prm.mode == MODE_VALUE);
   if (!p->smem_attr_set[eng]) {
-    if (eng == 0) CUDA_TRY(cudaFuncSetAttribute(plan_kernel<ENGINE_TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    else CUDA_TRY(cudaFuncSetAttribute(plan_kernel<ENGINE_SIMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    if (eng == 0) {
+      CUDA_TRY(cudaFuncSetAttribute(plan_kernel<ENGINE_TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      CUDA_TRY(cudaFuncSetAttribute(plan_kernel<ENGINE_TC, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    } else {
+      CUDA_TRY(cudaFuncSetAttribute(plan_kernel<ENGINE_SIMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      CUDA_TRY(cudaFuncSetAttribute(plan_kernel<ENGINE_SIMT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    }
     p->smem_attr_set[eng] = true;
   }
   int grid = std::min(ntiles, p->nslots);
@@ -499,6 +512,7 @@ static int launch_plan(tdmpc2_planner* p, const PlanParams& prm, int ntiles, cud
   if (pair) {
     if (!p->smem_attr_pair) {
       CUDA_TRY(cudaFuncSetAttribute(plan_kernel<ENGINE_TC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      CUDA_TRY(cudaFuncSetAttribute(plan_kernel<ENGINE_TC, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
       p->smem_attr_pair = true;
     }
     grid &= ~1;
@@ -508,9 +522,15 @@ static int launch_plan(tdmpc2_planner* p, const PlanParams& prm, int ntiles, cud
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, plan_kernel<ENGINE_TC, true>, prm2));
-  } else if (eng == 0) plan_kernel<ENGINE_TC><<<grid, kThreads, kSmemBytes, st>>>(prm2);
-  else plan_kernel<ENGINE_SIMT><<<grid, kThreads, kSmemBytes, st>>>(prm2);
+    if (epi) CUDA_TRY(cudaLaunchKernelEx(&cfg, plan_kernel<ENGINE_TC, true, true>, prm2));
+    else CUDA_TRY(cudaLaunchKernelEx(&cfg, plan_kernel<ENGINE_TC, true>, prm2));
+  } else if (eng == 0) {
+    if (epi) plan_kernel<ENGINE_TC, false, true><<<grid, kThreads, kSmemBytes, st>>>(prm2);
+    else plan_kernel<ENGINE_TC><<<grid, kThreads, kSmemBytes, st>>>(prm2);
+  } else {
+    if (epi) plan_kernel<ENGINE_SIMT, false, true><<<grid, kThreads, kSmemBytes, st>>>(prm2);
+    else plan_kernel<ENGINE_SIMT><<<grid, kThreads, kSmemBytes, st>>>(prm2);
+  }
   CUDA_TRY(cudaGetLastError());
   p->launches += 1;
   return 0;

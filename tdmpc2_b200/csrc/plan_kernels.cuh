@@ -82,7 +82,7 @@ enum Engine { ENGINE_TC = 0, ENGINE_SIMT = 1 };
 // X = [z | emb | a] input planes; H = hidden planes.  ONE hidden buffer is enough: a layer's epilogue only runs after
 // every MMA of its GEMM has consumed the A operand, so layer 1 overwrites its own input in place.
 enum Buf { BUF_X = 0, BUF_H1 = 1 };
-enum Epi { EPI_LN_MISH = 0, EPI_LN_SIMNORM = 1, EPI_TWOHOT = 2, EPI_PI = 3, EPI_RAW = 4 };
+enum Epi { EPI_LN_MISH = 0, EPI_LN_SIMNORM = 1, EPI_TWOHOT = 2, EPI_PI = 3, EPI_RAW = 4, EPI_TERM = 5 };
 enum HeadKind { HEAD_REWARD = 0, HEAD_Q1 = 1, HEAD_Q2 = 2 };
 
 struct LayerDev {
@@ -124,6 +124,7 @@ struct PlanParams {
   // MODE_LAYER
   int dbg_layer, dbg_mode, dbg_rows; const float* dbg_x; float* dbg_y;
   long long* prof;   // optional [gridDim.x][16] cycle counters (diagnostics), or nullptr
+  int li_term;       // first of the 3 termination-head layers (cfg.episodic, world_model.py:28), or -1
 };
 
 // What a layer's epilogue has to do besides the activation itself.
@@ -220,6 +221,7 @@ struct Ctx {
   float* part;              // [2][2][128]      LayerNorm partials (fused path)
   float* G;                 // [128] discounted reward sum
   float* q1;                // [128] first Q head
+  float* term;              // [128] sticky termination flag of the row (episodic models, tdmpc2.py:126-134)
   int* flags;               // small ints
   int* rowenv;              // [128]
   uint32_t tmem_base;
@@ -286,14 +288,17 @@ __device__ __forceinline__ float sample_action(const PlanParams& P, int e, int t
 
 // ------------------------------------------------------------------------------------ shared per-row commits
 // Value bookkeeping of _estimate_value (tdmpc2.py:128-136) for one row; called by exactly one thread per row.
+template <bool EPISODIC>
 __device__ __forceinline__ void head_commit(const PlanParams& P, Ctx& c, const EpiArgs& ea, int r, float val) {
+  // discount * (1 - termination), tdmpc2.py:130,136 (termination is identically 0 unless cfg.episodic)
+  const float disc = EPISODIC ? __fmul_rn(ea.disc, __fsub_rn(1.f, c.term[r])) : ea.disc;
   if (ea.head == HEAD_REWARD) {
-    c.G[r] = __fadd_rn(c.G[r], __fmul_rn(ea.disc, val));              // G + discount * reward
+    c.G[r] = __fadd_rn(c.G[r], __fmul_rn(disc, val));                 // G + discount * reward
   } else if (ea.head == HEAD_Q1) {
     c.q1[r] = val;
   } else {
     const float qavg = __fmul_rn(__fadd_rn(c.q1[r], val), 0.5f);      // Q.sum(0) / 2
-    float v = __fadd_rn(c.G[r], __fmul_rn(ea.disc, qavg));            // G + discount * Q
+    float v = __fadd_rn(c.G[r], __fmul_rn(disc, qavg));               // G + discount * Q
     if (P.mode == MODE_ITER) v = nan_to_num0(v);                        // tdmpc2.py:184
     const RowMap rm = map_row(P, ea.tile, r);
     if (rm.env >= 0) {
@@ -301,6 +306,12 @@ __device__ __forceinline__ void head_commit(const PlanParams& P, Ctx& c, const E
       dst[static_cast<size_t>(rm.env) * P.N + rm.idx] = v;
     }
   }
+}
+// termination = clip(termination + (sigmoid(logit) > 0.5), max=1)  (tdmpc2.py:133-134, world_model.py:132-141).
+// torch's fp32 sigmoid returns exactly 0.5 for |x| < ~3e-8, so "> 0.5" is evaluated on the same expression.
+__device__ __forceinline__ void term_commit(Ctx& c, int r, float logit) {
+  const float sg = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-logit)));
+  c.term[r] = fminf(__fadd_rn(c.term[r], sg > 0.5f ? 1.f : 0.f), 1.f);
 }
 // a = tanh(mean + eps * exp(log_std)) for one (row, action dim)  (world_model.py:151-174)
 __device__ __forceinline__ float pi_action(const PlanParams& P, float mu, float ls, float eps, int task, int a) {
@@ -629,6 +640,7 @@ __device__ __forceinline__ float two_hot_inv_row(const PlanParams& P, Ctx& c, co
   return symexp_f(acc);
 }
 
+template <bool EPISODIC>
 __device__ __forceinline__ void rows_head(const PlanParams& P, Ctx& c, const LayerDev& ly, const EpiArgs& ea) {
   float* myrow = c.rowbuf + c.warp * kMaxHeadCols;
   __half* xhi = plane_ptr(P, c.slot, BUF_X, 0);
@@ -643,9 +655,11 @@ __device__ __forceinline__ void rows_head(const PlanParams& P, Ctx& c, const Lay
       continue;
     }
     head_row_to_smem(P, c, ly, r, myrow);
-    if (ea.kind == EPI_TWOHOT) {
+    if (EPISODIC && ea.kind == EPI_TERM) {
+      if (c.lane == 0) term_commit(c, r, myrow[0]);
+    } else if (ea.kind == EPI_TWOHOT) {
       const float v = two_hot_inv_row(P, c, myrow);
-      if (c.lane == 0) head_commit(P, c, ea, r, v);
+      if (c.lane == 0) head_commit<EPISODIC>(P, c, ea, r, v);
     } else if (ea.kind == EPI_PI) {
       const RowMap rm = map_row(P, ea.tile, r);
       const int e = rm.env < 0 ? 0 : rm.env, idx = rm.env < 0 ? 0 : rm.idx;
@@ -1044,6 +1058,7 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
 // Head epilogues (plain Linear outputs, Npad <= 256 so the accumulator is chunk 0 only).
 // Two-hot heads with <= 128 bins and pi heads with <= 64 action dims are spread over all four column groups
 // (32 bins / 16 action dims per group); anything larger runs on column group 0 alone.
+template <bool EPISODIC>
 __device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, const LayerDev& ly, const EpiArgs& ea) {
   const EpiThread et = epi_thread(c);
   const float inv_scale = ly.inv_scale;
@@ -1097,8 +1112,14 @@ __device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, cons
       float S = 0.f, Acc = 0.f;
 #pragma unroll
       for (int g = 0; g < kEpiGroups; ++g) { S += c.part[(kEpiGroups + g) * kTileM + et.row]; Acc += xch[g * kTileM + et.row]; }
-      head_commit(P, c, ea, et.row, symexp_f(__fdiv_rn(Acc, S)));
+      head_commit<EPISODIC>(P, c, ea, et.row, symexp_f(__fdiv_rn(Acc, S)));
     }
+  } else if (EPISODIC && ea.kind == EPI_TERM) {
+    // termination head (one output column): group 0's thread of each row updates the row's sticky flag
+    uint32_t v[16];
+    ptx::tmem_ld_32x16(et.taddr, v);
+    ptx::tmem_ld_wait();
+    term_commit(c, et.row, fmaf(__uint_as_float(v[0]), inv_scale, sb[0]));
   } else if (ea.kind == EPI_TWOHOT) {
     const float* bins = c.vec + kFusedMaxN;
     const int B = P.B;
@@ -1124,7 +1145,7 @@ __device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, cons
           acc = fmaf(e, bins[c0 + i], acc);
         }
     }
-    head_commit(P, c, ea, et.row, symexp_f(__fdiv_rn(acc, ssum)));
+    head_commit<EPISODIC>(P, c, ea, et.row, symexp_f(__fdiv_rn(acc, ssum)));
   } else if (ea.kind == EPI_PI) {
     const RowMap rm = map_row(P, ea.tile, et.row);
     const int e = rm.env < 0 ? 0 : rm.env, idx = rm.env < 0 ? 0 : rm.idx;
@@ -1199,7 +1220,7 @@ __device__ __forceinline__ void publish_planes() {
 
 // ------------------------------------------------------------------------------------ one layer
 // GEMM + epilogue; on return the epilogue's outputs are published (CTA-synchronised, TMA-visible).
-template <int ENGINE>
+template <int ENGINE, bool EPISODIC>
 __device__ __forceinline__ void run_layer(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf, const EpiArgs& ea) {
   const bool is_ln = (ea.kind == EPI_LN_MISH || ea.kind == EPI_LN_SIMNORM);
   const bool fused = (ENGINE == ENGINE_TC) && (ly.Npad <= kFusedMaxN) && (is_ln || ly.Npad <= kNch) &&
@@ -1213,7 +1234,7 @@ __device__ __forceinline__ void run_layer(const PlanParams& P, Ctx& c, const Lay
       if (c.lane == 0 && (!c.cg2 || c.rank == 0)) tc_mma<true>(P, c, ly);
     } else if (c.warp >= kEpiWarp0) {
       if (is_ln) epi_ln_fused(P, c, ly, ea);
-      else epi_head_fused(P, c, ly, ea);
+      else epi_head_fused<EPISODIC>(P, c, ly, ea);
       ptx::tc_fence_before();
     }
     c.pf1 += clock64() - tl;
@@ -1222,7 +1243,7 @@ __device__ __forceinline__ void run_layer(const PlanParams& P, Ctx& c, const Lay
     if (ENGINE == ENGINE_TC) gemm_tc_wide(P, c, ly, srcbuf);
     else gemm_simt(P, c, ly, srcbuf);
     if (is_ln) rows_ln_act(P, c, ly, ea);
-    else rows_head(P, c, ly, ea);
+    else rows_head<EPISODIC>(P, c, ly, ea);
   }
   const long long tp = clock64();
   // LN layers that went out through TMA stores wrote nothing through the generic proxy: the leaders have
@@ -1341,8 +1362,11 @@ __device__ __forceinline__ void refit_env(const PlanParams& P, uint8_t* scratch,
 // CG2: CTA pairs (cluster of 2) run the GEMMs as tcgen05 cta_group::2 MMAs (M = 256: 128 rows of each CTA's own
 // tile; each CTA streams only half of every weight tile).  Only MODE_ITER with an even number of tiles per
 // environment and every layer on the fused path is launched this way.
-template <int ENGINE, bool CG2 = false>
+// EPISODIC (cfg.episodic, single-task models): every rollout step gains the 3-layer termination head on z_{t+1}
+// and the value bookkeeping its sticky (1 - termination) factor (tdmpc2.py:126-136); compiled out otherwise.
+template <int ENGINE, bool CG2 = false, bool EPISODIC = false>
 __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant__ PlanParams P) {
+  constexpr int SPT = EPISODIC ? 9 : 6;      // layer steps per rollout time step (ITER / VALUE)
   extern __shared__ uint8_t smem_raw[];
   Ctx c;
   {
@@ -1359,7 +1383,8 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
     c.tmem_ptr = reinterpret_cast<uint32_t*>(c.facc + 2);
     c.flags = reinterpret_cast<int*>(c.tmem_ptr + 1);          // [8]
     c.G = reinterpret_cast<float*>(ctrl + 256);                 // [128]  (18 mbarriers + tmem ptr + flags live below 256)
-    c.q1 = c.G + kTileM;                                        // [128]  (ends at ctrl + 1280 <= kSmemCtrl)
+    c.q1 = c.G + kTileM;                                        // [128]  (ends at ctrl + 1280)
+    c.term = c.q1 + kTileM;                                     // [128]  (ends at ctrl + 1792 <= kSmemCtrl)
     c.rowbuf = reinterpret_cast<float*>(ctrl + kSmemCtrl);
     c.rowenv = reinterpret_cast<int*>(ctrl + kSmemCtrl + kSmemRowBuf);
     c.vec = reinterpret_cast<float*>(ctrl + kSmemCtrl + kSmemRowBuf + kSmemRowEnv);
@@ -1409,7 +1434,10 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
        tile += gridDim.x) {
     // ---------------- tile set-up: fill the input planes of X ----------------
     const long long t_setup = clock64();
-    for (int r = threadIdx.x; r < kTileM; r += kThreads) { rowenv[r] = map_row(P, tile, r).env; c.G[r] = 0.f; c.q1[r] = 0.f; }
+    for (int r = threadIdx.x; r < kTileM; r += kThreads) {
+      rowenv[r] = map_row(P, tile, r).env; c.G[r] = 0.f; c.q1[r] = 0.f;
+      if (EPISODIC) c.term[r] = 0.f;
+    }
     __syncthreads();
     __half* xhi = plane_ptr(P, c.slot, BUF_X, 0);
     __half* xlo = plane_ptr(P, c.slot, BUF_X, 1);
@@ -1487,12 +1515,12 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
     // ---------------- the tile's layer program: ONE run_layer call site ----------------
     //   ENCODE : enc.0 .. enc.(n-1)
     //   PRIOR  : per t: pi.0-2 [, dyn.0-2 if t < H-1]
-    //   ITER   : per t: [a_t -> X] rew.0-2, dyn.0-2 ; then pi.0-2, q_a.0-2, q_b.0-2
+    //   ITER   : per t: [a_t -> X] rew.0-2, dyn.0-2 [, term.0-2 if EPISODIC] ; then pi.0-2, q_a.0-2, q_b.0-2
     int nsteps;
     if (P.mode == MODE_LAYER) nsteps = 1;
     else if (P.mode == MODE_ENCODE) nsteps = P.num_enc;
     else if (P.mode == MODE_PRIOR) nsteps = 6 * (P.H - 1) + 3;
-    else nsteps = 6 * P.H + 9;
+    else nsteps = SPT * P.H + 9;
     const float* dpow = P.disc_pow + static_cast<size_t>(task_tile) * (P.H + 1);
     const int* qi = (P.mode == MODE_ITER || P.mode == MODE_VALUE) ? P.qidx + static_cast<size_t>(env_tile) * 2 : nullptr;
 
@@ -1512,13 +1540,13 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
         else { ea.kind = EPI_LN_MISH; ea.dstbuf = BUF_H1; }
       } else {
         // which MLP, which of its 3 layers
-        int mlp, l, t = 0;       // mlp: 0 reward, 1 dynamics, 2 pi, 3 q_a, 4 q_b
+        int mlp, l, t = 0;       // mlp: 0 reward, 1 dynamics, 2 pi, 3 q_a, 4 q_b, 5 termination
         if (P.mode == MODE_PRIOR) {
           t = sidx / 6; l = sidx % 6;
           mlp = l < 3 ? 2 : 1; l %= 3;
-        } else if (sidx < 6 * P.H) {
-          t = sidx / 6; l = sidx % 6;
-          mlp = l < 3 ? 0 : 1; l %= 3;
+        } else if (sidx < SPT * P.H) {
+          t = sidx / SPT; l = sidx % SPT;
+          mlp = l < 3 ? 0 : ((EPISODIC && l >= 6) ? 5 : 1); l %= 3;
           if (mlp == 0 && l == 0) {
             // X action columns <- a_t  (tdmpc2.py:176-181)
             const long long t_act = clock64();
@@ -1561,11 +1589,12 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
             c.pf5 += clock64() - t_act;
           }
         } else {
-          const int u = sidx - 6 * P.H;
+          const int u = sidx - SPT * P.H;
           mlp = 2 + u / 3; l = u % 3;
         }
         src = l == 0 ? BUF_X : BUF_H1;
-        const int base = mlp == 0 ? P.li_rew : mlp == 1 ? P.li_dyn : mlp == 2 ? P.li_pi : P.li_q + 3 * qi[mlp - 3];
+        const int base = (EPISODIC && mlp == 5) ? P.li_term
+                         : mlp == 0 ? P.li_rew : mlp == 1 ? P.li_dyn : mlp == 2 ? P.li_pi : P.li_q + 3 * qi[mlp - 3];
         li = base + l;
         if (l < 2) {
           ea.kind = EPI_LN_MISH; ea.dstbuf = BUF_H1;
@@ -1581,12 +1610,14 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
           } else {                             // eps = noise_pi[e, n, :]
             ea.eps_base = P.noise_pi; ea.eps_rows = P.N;
           }
+        } else if (EPISODIC && mlp == 5) {     // termination(z_{t+1})  (world_model.py:132-141), input [z | emb]
+          ea.kind = EPI_TERM;
         } else {                               // Q heads (world_model.py:186-216)
           ea.kind = EPI_TWOHOT; ea.head = (mlp == 3) ? HEAD_Q1 : HEAD_Q2; ea.disc = dpow[P.H];
         }
       }
       c.trace_step = (tile == static_cast<int>(blockIdx.x)) ? sidx : (1 << 30);
-      run_layer<ENGINE>(P, c, LY[li], src, ea);
+      run_layer<ENGINE, EPISODIC>(P, c, LY[li], src, ea);
     }
 
     const long long t_refit = clock64();

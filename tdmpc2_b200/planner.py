@@ -185,6 +185,8 @@ class Planner:
             W.reward[i] = lin(f"_reward.{i}")
             W.pi[i] = lin(f"_pi.{i}")
             W.qs[i] = lin(f"_Qs.params.{i}")
+            if cfg.episodic:
+                W.termination[i] = lin(f"_termination.{i}")      # world_model.py:28
         if cfg.multitask:
             emb, masks = f("_task_emb.weight"), f("_action_masks")
             keep.extend([emb, masks])

@@ -41,6 +41,7 @@ def head_layout(cfg: Config) -> Dict[str, Dict]:
         "_reward": dict(dims=mlp_dims(D, 2 * [M], B), ln_last=False),      # world_model.py:27
         "_pi": dict(dims=mlp_dims(L + T, 2 * [M], 2 * A), ln_last=False),  # world_model.py:29
         "_Qs": dict(dims=mlp_dims(D, 2 * [M], B), ln_last=False),          # world_model.py:30
+        "_termination": dict(dims=mlp_dims(L + T, 2 * [M], 1), ln_last=False),   # world_model.py:28 (cfg.episodic only)
     }
 
 
@@ -92,6 +93,11 @@ def synth_state_dict(cfg: Config, seed: int = 1, perturb: bool = False,
         sd["_Qs.params." + sub] = v
         sd["_detach_Qs_params." + sub] = v            # shares storage (world_model.py:40)
         sd["_target_Qs_params." + sub] = v.clone()    # world_model.py:41
+    if cfg.episodic:     # drawn last: an episodic model shares every other tensor with the non-episodic one of the same seed
+        fill("_termination", lay["_termination"]["dims"], False)
+        # sigma 0.16 instead of 0.02 on the single output row: with init-scale weights every logit has the sign of
+        # the bias and all samples would (not) terminate together; this spreads them across the 0.5 boundary
+        sd["_termination.2.weight"] = sd["_termination.2.weight"] * 8.0
     sd["log_std_min"] = torch.tensor(float(cfg.log_std_min))
     sd["log_std_dif"] = torch.tensor(float(cfg.log_std_max)) - sd["log_std_min"]
     return sd

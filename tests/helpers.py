@@ -16,6 +16,8 @@ def load_golden(name):
     cfg = workload(str(f["workload"]), **over)
     sd = synth_state_dict(cfg, seed=int(f["weight_seed"]), perturb=bool(f["perturb"]),
                           emb_scale=float(f["emb_scale"]))
+    if "term_bias" in f.files:      # episodic fixtures: the calibrated termination bias they were minted with
+        sd["_termination.2.bias"] = torch.full_like(sd["_termination.2.bias"], float(f["term_bias"]))
     chk = state_dict_checksum(sd)
     assert abs(chk - float(f["weight_checksum"])) <= 1e-9 * abs(chk), \
         "synthetic weights differ from the ones the golden vectors were minted with (torch RNG drift?)"

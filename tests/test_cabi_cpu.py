@@ -25,14 +25,15 @@ def test_library_exports_every_header_symbol(lib):
     assert declared == set(_cabi.SYMBOLS), declared ^ set(_cabi.SYMBOLS)
     for s in declared:
         assert hasattr(lib, s), s
-    assert lib.tdmpc2_abi_version() == 1
+    want = int(re.search(r"#define TDMPC2_B200_ABI_VERSION (\d+)", hdr).group(1))
+    assert lib.tdmpc2_abi_version() == want == _cabi.ABI_VERSION
 
 
 def test_struct_layout_matches_header():
     from tdmpc2_b200 import _cabi
     assert C.sizeof(_cabi.Dims) == 18 * 4 + 5 * 4
     assert C.sizeof(_cabi.Linear) == 4 * 8
-    assert C.sizeof(_cabi.Weights) == 8 + (_cabi.MAX_ENC_LAYERS + 12) * 32 + 4 * 8
+    assert C.sizeof(_cabi.Weights) == 8 + (_cabi.MAX_ENC_LAYERS + 12) * 32 + 4 * 8 + 3 * 32   # ... + termination[3]
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -49,8 +50,12 @@ def test_no_cpu_fallback(lib):
     h = C.c_void_p()
     rc = lib.tdmpc2_planner_create(C.byref(d), C.byref(h))
     assert rc == -2 and b"no CUDA device" in lib.tdmpc2_last_error()       # TDMPC2_ERR_NO_DEVICE
-    d.episodic = 1
+    d.episodic = 1                                                           # termination head: accepted (single-task)
+    assert lib.tdmpc2_planner_create(C.byref(d), C.byref(h)) == -2
+    d.task_dim, d.num_tasks = 16, 3                                          # ... but not multi-task (world_model.py:136)
     assert lib.tdmpc2_planner_create(C.byref(d), C.byref(h)) == -5          # TDMPC2_ERR_UNSUPPORTED
+    d.episodic = 2
+    assert lib.tdmpc2_planner_create(C.byref(d), C.byref(h)) == -1          # TDMPC2_ERR_INVALID
 
 
 def test_world_model_state_dict_layout():
@@ -58,8 +63,8 @@ def test_world_model_state_dict_layout():
     from tdmpc2_b200.config import workload
     from tdmpc2_b200.synth import synth_state_dict
     from tdmpc2_b200.world_model import WorldModel, convert_legacy_checkpoint
-    for wl in ("tiny", "tiny-mt"):
-        cfg = workload(wl)
+    for wl, over in (("tiny", {}), ("tiny-mt", {}), ("tiny", {"episodic": True})):
+        cfg = workload(wl, **over)
         m = WorldModel(cfg)
         sd = m.state_dict()
         want = synth_state_dict(cfg, seed=3, perturb=True)

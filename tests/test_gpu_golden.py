@@ -8,7 +8,10 @@ from helpers import load_golden, stable_positions, boundary_separated
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["tiny", "tiny_mt", "c1_dog5m", "c3_humanoid48m_e1", "c4_mt80_317m_e1"]
+CASES = ["tiny", "tiny_mt", "c1_dog5m", "c3_humanoid48m_e1", "c4_mt80_317m_e1", "tiny_episodic", "c1_dog5m_episodic"]
+# A termination decision flips a trajectory value by O(1): samples whose termination logit lies within this margin
+# of the 0.5 boundary (by the oracle, which is bit-identical to the reference) are not compared.
+TERM_MARGIN = 2e-5
 # Absolute tolerance on O(1) trajectory values.  The 3-pass fp16-split GEMM carries ~22 bits per product, but the
 # tensor core's fp32 accumulator truncates on every K=16 step, so the error grows with the reduction length:
 # K <= 1792 (5M/48M presets): observed <= 1e-5; K = 4096 (317M): observed 1.1e-4.
@@ -38,13 +41,23 @@ def test_agent_matches_reference_golden(name):
         torch.cuda.synchronize()
         assert action.shape == (cfg.action_dim,)                    # reference return shape
         values = tr["values"][0].cpu()
+        decided = torch.ones(cfg.iterations, cfg.num_samples, dtype=torch.bool)
+        if cfg.episodic:
+            from oracle.plan_oracle import plan_oracle
+            want = plan_oracle(cfg, sd, c["obs"][None], t0=[c["t0"]], prev_mean=c["prev_mean"][None], noise=n,
+                               eval_mode=c["eval_mode"])
+            assert torch.equal(want.values[0], c["values"])          # the oracle IS the reference here (bit-exact)
+            decided = want.term_margin[0] > TERM_MARGIN
         clean = True
         for it in range(cfg.iterations):
             if not clean:
                 break
             tol = VALUE_TOL.get(name, 5e-5)
-            err = (values[it] - c["values"][it]).abs().max().item()
+            err = (values[it] - c["values"][it]).abs()[decided[it]].max().item()
             assert err < tol, f"{name}: values it={it} err={err:.3e}"
+            if not bool(decided[it].all()):
+                clean = False                    # a knife-edge termination may have moved one sample across the elite set
+                continue
             stable = stable_positions(c["values"][it], K, 2 * tol)
             assert torch.equal(tr["elite_idx"][0, it].cpu()[stable], c["elite_idx"][it][stable]), f"top-k it={it}"
             clean = bool(boundary_separated(c["values"][it], K, 2 * tol))

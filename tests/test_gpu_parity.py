@@ -36,15 +36,18 @@ def _layer_list(cfg):
     for h in range(cfg.num_q):
         for i in range(3):
             out.append((li, f"_Qs.params.{i}", h, i < 2, False)); li += 1
+    if cfg.episodic:                                   # appended last by the packer (include/tdmpc2_b200.h)
+        for i in range(3):
+            out.append((li, f"_termination.{i}", None, i < 2, False)); li += 1
     return out
 
 
 @pytest.mark.parametrize("engine", ENGINES)
-@pytest.mark.parametrize("wl", ["tiny", "tiny-mt", "c1", "tiny-wide"])
+@pytest.mark.parametrize("wl", ["tiny", "tiny-mt", "c1", "tiny-wide", "tiny-episodic"])
 def test_fused_layer_matches_fp64(engine, wl):
     """One packed layer (GEMM on split fp16 operands + bias + LN + Mish/SimNorm) vs float64.
     Tolerance: 1e-5 abs + 1e-5 rel -- fp32 round-off level (3-pass fp16 split carries ~22 bits)."""
-    cfg = workload(wl)
+    cfg = workload("tiny", episodic=True) if wl == "tiny-episodic" else workload(wl)
     sd = synth_state_dict(cfg, seed=5, perturb=True)
     pl = _planner(cfg, 2, engine, sd)
     g = torch.Generator().manual_seed(0)
@@ -250,3 +253,86 @@ def test_ping_pong_engine_matches_oracle_and_pair_engine(perturb):
             assert torch.allclose(mean_pp[e, it], want.iter_mean[e, it], atol=1e-4, rtol=0), f"mean env={e} it={it}"
             assert torch.allclose(std_pp[e, it], want.iter_std[e, it], atol=1e-4, rtol=0), f"std env={e} it={it}"
     assert n_checked > 0
+
+
+# ------------------------------------------------------------------------------------ cfg.episodic (termination head)
+TERM_MARGIN = 2e-5     # |termination logit| below this: the 0.5 decision is not well defined under ~1e-6 kernel error
+
+
+@pytest.mark.parametrize("engine", ["simt", "tcgen05", "tcgen05x2"])
+@pytest.mark.parametrize("wl,E", [("tiny", 2), ("c1", 2)])
+def test_episodic_plan_matches_oracle(engine, wl, E):
+    """Episodic models run the termination head on z_{t+1} inside the fused rollout and carry the sticky
+    (1 - termination) factor through the value (tdmpc2.py:126-136).  Same tolerances as the non-episodic test;
+    samples whose termination logit is within TERM_MARGIN of the decision boundary are excluded, and an environment
+    stops being compared after the first iteration that contains such a sample."""
+    from oracle.plan_oracle import balance_termination, draw_noise as oracle_noise, plan_oracle
+    cfg = workload(wl, num_envs=E, episodic=True)
+    sd = synth_state_dict(cfg, seed=21, perturb=True)
+    balance_termination(cfg, sd)
+    g = torch.Generator().manual_seed(8)
+    obs = torch.randn(E, cfg.obs_shape["state"][0], generator=g)
+    prev = 0.3 * torch.randn(E, cfg.horizon, cfg.action_dim, generator=g)
+    t0 = [bool(i % 2) for i in range(E)]
+    noise = oracle_noise(cfg, 44, E)
+    want = plan_oracle(cfg, sd, obs, task=None, t0=t0, prev_mean=prev, noise=noise)
+    assert 0.02 < float((want.values.abs() > 0).float().mean())             # sanity: not degenerate
+
+    pl = _planner(cfg, E, engine, sd)
+    action, new_mean, tr = pl.plan(obs.cuda().contiguous(), None, torch.tensor(t0, dtype=torch.uint8).cuda(),
+                                   prev.cuda().contiguous(), _to_gpu_noise(noise, False), trace=True)
+    torch.cuda.synchronize()
+    cpu = lambda t: t.detach().cpu()
+    K = cfg.num_elites
+    n_values = n_idx = n_refit = 0
+    for e in range(E):
+        for it in range(cfg.iterations):
+            decided = want.term_margin[e, it] > TERM_MARGIN
+            v_want, v_got = want.values[e, it], cpu(tr["values"][e, it])
+            err = (v_got - v_want).abs()[decided]
+            assert float(err.max()) < 5e-5, f"values env={e} it={it} err={float(err.max()):.3e}"
+            n_values += int(decided.sum())
+            if not bool(decided.all()):
+                break                                  # a flipped sample may have changed the elite set: stop comparing this env
+            stable = stable_positions(v_want, K, 1e-4)
+            assert torch.equal(cpu(tr["elite_idx"][e, it])[stable], want.elite_idx[e, it][stable]), f"top-k env={e} it={it}"
+            n_idx += int(stable.sum())
+            if not boundary_separated(v_want, K, 1e-4):
+                break
+            assert torch.allclose(cpu(tr["iter_mean"][e, it]), want.iter_mean[e, it], atol=1e-4, rtol=0), f"mean env={e} it={it}"
+            assert torch.allclose(cpu(tr["iter_std"][e, it]), want.iter_std[e, it], atol=1e-4, rtol=0), f"std env={e} it={it}"
+            n_refit += 1
+    assert n_values > 0 and n_idx > 0 and n_refit > 0, (n_values, n_idx, n_refit)
+    # the termination head really acted: a planner for the same weights without it gives different values
+    cfg0 = workload(wl, num_envs=E)
+    pl0 = _planner(cfg0, E, engine, {k: v for k, v in sd.items() if not k.startswith("_termination")})
+    _, _, tr0 = pl0.plan(obs.cuda().contiguous(), None, torch.tensor(t0, dtype=torch.uint8).cuda(), prev.cuda().contiguous(),
+                         _to_gpu_noise(noise, False), trace=True)
+    torch.cuda.synchronize()
+    assert float((cpu(tr0["values"][:, 0]) - cpu(tr["values"][:, 0])).abs().max()) > 1e-3
+
+
+@pytest.mark.parametrize("engine", ["simt", "tcgen05"])
+def test_episodic_estimate_value_matches_oracle(engine):
+    from oracle.plan_oracle import OracleModel, balance_termination, estimate_value
+    cfg = workload("tiny", num_envs=2, episodic=True)
+    sd = synth_state_dict(cfg, seed=9, perturb=True)
+    balance_termination(cfg, sd)
+    E, N, H, A, L = 2, cfg.num_samples, cfg.horizon, cfg.action_dim, cfg.latent_dim
+    g = torch.Generator().manual_seed(1)
+    z = torch.softmax(torch.randn(E, N, L // 8, 8, generator=g), -1).view(E, N, L)
+    actions = torch.rand(E, H, N, A, generator=g) * 2 - 1
+    eps = torch.randn(E, N, A, generator=g)
+    qidx = torch.tensor([[0, 2], [1, 0]])
+    model = OracleModel(cfg, sd)
+    want, decided = [], []
+    for e in range(E):
+        info = {}
+        want.append(estimate_value(model, z[e], actions[e], None, eps[e], qidx[e], info).squeeze(1))
+        decided.append(info["term_margin"] > TERM_MARGIN)
+    want, decided = torch.stack(want), torch.stack(decided)
+    pl = _planner(cfg, E, engine, sd)
+    got = pl.estimate_value(z.cuda().contiguous(), actions.cuda().contiguous(), None, eps.cuda().contiguous(),
+                            qidx.to(torch.int32).cuda().contiguous()).cpu()
+    assert decided.float().mean() > 0.99
+    assert float((got - want).abs()[decided].max()) < 5e-5

@@ -6,7 +6,7 @@ import torch
 from oracle.plan_oracle import draw_noise, plan_oracle
 from helpers import load_golden, stable_positions, boundary_separated
 
-CASES = ["tiny", "tiny_mt", "c1_dog5m",
+CASES = ["tiny", "tiny_mt", "c1_dog5m", "tiny_episodic", "c1_dog5m_episodic",
          pytest.param("c3_humanoid48m_e1", marks=pytest.mark.slow),
          pytest.param("c4_mt80_317m_e1", marks=pytest.mark.slow)]
 
@@ -66,3 +66,25 @@ def test_batched_oracle_is_independent_envs():
     for e in range(E):
         a = cfg.action_dims[task[e]]
         assert torch.all(tr.action[e, a:] == 0) and torch.all(tr.mean[e, :, a:] == 0)
+
+
+def test_episodic_oracle_properties():
+    """cfg.episodic (tdmpc2.py:126-136): a never-terminating head reproduces the non-episodic values bit for bit,
+    an always-terminating head leaves only the first discounted reward."""
+    from oracle.plan_oracle import OracleModel, estimate_value, two_hot_inv
+    from tdmpc2_b200.config import workload
+    from tdmpc2_b200.synth import synth_state_dict
+    cfg_e, cfg_0 = workload("tiny", episodic=True), workload("tiny")
+    sd = synth_state_dict(cfg_e, seed=4, perturb=True)
+    g = torch.Generator().manual_seed(2)
+    N = cfg_e.num_samples
+    z = torch.softmax(torch.randn(N, cfg_e.latent_dim // 8, 8, generator=g), -1).view(N, -1)
+    acts = torch.rand(cfg_e.horizon, N, cfg_e.action_dim, generator=g) * 2 - 1
+    eps, qidx = torch.randn(N, cfg_e.action_dim, generator=g), torch.tensor([1, 0])
+    base = estimate_value(OracleModel(cfg_0, sd), z, acts, None, eps, qidx)
+    sd["_termination.2.bias"] = torch.full((1,), -50.0)
+    assert torch.equal(estimate_value(OracleModel(cfg_e, sd), z, acts, None, eps, qidx), base)
+    sd["_termination.2.bias"] = torch.full((1,), 50.0)
+    m = OracleModel(cfg_e, sd)
+    first = two_hot_inv(m.reward(z, acts[0], None), cfg_e)
+    assert torch.equal(estimate_value(m, z, acts, None, eps, qidx), first)
