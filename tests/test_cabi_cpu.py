@@ -122,3 +122,10 @@ def test_world_model_forward_matches_oracle_model():
         assert torch.allclose(m.pi(z, task, eps=eps)[0], om.pi(z, 2, eps), atol=1e-6)
         q = m.Q(z, a, task, return_type="avg", qidx=torch.tensor([3, 1]))
         assert torch.allclose(q, om.Q_avg(z, a, 2, [3, 1]), atol=1e-5)
+
+
+def test_graft_entry_build():
+    """The driver's build check: __graft_entry__.build() compiles (or finds) the library, loads it, imports the package."""
+    import importlib
+    ge = importlib.import_module("__graft_entry__")
+    ge.build()
