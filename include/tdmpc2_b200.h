@@ -44,7 +44,7 @@ typedef enum tdmpc2_status {
   TDMPC2_ERR_NO_DEVICE = -2,   /* no CUDA device, or device is not sm_100      */
   TDMPC2_ERR_CUDA = -3,        /* a CUDA runtime / driver call failed          */
   TDMPC2_ERR_STATE = -4,       /* call order violated (e.g. plan before bind)  */
-  TDMPC2_ERR_UNSUPPORTED = -5  /* valid reference config this build lacks (episodic) */
+  TDMPC2_ERR_UNSUPPORTED = -5  /* config outside what the reference's planner itself accepts (multi-task episodic) */
 } tdmpc2_status;
 
 /* GEMM engine used by the fused MLP kernels. */
