@@ -154,7 +154,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default=None, choices=["tcgen05pp", "tcgen05x2", "tcgen05", "simt"])
+    ap.add_argument("--engine", default=None, choices=["tcgen05x2pf", "tcgen05pp", "tcgen05x2", "tcgen05", "simt"])
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--envs", type=int, default=None, help="environments per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

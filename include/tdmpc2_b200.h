@@ -54,10 +54,14 @@ typedef enum tdmpc2_engine {
   TDMPC2_ENGINE_TCGEN05_2SM = 2, /* as 0, but CEM iterations run on CTA pairs (tcgen05 cta_group::2, M = 256):
                                   each CTA streams half of every weight tile.  Falls back to 0 when a model has
                                   layers wider than TMEM or an odd number of 128-row tiles per environment */
-  TDMPC2_ENGINE_TCGEN05_PP = 3 /* as 2, but every CTA splits its tile into two 64-row halves (cta_group::2, M = 128)
+  TDMPC2_ENGINE_TCGEN05_PP = 3, /* as 2, but every CTA splits its tile into two 64-row halves (cta_group::2, M = 128)
                                   whose accumulators sit side by side in TMEM: the GEMM of one half overlaps the
                                   LayerNorm / head epilogue of the other.  Trunk layers must be 256 or 512 wide and
                                   heads at most 128 (the 5M preset); anything else runs as engine 2 */
+  TDMPC2_ENGINE_TCGEN05_2SM_PF = 4 /* as 2 (bit-identical results), but the TMA producer prefetches the next layer's first
+                                  weight chunks into the idle W ring during the epilogue, which then stages its output
+                                  in the A ring.  Episodic models or LayerNorm widths that are not multiples of 32
+                                  run as engine 2 */
 } tdmpc2_engine;
 
 /* Planner + model dimensions.  Mirrors the keys the reference reads from cfg:

@@ -295,7 +295,7 @@ extern "C" int tdmpc2_planner_set_profile(tdmpc2_planner* p, long long* device_b
 }
 extern "C" int tdmpc2_planner_set_engine(tdmpc2_planner* p, int engine) {
   if (!p || (engine != TDMPC2_ENGINE_TCGEN05 && engine != TDMPC2_ENGINE_SIMT && engine != TDMPC2_ENGINE_TCGEN05_2SM &&
-             engine != TDMPC2_ENGINE_TCGEN05_PP))
+             engine != TDMPC2_ENGINE_TCGEN05_PP && engine != TDMPC2_ENGINE_TCGEN05_2SM_PF))
     return fail(TDMPC2_ERR_INVALID, "bad engine");
   p->engine = engine;
   return 0;
@@ -469,6 +469,15 @@ static bool pp_eligible(const tdmpc2_planner* p) {
   return true;
 }
 
+// W prefetch (plan_kernel<..., WPF>): every LayerNorm layer of the CEM iteration must take the epilogue's fast path
+// (whole 32-column blocks out through TMA stores), which is the only one that stages in the A ring
+static bool wpf_eligible(const tdmpc2_planner* p) {
+  if (p->d.episodic || !p->all_fused) return false;
+  for (size_t i = static_cast<size_t>(p->li_dyn); i < p->layers.size(); ++i)
+    if (p->layers[i].has_ln && p->layers[i].N % 32 != 0) return false;
+  return true;
+}
+
 static int launch_plan(tdmpc2_planner* p, const PlanParams& prm, int ntiles, cudaStream_t st) {
   const int eng = p->engine == TDMPC2_ENGINE_SIMT ? 1 : 0;
   // episodic models: the rollout modes run the instantiations that carry the termination head
@@ -487,7 +496,8 @@ static int launch_plan(tdmpc2_planner* p, const PlanParams& prm, int ntiles, cud
   PlanParams prm2 = prm;
   prm2.prof = p->prof;
   // CTA-pair (cta_group::2) launch: CEM iterations only, whole pairs of tiles of one environment, fused layers only
-  const bool pair_engine = (p->engine == TDMPC2_ENGINE_TCGEN05_2SM || p->engine == TDMPC2_ENGINE_TCGEN05_PP);
+  const bool pair_engine = (p->engine == TDMPC2_ENGINE_TCGEN05_2SM || p->engine == TDMPC2_ENGINE_TCGEN05_PP ||
+                            p->engine == TDMPC2_ENGINE_TCGEN05_2SM_PF);
   if (p->engine == TDMPC2_ENGINE_TCGEN05_PP && prm.mode == MODE_ITER && (p->tiles_per_env % 2 == 0) && (ntiles % 2 == 0) &&
       pp_eligible(p)) {
     // ping-pong kernel (plan_pp.cuh): GEMM of one 64-row half overlaps the epilogue of the other
@@ -513,6 +523,7 @@ static int launch_plan(tdmpc2_planner* p, const PlanParams& prm, int ntiles, cud
     if (!p->smem_attr_pair) {
       CUDA_TRY(cudaFuncSetAttribute(plan_kernel<ENGINE_TC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
       CUDA_TRY(cudaFuncSetAttribute(plan_kernel<ENGINE_TC, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      CUDA_TRY(cudaFuncSetAttribute(plan_kernel<ENGINE_TC, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
       p->smem_attr_pair = true;
     }
     grid &= ~1;
@@ -523,6 +534,8 @@ static int launch_plan(tdmpc2_planner* p, const PlanParams& prm, int ntiles, cud
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     if (epi) CUDA_TRY(cudaLaunchKernelEx(&cfg, plan_kernel<ENGINE_TC, true, true>, prm2));
+    else if (p->engine == TDMPC2_ENGINE_TCGEN05_2SM_PF && wpf_eligible(p))
+      CUDA_TRY(cudaLaunchKernelEx(&cfg, plan_kernel<ENGINE_TC, true, false, true>, prm2));
     else CUDA_TRY(cudaLaunchKernelEx(&cfg, plan_kernel<ENGINE_TC, true>, prm2));
   } else if (eng == 0) {
     if (epi) plan_kernel<ENGINE_TC, false, true><<<grid, kThreads, kSmemBytes, st>>>(prm2);

@@ -227,6 +227,8 @@ struct Ctx {
   uint32_t tmem_base;
   int slot, warp, lane;
   int cg2, rank;             // CTA-pair mode (tcgen05 cta_group::2): pair rank 0 = leader issues the MMAs
+  int wpf;                   // W prefetch: the producer streams the NEXT layer's first weight chunks during the epilogue
+  uint32_t w_pref;           // (producer thread) weight chunks of the coming layer that are already in flight
   uint32_t w_ring, w_stride, w_lo_off;   // W ring geometry: 2 x 64 KiB (lo plane at +32 KiB) or, in pair mode, 4 x 32 KiB (+16 KiB)
   // pipeline counters (each role keeps its own; persist across layers / tiles)
   uint32_t pa_it, pw_it, ma_it, mw_it, a_it, d_it;
@@ -370,7 +372,7 @@ __device__ __forceinline__ void prod_load_w(Ctx& c, const CUtensorMap* tmW, cons
 }
 
 template <bool FUSED>
-__device__ __forceinline__ void tc_producer(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf) {
+__device__ __forceinline__ void tc_producer(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf, const LayerDev* next) {
   const int nkc = ly.Kpad / kKch;
   const int nnc = (ly.Npad + kNch - 1) / kNch;
   const CUtensorMap* tmA = (srcbuf == BUF_X) ? &P.tmX : &P.tmH;
@@ -378,9 +380,25 @@ __device__ __forceinline__ void tc_producer(const PlanParams& P, Ctx& c, const L
   const int arow_hi = plane_row0(P, c.slot, srcbuf, 0), arow_lo = plane_row0(P, c.slot, srcbuf, 1);
   TDMPC2_TRACE(P, c, 1);
   if (FUSED) {
+    uint32_t skip = c.wpf ? c.w_pref : 0u;     // chunks the previous layer's producer pass already requested
     for (int kc = 0; kc < nkc; ++kc) {
       prod_load_a(P, c, tmA, kc, arow_hi, arow_lo);
-      for (int nc = 0; nc < nnc; ++nc) prod_load_w(c, tmW, ly, kc, nc);
+      for (int nc = 0; nc < nnc; ++nc) {
+        if (skip) --skip;
+        else prod_load_w(c, tmW, ly, kc, nc);
+      }
+    }
+    if (c.wpf) {
+      // The W ring drains while this layer's last MMAs retire and then idles through the whole epilogue (which
+      // stages its output in the A ring in this mode): fill it with the head of the next layer's weight stream.
+      uint32_t n = 0;
+      if (next) {
+        const CUtensorMap* tmW2 = &P.tmW[next->wmap];
+        const int nkc2 = next->Kpad / kKch, nnc2 = (next->Npad + kNch - 1) / kNch;
+        for (int kc = 0; kc < nkc2 && n < c.w_ring; ++kc)
+          for (int nc = 0; nc < nnc2 && n < c.w_ring; ++nc) { prod_load_w(c, tmW2, *next, kc, nc); ++n; }
+      }
+      c.w_pref = n;
     }
   } else {
     for (int nc = 0; nc < nnc; ++nc)
@@ -477,7 +495,7 @@ __device__ __forceinline__ void tc_mma(const PlanParams& P, Ctx& c, const LayerD
 __device__ __forceinline__ void gemm_tc_wide(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf) {
   const int nnc = (ly.Npad + kNch - 1) / kNch;
   if (c.warp == 0) {
-    if (c.lane == 0) tc_producer<false>(P, c, ly, srcbuf);
+    if (c.lane == 0) tc_producer<false>(P, c, ly, srcbuf, nullptr);
   } else if (c.warp == 1) {
     if (c.lane == 0) tc_mma<false>(P, c, ly);
   } else if (c.warp >= kEpiWarp0 && c.warp < kEpiWarp0 + 4) {
@@ -741,7 +759,9 @@ template <int KIND>
 __device__ __forceinline__ void epi_pass2_fast(const PlanParams& P, Ctx& c, const EpiThread& et, const EpiArgs& ea, int cb,
                                                int nvalid, float inv_scale, float rstd, float nmr) {
   const float* sb = c.vec; const float* sg = c.vec + kFusedMaxN; const float* sbe = c.vec + 2 * kFusedMaxN;
-  uint8_t* stg = c.stage_base + kWRingOff + et.grp * (2 * kStgBuf);
+  // staging tiles: two per group aliasing the idle W ring -- or, when the W ring is busy prefetching the next layer
+  // (c.wpf), ONE per group in the idle A ring, re-used once the previous store has read it
+  uint8_t* stg = c.wpf ? c.stage_base + et.grp * kStgBuf : c.stage_base + kWRingOff + et.grp * (2 * kStgBuf);
   const bool leader = (et.q == 0) && (c.lane == 0);
   const CUtensorMap* tmD = (ea.dstbuf == BUF_X) ? &P.tmXs : &P.tmHs;
   const uint32_t swz = static_cast<uint32_t>((et.row >> 1) & 3);
@@ -750,9 +770,9 @@ __device__ __forceinline__ void epi_pass2_fast(const PlanParams& P, Ctx& c, cons
   const int nblk = nvalid >> 5;
   for (int blk = 0; blk < nblk; ++blk) {
     const int c0 = cb + (blk << 5);
-    uint8_t* buf = stg + (blk & 1) * kStgBuf;
+    uint8_t* buf = c.wpf ? stg : stg + (blk & 1) * kStgBuf;
     const uint32_t rowaddr = ptx::smem_u32(buf) + static_cast<uint32_t>(et.row) * 64u;
-    if (blk >= 2) {                                               // buffer reuse: its previous store must have read it
+    if (!c.wpf && blk >= 2) {                                     // buffer reuse: its previous store must have read it
       if (leader) ptx::bulk_wait_read<1>();
       group_bar_sync(et.grp);
     }
@@ -802,6 +822,11 @@ __device__ __forceinline__ void epi_pass2_fast(const PlanParams& P, Ctx& c, cons
         const __half2 l2 = __floats2half2_rn(df.x, df.y);
         hw[i] = *reinterpret_cast<const uint32_t*>(&h2);
         lw[i] = *reinterpret_cast<const uint32_t*>(&l2);
+      }
+      if (c.wpf && sub == 0 && blk >= 1) {
+        // single staging tile: the previous block's store was issued a whole block of math ago, so this wait is short
+        if (leader) ptx::bulk_wait_read<0>();
+        group_bar_sync(et.grp);
       }
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
@@ -1221,7 +1246,8 @@ __device__ __forceinline__ void publish_planes() {
 // ------------------------------------------------------------------------------------ one layer
 // GEMM + epilogue; on return the epilogue's outputs are published (CTA-synchronised, TMA-visible).
 template <int ENGINE, bool EPISODIC>
-__device__ __forceinline__ void run_layer(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf, const EpiArgs& ea) {
+__device__ __forceinline__ void run_layer(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf, const EpiArgs& ea,
+                                          const LayerDev* next) {
   const bool is_ln = (ea.kind == EPI_LN_MISH || ea.kind == EPI_LN_SIMNORM);
   const bool fused = (ENGINE == ENGINE_TC) && (ly.Npad <= kFusedMaxN) && (is_ln || ly.Npad <= kNch) &&
                      (ea.kind != EPI_RAW || ly.Npad <= kNch);
@@ -1229,7 +1255,7 @@ __device__ __forceinline__ void run_layer(const PlanParams& P, Ctx& c, const Lay
     const long long tl = clock64();
     if (threadIdx.x == 0) TDMPC2_TRACE(P, c, 0);
     if (c.warp == 0) {
-      if (c.lane == 0) tc_producer<true>(P, c, ly, srcbuf);
+      if (c.lane == 0) tc_producer<true>(P, c, ly, srcbuf, next);
     } else if (c.warp == 1) {
       if (c.lane == 0 && (!c.cg2 || c.rank == 0)) tc_mma<true>(P, c, ly);
     } else if (c.warp >= kEpiWarp0) {
@@ -1364,7 +1390,9 @@ __device__ __forceinline__ void refit_env(const PlanParams& P, uint8_t* scratch,
 // environment and every layer on the fused path is launched this way.
 // EPISODIC (cfg.episodic, single-task models): every rollout step gains the 3-layer termination head on z_{t+1}
 // and the value bookkeeping its sticky (1 - termination) factor (tdmpc2.py:126-136); compiled out otherwise.
-template <int ENGINE, bool CG2 = false, bool EPISODIC = false>
+// WPF (CEM iterations of fully fused models): the TMA producer prefetches the next layer's first weight chunks into
+// the W ring while the epilogue runs; the epilogue stages its output in the A ring instead.  Same arithmetic.
+template <int ENGINE, bool CG2 = false, bool EPISODIC = false, bool WPF = false>
 __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant__ PlanParams P) {
   constexpr int SPT = EPISODIC ? 9 : 6;      // layer steps per rollout time step (ITER / VALUE)
   extern __shared__ uint8_t smem_raw[];
@@ -1392,6 +1420,8 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
   }
   c.slot = blockIdx.x;
   c.cg2 = CG2 ? 1 : 0;
+  c.wpf = WPF ? 1 : 0;
+  c.w_pref = 0;
   c.w_ring = CG2 ? kWRingPair : kWRing;
   c.w_stride = CG2 ? kWSlotBytes / 2 : kWSlotBytes;
   c.w_lo_off = CG2 ? kAPlane : kWPlane;
@@ -1617,7 +1647,19 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
         }
       }
       c.trace_step = (tile == static_cast<int>(blockIdx.x)) ? sidx : (1 << 30);
-      run_layer<ENGINE, EPISODIC>(P, c, LY[li], src, ea);
+      const LayerDev* next = nullptr;
+      if (WPF && P.mode == MODE_ITER && sidx + 1 < nsteps) {
+        // layer of the step after this one (same mapping as above, without its side effects); none after the
+        // tile's last step: the refit and the next tile's set-up use the operand smem as scratch
+        const int s1 = sidx + 1;
+        int mlp1, l1;
+        if (s1 < SPT * P.H) { l1 = s1 % SPT; mlp1 = l1 < 3 ? 0 : ((EPISODIC && l1 >= 6) ? 5 : 1); l1 %= 3; }
+        else { const int u1 = s1 - SPT * P.H; mlp1 = 2 + u1 / 3; l1 = u1 % 3; }
+        const int base1 = (EPISODIC && mlp1 == 5) ? P.li_term
+                          : mlp1 == 0 ? P.li_rew : mlp1 == 1 ? P.li_dyn : mlp1 == 2 ? P.li_pi : P.li_q + 3 * qi[mlp1 - 3];
+        next = &LY[base1 + l1];
+      }
+      run_layer<ENGINE, EPISODIC>(P, c, LY[li], src, ea, next);
     }
 
     const long long t_refit = clock64();

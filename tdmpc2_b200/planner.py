@@ -147,7 +147,7 @@ class Planner:
         engine = engine or DEFAULT_ENGINE
         self.engine_name = engine
         code = {"tcgen05": _cabi.ENGINE_TCGEN05, "simt": _cabi.ENGINE_SIMT, "tcgen05x2": _cabi.ENGINE_TCGEN05_2SM,
-                "tcgen05pp": _cabi.ENGINE_TCGEN05_PP}[engine]
+                "tcgen05pp": _cabi.ENGINE_TCGEN05_PP, "tcgen05x2pf": _cabi.ENGINE_TCGEN05_2SM_PF}[engine]
         _cabi.check(self.lib.tdmpc2_planner_set_engine(self.h, code))
         self.engine = engine
 

@@ -213,6 +213,29 @@ def test_cta_pair_engine_is_bit_identical_to_single_cta():
         assert torch.equal(x, y)
 
 
+def test_prefetch_engine_is_bit_identical_to_pair_engine():
+    """tcgen05x2pf only changes WHEN weight chunks are requested (the next layer's first chunks stream into the W ring
+    during the epilogue) and where the epilogue stages its output (A ring): every value must be bit-identical."""
+    from oracle.plan_oracle import draw_noise as oracle_noise
+    E = 3
+    cfg = workload("c1", num_envs=E)
+    sd = synth_state_dict(cfg, seed=12, perturb=True)
+    g = torch.Generator().manual_seed(9)
+    obs = torch.randn(E, cfg.obs_shape["state"][0], generator=g).cuda()
+    prev = (0.3 * torch.randn(E, cfg.horizon, cfg.action_dim, generator=g)).cuda()
+    t0 = torch.tensor([0, 1, 0], dtype=torch.uint8).cuda()
+    noise = _to_gpu_noise(oracle_noise(cfg, 45, E), False)
+    out = {}
+    for engine in ("tcgen05x2", "tcgen05x2pf"):
+        pl = _planner(cfg, E, engine, sd)
+        for rep in range(2):                              # second plan(): warm-started, pipeline counters mid-stream
+            a, m, tr = pl.plan(obs, None, t0 if rep == 0 else torch.zeros_like(t0), prev if rep == 0 else m, noise, trace=True)
+            torch.cuda.synchronize()
+        out[engine] = (a.cpu(), m.cpu(), tr["values"].cpu(), tr["elite_idx"].cpu(), tr["iter_std"].cpu())
+    for x, y in zip(out["tcgen05x2"], out["tcgen05x2pf"]):
+        assert torch.equal(x, y)
+
+
 @pytest.mark.parametrize("perturb", [False, True])
 def test_ping_pong_engine_matches_oracle_and_pair_engine(perturb):
     """tcgen05pp (plan_pp.cuh) overlaps the GEMM of one 64-row half tile with the epilogue of the other.  Row
