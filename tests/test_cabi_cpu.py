@@ -129,3 +129,23 @@ def test_graft_entry_build():
     import importlib
     ge = importlib.import_module("__graft_entry__")
     ge.build()
+
+
+def test_plain_c_host_links_and_reports_no_device(lib, tmp_path):
+    """The boundary is a C ABI: a C11 program (examples/c_host.c) compiles against include/tdmpc2_b200.h, links the
+    shared library without Python or torch, and -- on a machine without a B200 -- gets TDMPC2_ERR_NO_DEVICE."""
+    import shutil, subprocess
+    from tdmpc2_b200 import _cabi
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    libdir = os.path.dirname(_cabi.LIB_PATH)
+    exe = str(tmp_path / "c_host")
+    subprocess.run([gcc, "-std=c11", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "c_host.c"), "-L" + libdir, "-ltdmpc2_b200",
+                    "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "ABI version" in res.stdout
+    if not torch.cuda.is_available():
+        assert "no CUDA device" in res.stdout
