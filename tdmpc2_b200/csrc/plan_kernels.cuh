@@ -1,7 +1,9 @@
 // Fused planning kernels for sm_100a (B200).
 //
-// One persistent kernel template, `plan_kernel<ENGINE>`, runs the MLP chains of
-// the TD-MPC2 planner on 128-row tiles.  All modes share the device code:
+// One persistent kernel template, `plan_kernel<ENGINE, PAIR, EPISODIC, WPF>`, runs the MLP chains of
+// the TD-MPC2 planner on 128-row tiles (the flags are compile-time so that an unused feature costs no code:
+// PAIR = CTA pairs / cta_group::2, EPISODIC = termination head in the rollout, WPF = weight prefetch during the
+// epilogue).  All modes share the device code:
 //
 //   MODE_ENCODE : rows = environments.      z = encode(obs, task)        (reference world_model.py:103-112)
 //   MODE_PRIOR  : rows = (env, pi-traj).    the P policy-prior rollouts  (reference tdmpc2.py:154-160)
@@ -21,6 +23,7 @@
 //
 //   * PAIR mode (CEM iterations): clusters of two CTAs issue cta_group::2 MMAs with
 //     M = 256 (each CTA's own 128-row tile); each CTA streams half of every W tile.
+//     plan_pp.cuh holds the ping-pong variant of this mode (two 64-row halves per CTA).
 //   * Layers with Npad <= 512 (the whole accumulator fits TMEM) use the FUSED
 //     epilogue: one thread per row reads its accumulator row straight from TMEM
 //     (tcgen05.ld), applies bias + LayerNorm + Mish / SimNorm / two-hot-inverse /
