@@ -88,3 +88,30 @@ def test_episodic_oracle_properties():
     m = OracleModel(cfg_e, sd)
     first = two_hot_inv(m.reward(z, acts[0], None), cfg_e)
     assert torch.equal(estimate_value(m, z, acts, None, eps, qidx), first)
+
+
+def test_oracle_properties_t0_eval_mode_nan():
+    """Properties SURVEY.md 8(c) lists for the reference planner, held on the oracle:
+    t0=True ignores _prev_mean (tdmpc2.py:166-167); eval_mode skips the final exploration draw and returns the picked
+    elite action itself (tdmpc2.py:203-204); NaN trajectory values count as 0 (tdmpc2.py:184)."""
+    from oracle.plan_oracle import OracleModel
+    cfg, sd, calls = load_golden("tiny")
+    model = OracleModel(cfg, sd)
+    obs = calls[0]["obs"][None]
+    noise = draw_noise(cfg, 9, 1)
+    pm_a = torch.zeros(1, cfg.horizon, cfg.action_dim)
+    pm_b = torch.full((1, cfg.horizon, cfg.action_dim), 0.7)
+    a = plan_oracle(cfg, model, obs, t0=[True], prev_mean=pm_a, noise=noise)
+    b = plan_oracle(cfg, model, obs, t0=[True], prev_mean=pm_b, noise=noise)
+    assert torch.equal(a.action, b.action) and torch.equal(a.values, b.values)
+    c = plan_oracle(cfg, model, obs, t0=[False], prev_mean=pm_b, noise=noise)
+    assert not torch.equal(a.values, c.values)                       # the warm start is used when t0 is False
+    # eval_mode: same trajectory values, action == the picked elite's first action (no std * randn term)
+    ev = plan_oracle(cfg, model, obs, t0=[True], prev_mean=pm_a, noise=noise, eval_mode=True)
+    assert torch.equal(ev.values, a.values) and torch.equal(ev.pick, a.pick)
+    assert not torch.equal(ev.action, a.action)
+    assert float((a.action - (ev.action + a.std[:, 0] * noise.final).clamp(-1, 1)).abs().max()) < 1e-6
+    # NaN observation -> every value NaN -> nan_to_num(0): all values exactly 0 (which K of the tied samples torch.topk
+    # returns is implementation-defined; the kernels break ties towards the lower index)
+    nan = plan_oracle(cfg, model, torch.full_like(obs, float("nan")), t0=[True], prev_mean=pm_a, noise=noise)
+    assert torch.all(nan.values == 0)
