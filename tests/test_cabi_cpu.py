@@ -149,3 +149,31 @@ def test_plain_c_host_links_and_reports_no_device(lib, tmp_path):
     assert "ABI version" in res.stdout
     if not torch.cuda.is_available():
         assert "no CUDA device" in res.stdout
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under tdmpc2_b200/ (or the drop-in shim) may import it, and bench.py
+    only inside its CPU-baseline / reference-arm function."""
+    import ast
+    def imports_oracle(path):
+        tree = ast.parse(open(path).read())
+        hits = []
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            hits += [(n, node.lineno) for n in names if n == "oracle" or n.startswith("oracle.")]
+        return hits
+    for d in ("tdmpc2_b200", "dropin"):
+        for fn in os.listdir(os.path.join(ROOT, d)):
+            if fn.endswith(".py"):
+                assert not imports_oracle(os.path.join(ROOT, d, fn)), fn
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    tree = ast.parse(src)
+    for fn in [n for n in tree.body if isinstance(n, ast.FunctionDef)]:
+        uses = [n for n in ast.walk(fn) if isinstance(n, ast.ImportFrom) and (n.module or "").startswith("oracle")]
+        if uses:
+            assert fn.name == "cpu_reference_run", fn.name   # the one function both CPU legs go through
+    assert not [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom)) and "oracle" in ast.dump(n)]
