@@ -866,7 +866,7 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
   const float* sb = c.vec; const float* sg = c.vec + kFusedMaxN; const float* sbe = c.vec + 2 * kFusedMaxN;
   if (nvalid > 0) {
     const long long tw = clock64();
-    ptx::mbar_wait(&c.facc[0], c.fph0);
+    ptx::mbar_wait_long(&c.facc[0], c.fph0);
     c.pf2 += clock64() - tw;
   }
   const bool tr0 = (et.grp == 0 && et.q == 0 && c.lane == 0), tr3 = (et.grp == 3 && et.q == 0 && c.lane == 0);
@@ -1102,7 +1102,7 @@ __device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, cons
   if (!wide_twohot && !wide_pi && et.grp != 0) return;
   {
     const long long tw = clock64();
-    ptx::mbar_wait(&c.facc[0], c.fph0);
+    ptx::mbar_wait_long(&c.facc[0], c.fph0);
     c.pf2 += clock64() - tw;
   }
   ptx::tc_fence_after();

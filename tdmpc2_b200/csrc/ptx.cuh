@@ -58,6 +58,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+// Long waits of many warps (the 16 epilogue warps wait ~28 k cycles per layer for the accumulator): TDMPC2_EPI_SLEEP_NS
+// > 0 puts a nanosleep between polls -- fewer issue slots and less power under the 1000 W cap, at the price of a
+// slower wake-up.  Experiment knob for an A/B build (build.build_variant); 0 = plain mbar_wait.
+#ifndef TDMPC2_EPI_SLEEP_NS
+#define TDMPC2_EPI_SLEEP_NS 0
+#endif
+__device__ __forceinline__ void mbar_wait_long(uint64_t* bar, uint32_t parity) {
+#if TDMPC2_EPI_SLEEP_NS > 0
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(TDMPC2_EPI_SLEEP_NS);
+    if (++spins > (1u << 24)) {
+      printf("tdmpc2_b200: mbarrier wait timed out (block %d thread %d bar %p parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, (void*)bar, parity);
+      __trap();
+    }
+  }
+#else
+  mbar_wait(bar, parity);
+#endif
+}
 
 // ------------------------------------------------------------------ proxies / fences
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
