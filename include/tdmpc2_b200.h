@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define TDMPC2_B200_ABI_VERSION 2   /* 2: tdmpc2_weights.termination, dims.episodic = 1 accepted */
+#define TDMPC2_B200_ABI_VERSION 3   /* 2: tdmpc2_weights.termination, dims.episodic = 1 accepted; 3: tdmpc2_planner_set_l2_persist */
 #define TDMPC2_MAX_ENC_LAYERS 8
 
 typedef enum tdmpc2_status {
@@ -134,6 +134,10 @@ int tdmpc2_planner_workspace_bytes(const tdmpc2_planner* p, size_t* out);
  * workspace and encode the TMA descriptors.  Synchronous. */
 int tdmpc2_planner_bind(tdmpc2_planner* p, void* packed, void* workspace);
 int tdmpc2_planner_set_engine(tdmpc2_planner* p, int engine);
+/* enable != 0: every planning launch carries an access-policy window that keeps the per-CTA activation scratch in the
+ * persisting part of L2 (sets the DEVICE-wide cudaLimitPersistingL2CacheSize, hence opt-in); 0 switches it off.
+ * No reference counterpart (the reference's activations are ordinary torch tensors). */
+int tdmpc2_planner_set_l2_persist(tdmpc2_planner* p, int enable);
 /* Replaces: agent.load()/WorldModel.to(device) weight placement (tdmpc2.py:81-95).
  * Packs the state-dict tensors into the kernel layout: per Linear two fp16
  * planes (hi, lo) of weight * 2^k, K-major, zero-padded; applies the

@@ -29,7 +29,28 @@ from typing import Dict, Optional
 import torch
 import torch.nn as nn
 
-REF_DIR = os.environ.get("TDMPC2_REFERENCE_DIR", "/root/reference/tdmpc2")
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# Where the reference's modules lie: the read-only checkout in the build container, or -- on the GPU box, where
+# /root/reference does not exist -- the git-ignored verbatim copy `baseline/_ref/tdmpc2` that `make_ref_copy()` (run by
+# __graft_entry__.build()) places next to the repo so that the unmodified reference can be timed beside the kernels.
+_CANDIDATES = [os.environ.get("TDMPC2_REFERENCE_DIR", ""), "/root/reference/tdmpc2",
+               os.path.join(_ROOT, "baseline", "_ref", "tdmpc2")]
+REF_DIR = next((d for d in _CANDIDATES if d and os.path.isfile(os.path.join(d, "tdmpc2.py"))), _CANDIDATES[1])
+
+
+def make_ref_copy(src: str = "/root/reference/tdmpc2") -> bool:
+    """Copy the files of the reference's planning path (tdmpc2.py + common/*.py, unmodified) to baseline/_ref/tdmpc2
+    (git-ignored, travels to the GPU box with the snapshot).  No-op where the checkout does not exist."""
+    import shutil
+    if not os.path.isfile(os.path.join(src, "tdmpc2.py")):
+        return False
+    dst = os.path.join(_ROOT, "baseline", "_ref", "tdmpc2")
+    os.makedirs(os.path.join(dst, "common"), exist_ok=True)
+    shutil.copy2(os.path.join(src, "tdmpc2.py"), os.path.join(dst, "tdmpc2.py"))
+    for f in os.listdir(os.path.join(src, "common")):
+        if f.endswith(".py"):
+            shutil.copy2(os.path.join(src, "common", f), os.path.join(dst, "common", f))
+    return True
 
 
 def available() -> bool:
@@ -60,8 +81,9 @@ def _import_reference():
     return _mods
 
 
-def build_agent(cfg, state_dict: Dict[str, torch.Tensor]):
-    """Reference TDMPC2 agent on CPU carrying `state_dict` (reference key layout)."""
+def build_agent(cfg, state_dict: Dict[str, torch.Tensor], device="cpu"):
+    """Reference TDMPC2 agent on `device` (CPU for the oracle pins; cuda:0 for the on-box GPU baseline) carrying
+    `state_dict` (reference key layout)."""
     layers, init, WorldModel, ref = _import_reference()
 
     class FuncEnsemble(nn.Module):                       # stands in for layers.Ensemble (layers.py:8-33)
@@ -114,16 +136,18 @@ def build_agent(cfg, state_dict: Dict[str, torch.Tensor]):
     assert not missing and not extra, f"state-dict mismatch: missing={sorted(missing)[:5]} extra={sorted(extra)[:5]}"
     model.load_state_dict(mapped)
     model.eval()
+    device = torch.device(device)
+    model.to(device)
 
     agent = ref.TDMPC2.__new__(ref.TDMPC2)
     nn.Module.__init__(agent)
-    agent.cfg, agent.device = cfg, torch.device("cpu")
+    agent.cfg, agent.device = cfg, device
     agent.model = model
     if cfg.multitask:                                    # tdmpc2.py:35-37
-        agent.discount = torch.tensor([ref.TDMPC2._get_discount(agent, ep) for ep in cfg.episode_lengths])
+        agent.discount = torch.tensor([ref.TDMPC2._get_discount(agent, ep) for ep in cfg.episode_lengths], device=device)
     else:
         agent.discount = ref.TDMPC2._get_discount(agent, cfg.episode_length)
-    agent._prev_mean = torch.nn.Buffer(torch.zeros(cfg.horizon, cfg.action_dim))
+    agent._prev_mean = torch.nn.Buffer(torch.zeros(cfg.horizon, cfg.action_dim, device=device))
     return agent
 
 

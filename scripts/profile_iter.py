@@ -13,24 +13,25 @@ cfg = workload(wl, num_envs=E)
 pl = Planner(cfg, E, "cuda:0", engine=os.environ.get("TDMPC2_ENGINE", "tcgen05x2"))
 pl.pack(synth_state_dict(cfg, seed=1))
 dev = torch.device("cuda:0")
-n = draw_noise(cfg, E, dev)
+n = draw_noise(cfg, E, dev, reference_order=False)
+NSM = torch.cuda.get_device_properties(0).multi_processor_count
 obs = torch.randn(E, cfg.obs_shape["state"][0], device=dev)
 task = (torch.arange(E) % len(cfg.tasks)).to(torch.int32).to(dev) if cfg.multitask else None
 pl.prologue(obs, task, torch.ones(E, dtype=torch.uint8, device=dev), torch.zeros(E, cfg.horizon, cfg.action_dim, device=dev), n.prior)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for i in range(iters):
-    a = (n.r[:, i].contiguous(), n.pi[:, i].contiguous(), n.qidx[:, i].contiguous())
+    a = (n.r[i % cfg.iterations], n.pi[i % cfg.iterations], n.qidx[i % cfg.iterations])
     e0.record(); pl.iterate(*a); e1.record(); torch.cuda.synchronize()
     print(f"iter {i}: {e0.elapsed_time(e1):.3f} ms (E={E}, tiles={E * ((cfg.num_samples + 127) // 128)})")
 
 if os.environ.get("TDMPC2_PHASE_PROF"):
-    buf = torch.zeros(148 * 4 * 12 + 32 * 16, dtype=torch.int64, device=dev)
+    buf = torch.zeros(NSM * 4 * 12 + 32 * 16, dtype=torch.int64, device=dev)
     pl.lib.tdmpc2_planner_set_profile(pl.h, buf.data_ptr())
-    a = (n.r[:, 0].contiguous(), n.pi[:, 0].contiguous(), n.qidx[:, 0].contiguous())
+    a = (n.r[0], n.pi[0], n.qidx[0])
     pl.iterate(*a); torch.cuda.synchronize()
     pl.lib.tdmpc2_planner_set_profile(pl.h, None)
-    b = buf[:148 * 4 * 12].view(148, 4, 12).double().cpu()
-    tr = buf[148 * 4 * 12:].view(32, 16).cpu()
+    b = buf[:NSM * 4 * 12].view(NSM, 4, 12).double().cpu()
+    tr = buf[NSM * 4 * 12:].view(32, 16).cpu()
     names = ["producer", "mma", "epilogue", "idle"]
     cols = ["bar_wait", "in_layers", "facc_wait", "publish", "setup", "kernel", "actions", "refit", "decode"]
     m = b.mean(0)

@@ -113,11 +113,12 @@ class BatchedTorchPlanner:
         return G + discount * (1 - termination) * self.q_avg(z, action, task, qidx)
 
     @torch.no_grad()
-    def plan(self, obs, task, t0, prev_mean, noise, eval_mode=False):
+    def plan(self, obs, task, t0, prev_mean, noise, eval_mode=False, iter_major=False):
         """obs [E,obs], task [E] | None, t0 [E] bool, prev_mean [E,H,A]; noise: prior [E,H,P,A], r [E,I,H,N-P,A],
         pi [E,I,N,A], qidx [E,I,2], expo [E,K], final [E,A] | None.  Returns (action [E,A], mean [E,H,A], values [E,I,N])."""
         cfg = self.cfg
         E, H, N, P, A, K = obs.shape[0], cfg.horizon, cfg.num_samples, cfg.num_pi_trajs, cfg.action_dim, cfg.num_elites
+        at = (lambda t, it: t[it]) if iter_major else (lambda t, it: t[:, it])   # planner.Noise is [I,E,...], the oracle's [E,I,...]
         x = obs[:, None, :]
         z0 = self._mlp("_encoder.state", self._emb(x, task), "simnorm")                     # [E,1,L]
         pi_actions = torch.zeros(E, H, P, A, device=self.dev)
@@ -137,10 +138,10 @@ class BatchedTorchPlanner:
         mask = self.sd["_action_masks"][task][:, None, None, :] if cfg.multitask else None
         values = []
         for it in range(cfg.iterations):
-            actions[:, :, P:] = (mean.unsqueeze(2) + std.unsqueeze(2) * noise.r[:, it]).clamp(-1, 1)
+            actions[:, :, P:] = (mean.unsqueeze(2) + std.unsqueeze(2) * at(noise.r, it)).clamp(-1, 1)
             if mask is not None:
                 actions = actions * mask
-            value = self.estimate_value(z, actions, task, noise.pi[:, it], noise.qidx[:, it].long()).nan_to_num(0)
+            value = self.estimate_value(z, actions, task, at(noise.pi, it), at(noise.qidx, it).long()).nan_to_num(0)
             elite_idxs = torch.topk(value.squeeze(-1), K, dim=1).indices                    # [E,K]
             elite_value = torch.gather(value, 1, elite_idxs[:, :, None])                    # [E,K,1]
             elite_actions = torch.gather(actions, 2, elite_idxs[:, None, :, None].expand(-1, H, -1, A))   # [E,H,K,A]
@@ -161,39 +162,58 @@ class BatchedTorchPlanner:
         return a.clamp(-1, 1), mean, torch.stack(values, 1)
 
 
+def run(workload_name="c2", envs=None, steps=5, device="cuda:0", tf32=False, budget_s=60.0):
+    """Time `plan()` of the batched eager-PyTorch restatement (CUDA events on a GPU, wall clock on CPU);
+    returns the JSON-able record.  `envs` environments are planned per call (a bounded sample of the workload);
+    tf32=True lets cuBLAS use TF32 tensor cores (torch.backends.cuda.matmul.allow_tf32), fp32 otherwise."""
+    from tdmpc2_b200.planner import draw_noise
+    over = {} if envs is None else {"num_envs": envs}
+    cfg = workload(workload_name, iterations_effective=True, **over)
+    dev = torch.device(device)
+    E = cfg.num_envs
+    prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
+    try:
+        pl = BatchedTorchPlanner(cfg, synth_state_dict(cfg, seed=1), dev)
+        obs = torch.randn(E, cfg.obs_shape["state"][0], device=dev)
+        task = (torch.arange(E, device=dev) % len(cfg.tasks)) if cfg.multitask else None
+        state = {"prev": torch.zeros(E, cfg.horizon, cfg.action_dim, device=dev)}
+        on_gpu = dev.type == "cuda"
+        sync = (lambda: torch.cuda.synchronize(dev)) if on_gpu else (lambda: None)
+
+        def step(t0):
+            n = draw_noise(cfg, E, dev, reference_order=False)
+            a, state["prev"], _ = pl.plan(obs, task, torch.full((E,), t0, device=dev), state["prev"], n, iter_major=True)
+            return a
+
+        step(True); step(False); sync()
+        t_begin, times = time.perf_counter(), []
+        for _ in range(steps):
+            if times and time.perf_counter() - t_begin > budget_s:
+                break
+            if on_gpu:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); step(False); e1.record(); sync()
+                times.append(e0.elapsed_time(e1))
+            else:
+                t = time.perf_counter(); step(False); times.append((time.perf_counter() - t) * 1e3)
+        ms = sum(times) / len(times)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+    return {"impl": "batched eager PyTorch / cuBLAS (reference algorithm, all num_q heads)", "device": str(dev),
+            "matmul": "tf32" if tf32 else "fp32", "workload": workload_name, "envs": E, "ms_per_step": ms,
+            "value": E * cfg.num_samples * cfg.horizon / (ms * 1e-3), "unit": "steps/s", "steps": len(times)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--envs", type=int, default=None)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--device", default="cuda:0")
+    ap.add_argument("--tf32", action="store_true")
     args = ap.parse_args()
-    from tdmpc2_b200.planner import draw_noise
-    over = {} if args.envs is None else {"num_envs": args.envs}
-    cfg = workload(args.workload, iterations_effective=True, **over)
-    dev = torch.device(args.device)
-    E = cfg.num_envs
-    pl = BatchedTorchPlanner(cfg, synth_state_dict(cfg, seed=1), dev)
-    obs = torch.randn(E, cfg.obs_shape["state"][0], device=dev)
-    task = (torch.arange(E, device=dev) % len(cfg.tasks)) if cfg.multitask else None
-    prev = torch.zeros(E, cfg.horizon, cfg.action_dim, device=dev)
-    sync = torch.cuda.synchronize if dev.type == "cuda" else (lambda: None)
-
-    def step(t0):
-        nonlocal prev
-        n = draw_noise(cfg, E, dev, reference_order=False)
-        a, prev, _ = pl.plan(obs, task, torch.full((E,), t0, device=dev), prev, n)
-        return a
-
-    step(True); step(False); sync()
-    t = time.perf_counter()
-    for _ in range(args.steps):
-        step(False)
-    sync()
-    ms = (time.perf_counter() - t) / args.steps * 1e3
-    print(json.dumps({"impl": "batched eager PyTorch (reference algorithm, all num_q heads)", "device": str(dev),
-                      "workload": args.workload, "envs": E, "ms_per_step": ms,
-                      "value": E * cfg.num_samples * cfg.horizon / (ms * 1e-3), "unit": "steps/s", "steps": args.steps}))
+    print(json.dumps(run(args.workload, args.envs, args.steps, args.device, args.tf32)))
 
 
 if __name__ == "__main__":

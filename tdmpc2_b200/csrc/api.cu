@@ -129,6 +129,9 @@ struct tdmpc2_planner {
   int engine = TDMPC2_ENGINE_TCGEN05;
   bool bound = false, weights_ok = false, smem_attr_set[2] = {false, false}, smem_attr_pair = false, smem_attr_pp = false, all_fused = true;
   int64_t launches = 0;
+  size_t l2_window_bytes = 0;       // > 0: launches carry a persisting-L2 access-policy window over the activation scratch
+  float l2_hit_ratio = 1.f;
+  bool pair_ok = true;              // every layer of the CEM iteration can run as cta_group::2
   const int32_t* cur_task = nullptr;
   long long* prof = nullptr;
 };
@@ -178,9 +181,12 @@ extern "C" int tdmpc2_planner_create(const tdmpc2_dims* dims, tdmpc2_planner** o
   if (d.episodic && d.task_dim > 0)   // WorldModel.termination asserts task is None (world_model.py:136)
     return fail(TDMPC2_ERR_UNSUPPORTED, "episodic (termination head) models are single-task in the reference");
   if (d.num_envs < 1 || d.num_samples < 1 || d.horizon < 1 || d.iterations < 1 || d.obs_dim < 1 || d.action_dim < 1 ||
-      d.latent_dim < 1 || d.mlp_dim < 1 || d.enc_dim < 1 || d.num_enc_layers < 1 || d.num_q < 2 || d.num_bins < 2 ||
+      d.latent_dim < 1 || d.mlp_dim < 1 || d.enc_dim < 1 || d.num_enc_layers < 1 || d.num_q < 2 || d.num_bins < 0 ||
       d.task_dim < 0 || d.num_tasks < 1)
     return fail(TDMPC2_ERR_INVALID, "non-positive dimension");
+  if (d.num_bins < 2)   // math.two_hot_inv's num_bins == 0 (raw) / == 1 (symexp only) regression heads (math.py:76-79)
+    return fail(TDMPC2_ERR_UNSUPPORTED, "num_bins=%d: only the discrete-regression heads (num_bins >= 2) are built; the "
+                "reference's num_bins 0 / 1 scalar heads are not supported by the fused planner", d.num_bins);
   if (d.num_elites < 1 || d.num_elites > d.num_samples) return fail(TDMPC2_ERR_INVALID, "num_elites must be in [1, num_samples]");
   if (d.num_pi_trajs < 0 || d.num_pi_trajs > 128 || d.num_pi_trajs > d.num_samples)
     return fail(TDMPC2_ERR_INVALID, "num_pi_trajs must be in [0, min(128, num_samples)]");
@@ -231,6 +237,7 @@ extern "C" int tdmpc2_planner_create(const tdmpc2_dims* dims, tdmpc2_planner** o
   p->Ppad = 1;
   while (p->Ppad < d.num_pi_trajs) p->Ppad <<= 1;
   p->tiles_per_env = (d.num_samples + kTileM - 1) / kTileM;
+  p->pair_ok = p->all_fused;
 
   // ---- packed blob layout
   size_t off = 0;
@@ -478,6 +485,25 @@ static bool wpf_eligible(const tdmpc2_planner* p) {
   return true;
 }
 
+// Launch attributes shared by every plan_kernel launch: the cluster dimension of the CTA-pair engines and -- when
+// enabled (tdmpc2_planner_set_l2_persist) -- an access-policy window that keeps the per-CTA activation scratch
+// (X + H planes, contiguous in the workspace) resident in the persisting part of L2, so that its dirty lines are not
+// written back to HBM while noise and weights stream through.
+struct LaunchCfg {
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[2];
+  LaunchCfg(tdmpc2_planner* p, int grid, size_t smem, cudaStream_t st, bool cluster2);
+};
+
+template <class K>
+static int launch_one(tdmpc2_planner* p, K kernel, int grid, size_t smem, cudaStream_t st, bool cluster2, const PlanParams& prm) {
+  LaunchCfg lc(p, grid, smem, st, cluster2);
+  CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, kernel, prm));
+  CUDA_TRY(cudaGetLastError());
+  p->launches += 1;
+  return 0;
+}
+
 static int launch_plan(tdmpc2_planner* p, const PlanParams& prm, int ntiles, cudaStream_t st) {
   const int eng = p->engine == TDMPC2_ENGINE_SIMT ? 1 : 0;
   // episodic models: the rollout modes run the instantiations that carry the termination head
@@ -495,7 +521,8 @@ static int launch_plan(tdmpc2_planner* p, const PlanParams& prm, int ntiles, cud
   int grid = std::min(ntiles, p->nslots);
   PlanParams prm2 = prm;
   prm2.prof = p->prof;
-  // CTA-pair (cta_group::2) launch: CEM iterations only, whole pairs of tiles of one environment, fused layers only
+  prm2.prof_slots = p->nslots;
+  // CTA-pair (cta_group::2) launch: CEM iterations only, whole pairs of tiles of one environment
   const bool pair_engine = (p->engine == TDMPC2_ENGINE_TCGEN05_2SM || p->engine == TDMPC2_ENGINE_TCGEN05_PP ||
                             p->engine == TDMPC2_ENGINE_TCGEN05_2SM_PF);
   if (p->engine == TDMPC2_ENGINE_TCGEN05_PP && prm.mode == MODE_ITER && (p->tiles_per_env % 2 == 0) && (ntiles % 2 == 0) &&
@@ -505,20 +532,9 @@ static int launch_plan(tdmpc2_planner* p, const PlanParams& prm, int ntiles, cud
       CUDA_TRY(cudaFuncSetAttribute(plan_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPPSmemBytes));
       p->smem_attr_pp = true;
     }
-    grid &= ~1;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kPPSmemBytes; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, plan_pp_kernel, prm2));
-    CUDA_TRY(cudaGetLastError());
-    p->launches += 1;
-    return 0;
+    return launch_one(p, plan_pp_kernel, grid & ~1, kPPSmemBytes, st, true, prm2);
   }
-  bool pair = pair_engine && prm.mode == MODE_ITER && (p->tiles_per_env % 2 == 0) &&
-              (ntiles % 2 == 0) && p->all_fused;
+  const bool pair = pair_engine && prm.mode == MODE_ITER && (p->tiles_per_env % 2 == 0) && (ntiles % 2 == 0) && p->pair_ok;
   if (pair) {
     if (!p->smem_attr_pair) {
       CUDA_TRY(cudaFuncSetAttribute(plan_kernel<ENGINE_TC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -527,25 +543,55 @@ static int launch_plan(tdmpc2_planner* p, const PlanParams& prm, int ntiles, cud
       p->smem_attr_pair = true;
     }
     grid &= ~1;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    if (epi) CUDA_TRY(cudaLaunchKernelEx(&cfg, plan_kernel<ENGINE_TC, true, true>, prm2));
-    else if (p->engine == TDMPC2_ENGINE_TCGEN05_2SM_PF && wpf_eligible(p))
-      CUDA_TRY(cudaLaunchKernelEx(&cfg, plan_kernel<ENGINE_TC, true, false, true>, prm2));
-    else CUDA_TRY(cudaLaunchKernelEx(&cfg, plan_kernel<ENGINE_TC, true>, prm2));
-  } else if (eng == 0) {
-    if (epi) plan_kernel<ENGINE_TC, false, true><<<grid, kThreads, kSmemBytes, st>>>(prm2);
-    else plan_kernel<ENGINE_TC><<<grid, kThreads, kSmemBytes, st>>>(prm2);
-  } else {
-    if (epi) plan_kernel<ENGINE_SIMT, false, true><<<grid, kThreads, kSmemBytes, st>>>(prm2);
-    else plan_kernel<ENGINE_SIMT><<<grid, kThreads, kSmemBytes, st>>>(prm2);
+    if (epi) return launch_one(p, plan_kernel<ENGINE_TC, true, true>, grid, kSmemBytes, st, true, prm2);
+    if (p->engine == TDMPC2_ENGINE_TCGEN05_2SM_PF && wpf_eligible(p))
+      return launch_one(p, plan_kernel<ENGINE_TC, true, false, true>, grid, kSmemBytes, st, true, prm2);
+    return launch_one(p, plan_kernel<ENGINE_TC, true>, grid, kSmemBytes, st, true, prm2);
   }
-  CUDA_TRY(cudaGetLastError());
-  p->launches += 1;
+  if (eng == 0) {
+    if (epi) return launch_one(p, plan_kernel<ENGINE_TC, false, true>, grid, kSmemBytes, st, false, prm2);
+    return launch_one(p, plan_kernel<ENGINE_TC>, grid, kSmemBytes, st, false, prm2);
+  }
+  if (epi) return launch_one(p, plan_kernel<ENGINE_SIMT, false, true>, grid, kSmemBytes, st, false, prm2);
+  return launch_one(p, plan_kernel<ENGINE_SIMT>, grid, kSmemBytes, st, false, prm2);
+}
+
+LaunchCfg::LaunchCfg(tdmpc2_planner* p, int grid, size_t smem, cudaStream_t st, bool cluster2) {
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  int n = 0;
+  if (cluster2) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = 2; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (p->l2_window_bytes > 0) {
+    attr[n].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[n].val.accessPolicyWindow.base_ptr = p->ws + p->off_X;
+    attr[n].val.accessPolicyWindow.num_bytes = p->l2_window_bytes;
+    attr[n].val.accessPolicyWindow.hitRatio = p->l2_hit_ratio;
+    attr[n].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[n].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    ++n;
+  }
+  cfg.attrs = attr; cfg.numAttrs = n;
+}
+
+// Keep the activation scratch in the persisting part of L2 (0 = off).  Sets the device's persisting-L2 carve-out to
+// what the scratch needs (capped by the device maximum) -- a device-wide setting, hence opt-in.
+extern "C" int tdmpc2_planner_set_l2_persist(tdmpc2_planner* p, int enable) {
+  if (!p) return fail(TDMPC2_ERR_INVALID, "null planner");
+  if (!p->bound) return fail(TDMPC2_ERR_STATE, "tdmpc2_planner_bind must be called first");
+  if (!enable) { p->l2_window_bytes = 0; return 0; }
+  int dev = 0, max_persist = 0, max_window = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+  const size_t scratch = p->off_raw - p->off_X;              // X planes + H planes of all slots
+  if (max_persist <= 0 || max_window <= 0) return fail(TDMPC2_ERR_UNSUPPORTED, "device has no persisting L2");
+  const size_t carve = std::min<size_t>(scratch, static_cast<size_t>(max_persist));
+  CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+  p->l2_window_bytes = std::min<size_t>(scratch, static_cast<size_t>(max_window));
+  p->l2_hit_ratio = std::min(1.0f, static_cast<float>(carve) / static_cast<float>(p->l2_window_bytes));
   return 0;
 }
 

@@ -126,7 +126,8 @@ struct PlanParams {
   long long* elite_idx_out; float* values_out;
   // MODE_LAYER
   int dbg_layer, dbg_mode, dbg_rows; const float* dbg_x; float* dbg_y;
-  long long* prof;   // optional [gridDim.x][16] cycle counters (diagnostics), or nullptr
+  long long* prof;   // optional [prof_slots][4][12] cycle counters + [32][16] trace stamps of CTA 0 (diagnostics), or nullptr
+  int prof_slots;    // = number of scratch slots (SM count)
   int li_term;       // first of the 3 termination-head layers (cfg.episodic, world_model.py:28), or -1
 };
 
@@ -205,7 +206,7 @@ __device__ __forceinline__ void epi_bar_sync() {   // named barrier among the 8 
 #define TDMPC2_TRACE(P_, c_, ev_)                                                                         \
   do {                                                                                                    \
     if ((P_).prof && blockIdx.x == 0 && (c_).trace_step < 32)                                              \
-      (P_).prof[148 * 4 * 12 + (c_).trace_step * 16 + (ev_)] = clock64();                                  \
+      (P_).prof[static_cast<size_t>((P_).prof_slots) * 4 * 12 + (c_).trace_step * 16 + (ev_)] = clock64();                                  \
   } while (0)
 
 // ------------------------------------------------------------------------------------ CTA context
@@ -283,7 +284,7 @@ __device__ __forceinline__ float sample_action(const PlanParams& P, int e, int t
     v = P.pi_actions[((static_cast<size_t>(e) * P.H + t) * P.P + n) * P.A + a];
   } else {
     const size_t sa = (static_cast<size_t>(e) * P.H + t) * P.A + a;
-    const float r = P.noise_r[((static_cast<size_t>(e) * P.H + t) * (P.N - P.P) + (n - P.P)) * P.A + a];
+    const float r = __ldcs(&P.noise_r[((static_cast<size_t>(e) * P.H + t) * (P.N - P.P) + (n - P.P)) * P.A + a]);
     v = __fadd_rn(P.mean[sa], __fmul_rn(P.std[sa], r));       // mean + std * r, two roundings like eager torch
     v = fminf(fmaxf(v, -1.f), 1.f);
   }
@@ -686,7 +687,7 @@ __device__ __forceinline__ void rows_head(const PlanParams& P, Ctx& c, const Lay
       const int e = rm.env < 0 ? 0 : rm.env, idx = rm.env < 0 ? 0 : rm.idx;
       const int task = P.task ? P.task[e] : 0;
       for (int a = c.lane; a < P.A; a += 32) {
-        const float eps = ea.eps_base[(static_cast<size_t>(e) * ea.eps_rows + idx) * P.A + a];
+        const float eps = __ldcs(&ea.eps_base[(static_cast<size_t>(e) * ea.eps_rows + idx) * P.A + a]);
         const float act = pi_action(P, myrow[a], myrow[P.Apad + a], eps, task, a);
         const size_t o = static_cast<size_t>(r) * P.KpadX + P.L + P.T + a;
         split_store(xhi + o, xlo + o, act);
@@ -1202,7 +1203,7 @@ __device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, cons
           if (a < a_end) {
             const float mu = fmaf(__uint_as_float(vm[i + u]), inv_scale, sb[a]);
             const float ls = fmaf(__uint_as_float(vs[i + u]), inv_scale, sb[P.Apad + a]);
-            act2[u] = pi_action(P, mu, ls, eps[a], task, a);
+            act2[u] = pi_action(P, mu, ls, __ldcs(&eps[a]), task, a);
             if (!vec) split_store(xhi + a, xlo + a, act2[u]);
             if (ea.act_out && rm.env >= 0)
               ea.act_out[((static_cast<size_t>(e) * P.H + ea.t_out) * P.P + idx) * P.A + a] = act2[u];
@@ -1610,7 +1611,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
                 float v;
                 if (n < P.P) v = pa[static_cast<size_t>(n) * P.A + a];
                 else {
-                  v = __fadd_rn(sm_mean[a], __fmul_rn(sm_std[a], nz[static_cast<size_t>(n - P.P) * P.A + a]));
+                  v = __fadd_rn(sm_mean[a], __fmul_rn(sm_std[a], __ldcs(&nz[static_cast<size_t>(n - P.P) * P.A + a])));   // one-shot: evict-first
                   v = fminf(fmaxf(v, -1.f), 1.f);
                 }
                 v *= sm_mask[a];
@@ -1726,6 +1727,8 @@ __global__ void pick_kernel(const float* score, const float* elite_act0, const f
   const int lane = threadIdx.x & 31;
   if (e >= E) return;
   // argmax_k softmax(log(score_k) - log(expo_k)) == argmax of the logits (first max on ties)
+  // NaN logits (score == 0 together with expo == 0, or a NaN temperature) never win a comparison: the pick then stays
+  // at elite 0 (in range), where torch.argmax would return the first NaN position -- degenerate input either way.
   float best = -CUDART_INF_F;
   int bi = 0x7fffffff;
   for (int k = lane; k < K; k += 32) {
@@ -1738,6 +1741,7 @@ __global__ void pick_kernel(const float* score, const float* elite_act0, const f
     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
     if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
   }
+  if (bi < 0 || bi >= K) bi = 0;
   if (lane == 0 && pick_out) pick_out[e] = bi;
   for (int a = lane; a < A; a += 32) {
     float v = elite_act0[(static_cast<size_t>(e) * K + bi) * A + a];

@@ -49,7 +49,7 @@ static_assert(kPPSmemBytes <= 232448, "ping-pong kernel shared memory");
 // Diagnostics: clock stamps of CTA 0's first tile, [step][event] after the per-CTA counters (see TDMPC2_TRACE).
 #define PP_TRACE(P_, on_, s_, ev_)                                                           \
   do {                                                                                      \
-    if ((P_).prof && (on_) && (s_) < 32) (P_).prof[148 * 4 * 12 + (s_) * 16 + (ev_)] = clock64(); \
+    if ((P_).prof && (on_) && (s_) < 32) (P_).prof[static_cast<size_t>((P_).prof_slots) * 4 * 12 + (s_) * 16 + (ev_)] = clock64(); \
   } while (0)
 
 struct PPStep {

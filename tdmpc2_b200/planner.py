@@ -29,8 +29,10 @@ DEFAULT_ENGINE = os.environ.get("TDMPC2_B200_ENGINE", "tcgen05x2")
 @dataclass
 class Noise:
     """All random numbers of one batched plan() in reference draw order
-    (SURVEY.md section 8(a)).  Shapes: prior [E,H,P,A], r [E,I,H,N-P,A],
-    pi [E,I,N,A], qidx [E,I,2] int32, expo [E,K], final [E,A] or None (eval_mode)."""
+    (SURVEY.md section 8(a)), ITERATION-major so that every CEM iteration reads one
+    contiguous slab (no per-iteration copies):
+    prior [E,H,P,A], r [I,E,H,N-P,A], pi [I,E,N,A], qidx [I,E,2] int32, expo [E,K],
+    final [E,A] or None (eval_mode)."""
     prior: torch.Tensor
     r: torch.Tensor
     pi: torch.Tensor
@@ -38,9 +40,41 @@ class Noise:
     expo: torch.Tensor
     final: Optional[torch.Tensor]
 
+    @classmethod
+    def from_env_major(cls, prior, r, pi, qidx, expo, final, device=None) -> "Noise":
+        """From the oracle's environment-major layout (r [E,I,...], pi [E,I,...], qidx [E,I,2])."""
+        mv = lambda t: t if device is None else t.to(device)
+        return cls(mv(prior).contiguous(), mv(r).transpose(0, 1).contiguous(), mv(pi).transpose(0, 1).contiguous(),
+                   mv(qidx).to(torch.int32).transpose(0, 1).contiguous(), mv(expo).contiguous(),
+                   None if final is None else mv(final).contiguous())
+
+    def tensors(self):
+        return [t for t in (self.prior, self.r, self.pi, self.qidx, self.expo, self.final) if t is not None]
+
+
+def alloc_noise(cfg: Config, num_envs: int, device, eval_mode: bool = False) -> Noise:
+    """Uninitialised noise buffers of one plan() (the normal draws share ONE flat allocation so that a batched
+    draw is a single Philox launch)."""
+    H, N, P, A, I, K = (cfg.horizon, cfg.num_samples, cfg.num_pi_trajs, cfg.action_dim,
+                        cfg.iterations, cfg.num_elites)
+    E = num_envs
+    shapes = [(E, H, P, A), (I, E, H, N - P, A), (I, E, N, A)] + ([] if eval_mode else [(E, A)])
+    sizes = [int(torch.Size(sh).numel()) for sh in shapes]
+    pad = lambda n: (n + 63) // 64 * 64                     # keep every view 256-byte aligned
+    flat = torch.empty(sum(pad(n) for n in sizes), device=device, dtype=torch.float32)
+    views, off = [], 0
+    for sh, n in zip(shapes, sizes):
+        views.append(flat[off:off + n].view(sh))
+        off += pad(n)
+    nz = Noise(views[0], views[1], views[2], torch.empty(I, E, 2, device=device, dtype=torch.int32),
+               torch.empty(E, K, device=device, dtype=torch.float32), None if eval_mode else views[3])
+    nz._flat = flat
+    return nz
+
 
 def draw_noise(cfg: Config, num_envs: int, device, eval_mode: bool = False,
-               generator: Optional[torch.Generator] = None, reference_order: Optional[bool] = None) -> Noise:
+               generator: Optional[torch.Generator] = None, reference_order: Optional[bool] = None,
+               out: Optional[Noise] = None) -> Noise:
     """Draw the planner's noise with torch's generator on `device`.
 
     reference_order (default: num_envs == 1): issue the draws one by one in the
@@ -55,28 +89,28 @@ def draw_noise(cfg: Config, num_envs: int, device, eval_mode: bool = False,
     kw = dict(device=device, dtype=torch.float32, generator=g)
     if reference_order is None:
         reference_order = (E == 1)
+    nz = out if out is not None else alloc_noise(cfg, E, device, eval_mode)
     if reference_order and E == 1:
-        prior = torch.zeros(1, H, max(P, 0), A, device=device)
         for t in range(H if P > 0 else 0):
-            prior[0, t] = torch.randn(P, A, **kw)
-        r = torch.empty(1, I, H, N - P, A, device=device)
-        pi = torch.empty(1, I, N, A, device=device)
-        qidx = torch.empty(1, I, 2, device=device, dtype=torch.int32)
+            nz.prior[0, t] = torch.randn(P, A, **kw)
         for it in range(I):
-            r[0, it] = torch.randn(H, N - P, A, **kw)
-            pi[0, it] = torch.randn(N, A, **kw)
-            qidx[0, it] = torch.randperm(cfg.num_q, device=device, generator=g)[:2].to(torch.int32)
-        expo = torch.empty(1, K, device=device).exponential_(generator=g)
-        final = None if eval_mode else torch.randn(A, **kw).view(1, A)
-        return Noise(prior, r, pi, qidx, expo, final)
-    prior = torch.randn(E, H, P, A, **kw)
-    r = torch.randn(E, I, H, N - P, A, **kw)
-    pi = torch.randn(E, I, N, A, **kw)
-    # randperm(num_q)[:2] per (env, iteration): the two smallest of num_q iid uniforms
-    qidx = torch.rand(E, I, cfg.num_q, **kw).argsort(dim=-1)[..., :2].to(torch.int32).contiguous()
-    expo = torch.empty(E, K, device=device).exponential_(generator=g)
-    final = None if eval_mode else torch.randn(E, A, **kw)
-    return Noise(prior, r, pi, qidx, expo, final)
+            nz.r[it, 0] = torch.randn(H, N - P, A, **kw)
+            nz.pi[it, 0] = torch.randn(N, A, **kw)
+            nz.qidx[it, 0] = torch.randperm(cfg.num_q, device=device, generator=g)[:2].to(torch.int32)
+        nz.expo.exponential_(generator=g)
+        if not eval_mode:
+            nz.final[0] = torch.randn(A, **kw)
+        return nz
+    flat = getattr(nz, "_flat", None)
+    if flat is not None:
+        flat.normal_(generator=g)                            # prior | r | pi | final: one launch
+    else:
+        for t in (nz.prior, nz.r, nz.pi) + (() if nz.final is None else (nz.final,)):
+            t.normal_(generator=g)
+    # randperm(num_q)[:2] per (iteration, env): the two smallest of num_q iid uniforms
+    nz.qidx.copy_(torch.rand(I, E, cfg.num_q, **kw).argsort(dim=-1)[..., :2])
+    nz.expo.exponential_(generator=g)
+    return nz
 
 
 def discount_table(cfg: Config, device) -> torch.Tensor:
@@ -132,8 +166,15 @@ class Planner:
             self.workspace = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
             _cabi.check(self.lib.tdmpc2_planner_bind(h, self.packed.data_ptr(), self.workspace.data_ptr()))
         self.set_engine(engine)
+        # TDMPC2_B200_L2_PERSIST=1: keep the activation scratch in the persisting part of L2 (device-wide carve-out)
+        self.l2_persist = os.environ.get("TDMPC2_B200_L2_PERSIST", "0") not in ("", "0")
+        if self.l2_persist:
+            with torch.cuda.device(self.device):
+                _cabi.check(self.lib.tdmpc2_planner_set_l2_persist(self.h, 1))
         self._keep = []       # tensors referenced by in-flight async calls
         self.weights_version = None
+        self._graphs = {}     # eval_mode -> captured launch chain + its static buffers
+        self._graph_launches = 0
 
     def __del__(self):
         try:
@@ -153,7 +194,8 @@ class Planner:
 
     @property
     def launches(self) -> int:
-        return int(self.lib.tdmpc2_planner_launch_count(self.h))
+        """Kernels of this library launched so far (graph replays count the launches they contain)."""
+        return int(self.lib.tdmpc2_planner_launch_count(self.h)) + self._graph_launches
 
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -229,26 +271,16 @@ class Planner:
                                                        _ptr(out["pi_actions"]), _ptr(out["score"]), self._stream()))
         return out
 
-    def plan(self, obs, task, t0, prev_mean, noise: Noise, trace: bool = False):
-        """One batched plan().  obs [E,obs_dim] f32, task [E] int32 | None, t0 [E] uint8,
-        prev_mean [E,H,A] f32 (all on self.device, contiguous).  Returns (action [E,A],
-        new prev_mean [E,H,A], trace dict | None)."""
+    def _launch_chain(self, obs, task, t0, prev_mean, noise: Noise, action, new_mean, tr=None) -> None:
+        """prologue -> I x iter -> epilogue on the current stream (10 launches for I = 6)."""
         cfg, E, dev = self.cfg, self.E, self.device
-        action = torch.empty(E, cfg.action_dim, device=dev, dtype=torch.float32)
-        new_mean = torch.empty(E, cfg.horizon, cfg.action_dim, device=dev, dtype=torch.float32)
-        tr = None
-        if trace:
-            tr = dict(values=torch.empty(E, cfg.iterations, cfg.num_samples, device=dev),
-                      elite_idx=torch.empty(E, cfg.iterations, cfg.num_elites, device=dev, dtype=torch.int64),
-                      iter_mean=[], iter_std=[], pick=torch.empty(E, device=dev, dtype=torch.int32))
         self.prologue(obs, task, t0, prev_mean, noise.prior)
-        if trace:
+        if tr is not None:
             st = self.get_state()
             tr["z"], tr["pi_actions"] = st["z"], st["pi_actions"]
         for it in range(cfg.iterations):
-            nr, npi, qi = noise.r[:, it].contiguous(), noise.pi[:, it].contiguous(), noise.qidx[:, it].contiguous()
-            self._keep.extend([nr, npi, qi])
-            if trace:
+            nr, npi, qi = noise.r[it], noise.pi[it], noise.qidx[it]          # contiguous slabs of the [I, E, ...] tensors
+            if tr is not None:
                 v, ei = torch.empty(E, cfg.num_samples, device=dev), torch.empty(E, cfg.num_elites, device=dev, dtype=torch.int64)
                 self.iterate(nr, npi, qi, v, ei)
                 tr["values"][:, it], tr["elite_idx"][:, it] = v, ei
@@ -256,11 +288,73 @@ class Planner:
                 tr["iter_mean"].append(st["mean"]); tr["iter_std"].append(st["std"])
             else:
                 self.iterate(nr, npi, qi)
-        if trace:
+        if tr is not None:
             tr["score"] = self.get_state()["score"]
             tr["iter_mean"], tr["iter_std"] = torch.stack(tr["iter_mean"], 1), torch.stack(tr["iter_std"], 1)
-        self.epilogue(noise.expo, noise.final, action, new_mean, tr["pick"] if trace else None)
+        self.epilogue(noise.expo, noise.final, action, new_mean, tr["pick"] if tr is not None else None)
+
+    def plan(self, obs, task, t0, prev_mean, noise: Noise, trace: bool = False):
+        """One batched plan().  obs [E,obs_dim] f32, task [E] int32 | None, t0 [E] uint8,
+        prev_mean [E,H,A] f32 (all on self.device, contiguous).  Returns (action [E,A],
+        new prev_mean [E,H,A], trace dict | None)."""
+        cfg, E, dev = self.cfg, self.E, self.device
+        for t in noise.tensors():
+            if not t.is_contiguous():
+                raise ValueError("noise tensors must be contiguous (iteration-major: see planner.Noise)")
+        if noise.r.shape[:2] != (cfg.iterations, E) or noise.pi.shape[:2] != (cfg.iterations, E):
+            raise ValueError("noise.r / noise.pi must be [iterations, num_envs, ...] (Noise.from_env_major converts)")
+        action = torch.empty(E, cfg.action_dim, device=dev, dtype=torch.float32)
+        new_mean = torch.empty(E, cfg.horizon, cfg.action_dim, device=dev, dtype=torch.float32)
+        tr = None
+        if trace:
+            tr = dict(values=torch.empty(E, cfg.iterations, cfg.num_samples, device=dev),
+                      elite_idx=torch.empty(E, cfg.iterations, cfg.num_elites, device=dev, dtype=torch.int64),
+                      iter_mean=[], iter_std=[], pick=torch.empty(E, device=dev, dtype=torch.int32))
+        self._launch_chain(obs, task, t0, prev_mean, noise, action, new_mean, tr)
         return action, new_mean, tr
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the launch chain
+    def plan_graphed(self, obs, task, t0, prev_mean, eval_mode: bool = False,
+                     generator: Optional[torch.Generator] = None):
+        """plan() for the steady state (reference tdmpc2.py:45-55 replays a `reduce-overhead` CUDA graph): the
+        prologue -> I x iter -> epilogue chain is captured ONCE per eval_mode over static buffers and replayed; the
+        noise is drawn into the static buffers before every replay (batched draws unless E == 1, see draw_noise).
+        Returns (action [E,A], new prev_mean [E,H,A]) -- fresh tensors, the static outputs are copied out."""
+        cfg, E, dev = self.cfg, self.E, self.device
+        key = bool(eval_mode)
+        st = self._graphs.get(key)
+        if st is None:
+            st = self._capture(key)
+        st["obs"].copy_(obs, non_blocking=True)
+        st["t0"].copy_(t0, non_blocking=True)
+        st["prev"].copy_(prev_mean, non_blocking=True)
+        if st["task"] is not None:
+            st["task"].copy_(task, non_blocking=True)
+        draw_noise(cfg, E, dev, eval_mode=eval_mode, generator=generator, out=st["noise"])
+        st["graph"].replay()
+        self._graph_launches += st["launches"]
+        return st["action"].clone(), st["new_mean"].clone()
+
+    def _capture(self, eval_mode: bool):
+        cfg, E, dev = self.cfg, self.E, self.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        st = dict(obs=torch.zeros(E, cfg.obs_shape["state"][0], **f32), t0=torch.ones(E, device=dev, dtype=torch.uint8),
+                  prev=torch.zeros(E, cfg.horizon, cfg.action_dim, **f32),
+                  task=torch.zeros(E, device=dev, dtype=torch.int32) if cfg.multitask else None,
+                  noise=alloc_noise(cfg, E, dev, eval_mode), action=torch.empty(E, cfg.action_dim, **f32),
+                  new_mean=torch.empty(E, cfg.horizon, cfg.action_dim, **f32))
+        draw_noise(cfg, E, dev, eval_mode=eval_mode, out=st["noise"], reference_order=False)
+        args = (st["obs"], st["task"], st["t0"], st["prev"], st["noise"], st["action"], st["new_mean"])
+        self._launch_chain(*args)                      # eager warm-up: lazy function attributes are set outside capture
+        torch.cuda.current_stream(dev).synchronize()
+        n0 = self.launches
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._launch_chain(*args)
+        st["graph"], st["launches"] = g, self.launches - n0
+        self._graph_launches -= st["launches"]         # the capture pass itself launched nothing
+        self._graphs[eval_mode] = st
+        return st
 
     def estimate_value(self, z, actions, task, noise_pi, qidx):
         """z [E,N,L], actions [E,H,N,A], noise_pi [E,N,A], qidx [E,2] int32 -> [E,N]."""

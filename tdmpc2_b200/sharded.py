@@ -37,10 +37,18 @@ class ShardedActor:
             return x
         return x[self.lo:self.hi]
 
-    def act(self, obs, t0=False, task=None, **kw) -> torch.Tensor:
-        a_local = self.plan_local(self.local(obs), self.local(t0) if torch.is_tensor(t0) else t0, self.local(task), **kw)
+    def gather(self, a_local: torch.Tensor) -> torch.Tensor:
+        """[E/G, A] of every rank -> [E, A] in rank order: the ONE collective of a sharded plan()."""
         if self.world == 1:
             return a_local
         out = torch.empty(self.num_envs, a_local.shape[-1], dtype=a_local.dtype, device=a_local.device)
         dist.all_gather_into_tensor(out, a_local.contiguous(), group=self.group)
         return out
+
+    def act_local(self, obs_local, t0=False, task=None, **kw) -> torch.Tensor:
+        """This rank's shard in (already sliced), GLOBAL actions out."""
+        return self.gather(self.plan_local(obs_local, t0, task, **kw))
+
+    def act(self, obs, t0=False, task=None, **kw) -> torch.Tensor:
+        """GLOBAL batch in, GLOBAL actions out."""
+        return self.act_local(self.local(obs), self.local(t0) if torch.is_tensor(t0) else t0, self.local(task), **kw)

@@ -41,6 +41,7 @@ class TDMPC2(torch.nn.Module):
         self._planner: Optional[Planner] = None
         self._weights_dirty = True
         self.generator: Optional[torch.Generator] = None     # None -> torch's default CUDA generator, like the reference
+        self._use_graph = bool(cfg.get("cuda_graph", True))   # replay the launch chain as one CUDA graph (cfg.compile's role)
 
     # ------------------------------------------------------------------ planner plumbing
     @property
@@ -121,12 +122,25 @@ class TDMPC2(torch.nn.Module):
                 raise ValueError("multi-task model needs `task`")
             taskv = torch.as_tensor(task, device=dev).reshape(-1).to(torch.int32)
             taskv = taskv.expand(E).contiguous() if taskv.numel() == 1 else taskv.contiguous()
-        if noise is None:
-            noise = draw_noise(cfg, E, dev, eval_mode=eval_mode, generator=self.generator)
-        elif eval_mode:
-            noise = Noise(noise.prior, noise.r, noise.pi, noise.qidx, noise.expo, None)
         prev = self._prev_mean.reshape(E, cfg.horizon, cfg.action_dim).contiguous()
-        action, new_mean, trace = self.planner.plan(obs, taskv, t0v, prev, noise, trace=return_trace)
+        trace = None
+        if noise is None and not return_trace and self._use_graph:
+            # steady state: replay the captured prologue -> I x iter -> epilogue chain (tdmpc2.py:45-55 replays a
+            # `reduce-overhead` graph); noise is drawn into the graph's static buffers
+            try:
+                action, new_mean = self.planner.plan_graphed(obs, taskv, t0v, prev, eval_mode=eval_mode,
+                                                             generator=self.generator)
+            except RuntimeError as e:                      # capture unsupported here: keep the eager launch chain
+                import warnings
+                warnings.warn(f"CUDA-graph capture of the plan chain failed ({e}); launching eagerly")
+                self._use_graph = False
+                return self._plan(obs, t0=t0, eval_mode=eval_mode, task=task)
+        else:
+            if noise is None:
+                noise = draw_noise(cfg, E, dev, eval_mode=eval_mode, generator=self.generator)
+            elif eval_mode:
+                noise = Noise(noise.prior, noise.r, noise.pi, noise.qidx, noise.expo, None)
+            action, new_mean, trace = self.planner.plan(obs, taskv, t0v, prev, noise, trace=return_trace)
         self._prev_mean.copy_(new_mean.reshape(self._prev_mean.shape))           # tdmpc2.py:205
         out = action[0] if E == 1 else action
         return (out, trace) if return_trace else out

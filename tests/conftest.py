@@ -2,6 +2,10 @@ import os
 import sys
 
 import pytest
+import torch
+
+# The CPU oracle is eager PyTorch on small GEMMs: it collapses on a 100+ core host (barrier overhead); 16 is plenty.
+torch.set_num_threads(max(1, min(16, os.cpu_count() or 1)))
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:

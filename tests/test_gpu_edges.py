@@ -23,9 +23,7 @@ def _run_and_compare(cfg, E, sd, seed=11, eval_mode=False, obs_scale=1.0, atol_v
     want = plan_oracle(cfg, sd, obs, task=task, t0=t0, prev_mean=prev, noise=n, eval_mode=eval_mode)
     pl = Planner(cfg, E, "cuda:0")
     pl.pack(sd)
-    noise = Noise(n.prior.cuda().contiguous(), n.r.cuda().contiguous(), n.pi.cuda().contiguous(),
-                  n.qidx.to(torch.int32).cuda().contiguous(), n.expo.cuda().contiguous(),
-                  None if eval_mode else n.final.cuda().contiguous())
+    noise = Noise.from_env_major(n.prior, n.r, n.pi, n.qidx, n.expo, None if eval_mode else n.final, device="cuda")
     taskv = torch.tensor(task, dtype=torch.int32).cuda() if task is not None else None
     action, new_mean, tr = pl.plan(obs.cuda().contiguous(), taskv, torch.tensor(t0, dtype=torch.uint8).cuda(),
                                    prev.cuda().contiguous(), noise, trace=True)

@@ -32,8 +32,7 @@ def test_agent_matches_reference_golden(name):
     checked_actions = 0
     for c in calls:
         n = oracle_noise(cfg, c["seed"], 1, eval_mode=c["eval_mode"])
-        noise = Noise(n.prior.cuda(), n.r.cuda(), n.pi.cuda(), n.qidx.to(torch.int32).cuda(), n.expo.cuda(),
-                      None if c["eval_mode"] else n.final.cuda())
+        noise = Noise.from_env_major(n.prior, n.r, n.pi, n.qidx, n.expo, None if c["eval_mode"] else n.final, device="cuda")
         agent._prev_mean.copy_(c["prev_mean"].cuda())
         action, tr = agent._plan(c["obs"].cuda().unsqueeze(0), t0=c["t0"], eval_mode=c["eval_mode"],
                                  task=None if c["task"] is None else torch.tensor([c["task"]]).cuda(),

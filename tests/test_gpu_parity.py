@@ -94,9 +94,7 @@ def test_fused_layer_matches_fp64(engine, wl):
 
 def _to_gpu_noise(n, eval_mode):
     from tdmpc2_b200.planner import Noise
-    return Noise(n.prior.cuda().contiguous(), n.r.cuda().contiguous(), n.pi.cuda().contiguous(),
-                 n.qidx.to(torch.int32).cuda().contiguous(), n.expo.cuda().contiguous(),
-                 None if eval_mode else n.final.cuda().contiguous())
+    return Noise.from_env_major(n.prior, n.r, n.pi, n.qidx, n.expo, None if eval_mode else n.final, device="cuda")
 
 
 CASES = [  # workload, E, perturb, emb_scale, eval_mode
