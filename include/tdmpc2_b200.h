@@ -138,6 +138,11 @@ int tdmpc2_planner_set_engine(tdmpc2_planner* p, int engine);
  * persisting part of L2 (sets the DEVICE-wide cudaLimitPersistingL2CacheSize, hence opt-in); 0 switches it off.
  * No reference counterpart (the reference's activations are ordinary torch tensors). */
 int tdmpc2_planner_set_l2_persist(tdmpc2_planner* p, int enable);
+/* Accuracy knob of layers wider than 512 outputs (48M / 317M presets).  The tensor core's fp32 accumulator rounds toward
+ * zero on every K = 16 step, so its error grows with the reduction length K; with k_elems > 0 the partial sums are
+ * flushed to fp32 every k_elems elements of K and added with round-to-nearest (one extra accumulator drain per
+ * segment).  0 = whole K in one accumulation.  No reference counterpart. */
+int tdmpc2_planner_set_kseg(tdmpc2_planner* p, int k_elems);
 /* Replaces: agent.load()/WorldModel.to(device) weight placement (tdmpc2.py:81-95).
  * Packs the state-dict tensors into the kernel layout: per Linear two fp16
  * planes (hi, lo) of weight * 2^k, K-major, zero-padded; applies the

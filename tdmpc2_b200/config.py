@@ -160,6 +160,11 @@ def workload(name: str, **overrides: Any) -> Config:
                   enc_dim=96, mlp_dim=640, latent_dim=64, num_enc_layers=2, num_q=3,
                   num_envs=2, num_samples=128, num_elites=16, num_pi_trajs=8,
                   horizon=2, iterations=2)
+    elif name == "tiny-wide2":  # wide hidden (2 full super-chunks + 128), wide SimNorm latent, wide encoder; 2 tiles per env
+        kw = dict(obs_dim=19, action_dim=7, model_size=None, task="tiny-wide2",
+                  enc_dim=640, mlp_dim=1152, latent_dim=576, num_enc_layers=2, num_q=2,
+                  num_envs=2, num_samples=256, num_elites=16, num_pi_trajs=8,
+                  horizon=2, iterations=2)
     elif name == "tiny-mt":  # test-sized multi-task model
         kw = dict(obs_dim=11, action_dim=5, model_size=None, task="tiny-mt",
                   tasks=[f"t{i}" for i in range(4)], action_dims=[5, 3, 4, 2],

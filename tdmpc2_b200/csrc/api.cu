@@ -129,6 +129,7 @@ struct tdmpc2_planner {
   int engine = TDMPC2_ENGINE_TCGEN05;
   bool bound = false, weights_ok = false, smem_attr_set[2] = {false, false}, smem_attr_pair = false, smem_attr_pp = false, all_fused = true;
   int64_t launches = 0;
+  int kseg = 0;                     // wide layers: K-chunks per TMEM accumulation segment (0 = whole K)
   size_t l2_window_bytes = 0;       // > 0: launches carry a persisting-L2 access-policy window over the activation scratch
   float l2_hit_ratio = 1.f;
   bool pair_ok = true;              // every layer of the CEM iteration can run as cta_group::2
@@ -237,7 +238,7 @@ extern "C" int tdmpc2_planner_create(const tdmpc2_dims* dims, tdmpc2_planner** o
   p->Ppad = 1;
   while (p->Ppad < d.num_pi_trajs) p->Ppad <<= 1;
   p->tiles_per_env = (d.num_samples + kTileM - 1) / kTileM;
-  p->pair_ok = p->all_fused;
+  p->pair_ok = true;   // fused layers and the super-chunked wide layers both run as cta_group::2
 
   // ---- packed blob layout
   size_t off = 0;
@@ -305,6 +306,15 @@ extern "C" int tdmpc2_planner_set_engine(tdmpc2_planner* p, int engine) {
              engine != TDMPC2_ENGINE_TCGEN05_PP && engine != TDMPC2_ENGINE_TCGEN05_2SM_PF))
     return fail(TDMPC2_ERR_INVALID, "bad engine");
   p->engine = engine;
+  return 0;
+}
+
+// Wide layers (output wider than the 512 TMEM columns): flush the TMEM partial sums to fp32 every `k_elems` elements of
+// the reduction dimension (rounded to 64-element chunks) and add the segments with round-to-nearest.  0 = accumulate the
+// whole reduction in TMEM (fastest).
+extern "C" int tdmpc2_planner_set_kseg(tdmpc2_planner* p, int k_elems) {
+  if (!p || k_elems < 0) return fail(TDMPC2_ERR_INVALID, "bad kseg");
+  p->kseg = (k_elems + kKch - 1) / kKch;
   return 0;
 }
 
@@ -522,6 +532,7 @@ static int launch_plan(tdmpc2_planner* p, const PlanParams& prm, int ntiles, cud
   PlanParams prm2 = prm;
   prm2.prof = p->prof;
   prm2.prof_slots = p->nslots;
+  prm2.kseg = p->kseg;
   // CTA-pair (cta_group::2) launch: CEM iterations only, whole pairs of tiles of one environment
   const bool pair_engine = (p->engine == TDMPC2_ENGINE_TCGEN05_2SM || p->engine == TDMPC2_ENGINE_TCGEN05_PP ||
                             p->engine == TDMPC2_ENGINE_TCGEN05_2SM_PF);

@@ -129,6 +129,8 @@ struct PlanParams {
   long long* prof;   // optional [prof_slots][4][12] cycle counters + [32][16] trace stamps of CTA 0 (diagnostics), or nullptr
   int prof_slots;    // = number of scratch slots (SM count)
   int li_term;       // first of the 3 termination-head layers (cfg.episodic, world_model.py:28), or -1
+  int kseg;          // wide layers: K-chunks (of 64) accumulated in TMEM before the partial sum is flushed to the fp32 raw
+                     // scratch and added there with round-to-nearest (0 = the whole K in one go); see epi_wide
 };
 
 // What a layer's epilogue has to do besides the activation itself.
@@ -375,41 +377,35 @@ __device__ __forceinline__ void prod_load_w(Ctx& c, const CUtensorMap* tmW, cons
   ++c.pw_it;
 }
 
-template <bool FUSED>
-__device__ __forceinline__ void tc_producer(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf, const LayerDev* next) {
-  const int nkc = ly.Kpad / kKch;
-  const int nnc = (ly.Npad + kNch - 1) / kNch;
+// N-chunks [nc0, nc0 + nnc_lim) of the layer (default: all of them): K-chunks outermost, each A chunk is loaded once
+// and multiplied with every N-chunk of the range; layers wider than TMEM call this once per 512-column super-chunk.
+__device__ __forceinline__ void tc_producer(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf, const LayerDev* next,
+                                            int nc0 = 0, int nnc_lim = 1 << 30, int kc0 = 0, int kc_lim = 1 << 30) {
+  const int nkc = min(ly.Kpad / kKch, kc0 + kc_lim);
+  const int nnc = min((ly.Npad + kNch - 1) / kNch - nc0, nnc_lim);
   const CUtensorMap* tmA = (srcbuf == BUF_X) ? &P.tmX : &P.tmH;
   const CUtensorMap* tmW = &P.tmW[ly.wmap];
   const int arow_hi = plane_row0(P, c.slot, srcbuf, 0), arow_lo = plane_row0(P, c.slot, srcbuf, 1);
   TDMPC2_TRACE(P, c, 1);
-  if (FUSED) {
-    uint32_t skip = c.wpf ? c.w_pref : 0u;     // chunks the previous layer's producer pass already requested
-    for (int kc = 0; kc < nkc; ++kc) {
-      prod_load_a(P, c, tmA, kc, arow_hi, arow_lo);
-      for (int nc = 0; nc < nnc; ++nc) {
-        if (skip) --skip;
-        else prod_load_w(c, tmW, ly, kc, nc);
-      }
+  uint32_t skip = c.wpf ? c.w_pref : 0u;     // chunks the previous layer's producer pass already requested
+  for (int kc = kc0; kc < nkc; ++kc) {
+    prod_load_a(P, c, tmA, kc, arow_hi, arow_lo);
+    for (int nc = nc0; nc < nc0 + nnc; ++nc) {
+      if (skip) --skip;
+      else prod_load_w(c, tmW, ly, kc, nc);
     }
-    if (c.wpf) {
-      // The W ring drains while this layer's last MMAs retire and then idles through the whole epilogue (which
-      // stages its output in the A ring in this mode): fill it with the head of the next layer's weight stream.
-      uint32_t n = 0;
-      if (next) {
-        const CUtensorMap* tmW2 = &P.tmW[next->wmap];
-        const int nkc2 = next->Kpad / kKch, nnc2 = (next->Npad + kNch - 1) / kNch;
-        for (int kc = 0; kc < nkc2 && n < c.w_ring; ++kc)
-          for (int nc = 0; nc < nnc2 && n < c.w_ring; ++nc) { prod_load_w(c, tmW2, *next, kc, nc); ++n; }
-      }
-      c.w_pref = n;
+  }
+  if (c.wpf) {
+    // The W ring drains while this layer's last MMAs retire and then idles through the whole epilogue (which
+    // stages its output in the A ring in this mode): fill it with the head of the next layer's weight stream.
+    uint32_t n = 0;
+    if (next) {
+      const CUtensorMap* tmW2 = &P.tmW[next->wmap];
+      const int nkc2 = next->Kpad / kKch, nnc2 = (next->Npad + kNch - 1) / kNch;
+      for (int kc = 0; kc < nkc2 && n < c.w_ring; ++kc)
+        for (int nc = 0; nc < nnc2 && n < c.w_ring; ++nc) { prod_load_w(c, tmW2, *next, kc, nc); ++n; }
     }
-  } else {
-    for (int nc = 0; nc < nnc; ++nc)
-      for (int kc = 0; kc < nkc; ++kc) {
-        prod_load_a(P, c, tmA, kc, arow_hi, arow_lo);
-        prod_load_w(c, tmW, ly, kc, nc);
-      }
+    c.w_pref = n;
   }
 }
 
@@ -447,89 +443,36 @@ __device__ __forceinline__ uint32_t mma_wait_w(Ctx& c) {
   return s;
 }
 
-template <bool FUSED>
-__device__ __forceinline__ void tc_mma(const PlanParams& P, Ctx& c, const LayerDev& ly) {
-  const int nkc = ly.Kpad / kKch;
-  const int nnc = (ly.Npad + kNch - 1) / kNch;
+// Accumulates N-chunks [nc0, nc0 + nnc_lim) of the layer into TMEM columns [0, 256 * nnc); facc[0] fires when all of
+// them are complete.
+__device__ __forceinline__ void tc_mma(const PlanParams& P, Ctx& c, const LayerDev& ly, int nc0 = 0, int nnc_lim = 1 << 30,
+                                       int kc0 = 0, int kc_lim = 1 << 30) {
+  const int nkc = min(ly.Kpad / kKch, kc0 + kc_lim);
+  const int nnc = min((ly.Npad + kNch - 1) / kNch - nc0, nnc_lim);
   const uint32_t sbase = ptx::smem_u32(c.stage_base);
-  if (FUSED) {
-    for (int kc = 0; kc < nkc; ++kc) {
-      const uint32_t as = mma_wait_a(c);
-      if (kc == 0) TDMPC2_TRACE(P, c, 2);
-      for (int nc = 0; nc < nnc; ++nc) {
-        const uint32_t ws = mma_wait_w(c);
-        ptx::tc_fence_after();
-        const int ncols = min(kNch, ly.Npad - nc * kNch);
-        mma_stage(c.tmem_base + nc * kNch, sbase + as * kASlotBytes, sbase + kWRingOff + ws * c.w_stride, c.w_lo_off,
-                  ptx::make_idesc_f16(c.cg2 ? 2 * kTileM : kTileM, ncols), kc == 0, c.cg2 != 0);
-        if (c.cg2) ptx::umma_commit_2sm(&c.w_empty[ws]);
-        else ptx::umma_commit(&c.w_empty[ws]);     // frees the W slot when these MMAs retire
-        ++c.mw_it;
-      }
-      if (c.cg2) ptx::umma_commit_2sm(&c.a_empty[as]);
-      else ptx::umma_commit(&c.a_empty[as]);
-      ++c.ma_it;
-    }
-    if (c.cg2) ptx::umma_commit_2sm(&c.facc[0]);
-    else ptx::umma_commit(&c.facc[0]);
-    TDMPC2_TRACE(P, c, 3);
-  } else {
-    for (int nc = 0; nc < nnc; ++nc) {
-      const int ncols = min(kNch, ly.Npad - nc * kNch);
-      const uint32_t idesc = ptx::make_idesc_f16(kTileM, ncols);
-      const uint32_t slot = c.a_it & 1, aph = (c.a_it >> 1) & 1;
-      ptx::mbar_wait(&c.acc_empty[slot], aph ^ 1);
+  for (int kc = kc0; kc < nkc; ++kc) {
+    const uint32_t as = mma_wait_a(c);
+    if (kc == kc0) TDMPC2_TRACE(P, c, 2);
+    for (int nc = nc0; nc < nc0 + nnc; ++nc) {
+      const uint32_t ws = mma_wait_w(c);
       ptx::tc_fence_after();
-      for (int kc = 0; kc < nkc; ++kc) {
-        const uint32_t as = mma_wait_a(c);
-        const uint32_t ws = mma_wait_w(c);
-        ptx::tc_fence_after();
-        mma_stage(c.tmem_base + slot * kNch, sbase + as * kASlotBytes, sbase + kWRingOff + ws * c.w_stride, c.w_lo_off, idesc, kc == 0, false);
-        ptx::umma_commit(&c.w_empty[ws]);
-        ptx::umma_commit(&c.a_empty[as]);
-        ++c.mw_it; ++c.ma_it;
-      }
-      ptx::umma_commit(&c.acc_full[slot]);
-      ++c.a_it;
+      const int ncols = min(kNch, ly.Npad - nc * kNch);
+      mma_stage(c.tmem_base + (nc - nc0) * kNch, sbase + as * kASlotBytes, sbase + kWRingOff + ws * c.w_stride, c.w_lo_off,
+                ptx::make_idesc_f16(c.cg2 ? 2 * kTileM : kTileM, ncols), kc == kc0, c.cg2 != 0);
+      if (c.cg2) ptx::umma_commit_2sm(&c.w_empty[ws]);
+      else ptx::umma_commit(&c.w_empty[ws]);     // frees the W slot when these MMAs retire
+      ++c.mw_it;
     }
+    if (c.cg2) ptx::umma_commit_2sm(&c.a_empty[as]);
+    else ptx::umma_commit(&c.a_empty[as]);
+    ++c.ma_it;
   }
+  if (c.cg2) ptx::umma_commit_2sm(&c.facc[0]);
+  else ptx::umma_commit(&c.facc[0]);
+  TDMPC2_TRACE(P, c, 3);
 }
 
-// ------------------------------------------------------------------------------------ wide path: GEMM -> raw scratch
-__device__ __forceinline__ void gemm_tc_wide(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf) {
-  const int nnc = (ly.Npad + kNch - 1) / kNch;
-  if (c.warp == 0) {
-    if (c.lane == 0) tc_producer<false>(P, c, ly, srcbuf, nullptr);
-  } else if (c.warp == 1) {
-    if (c.lane == 0) tc_mma<false>(P, c, ly);
-  } else if (c.warp >= kEpiWarp0 && c.warp < kEpiWarp0 + 4) {
-    // TMEM drain: accumulator chunk -> raw scratch (fp32)
-    const int q = c.warp & 3;                  // TMEM lane quarter this warp may touch
-    const int row = q * 32 + c.lane;
-    float* rawrow = raw_ptr(P, c.slot) + static_cast<size_t>(row) * P.NpadMax;
-    for (int nc = 0; nc < nnc; ++nc) {
-      const int ncols = min(kNch, ly.Npad - nc * kNch);
-      const uint32_t slot = c.d_it & 1, dph = (c.d_it >> 1) & 1;
-      ptx::mbar_wait(&c.acc_full[slot], dph);
-      ptx::tc_fence_after();
-      for (int c0 = 0; c0 < ncols; c0 += 32) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(c.tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * kNch + c0, v);
-        ptx::tmem_ld_wait();
-        float4* dst = reinterpret_cast<float4*>(rawrow + nc * kNch + c0);
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          __stcg(dst + i, make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                      __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
-      }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&c.acc_empty[slot]);
-      ++c.d_it;
-    }
-  }
-  __syncthreads();
-}
-
+// ------------------------------------------------------------------------------------ SIMT engine: GEMM -> raw scratch
 // Same operands, plain fp32 FFMA on CUDA cores (exact products of the split operands).
 __device__ __forceinline__ void gemm_simt(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf) {
   constexpr int BN = 64, BK = 32;
@@ -1239,6 +1182,299 @@ __device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, cons
   }
 }
 
+// ------------------------------------------------------------------------------------ layers wider than TMEM (48M / 317M presets)
+// A LayerNorm layer with Npad > 512 is produced in SUPER-CHUNKS of 512 output columns (the whole TMEM): each is one
+// fused-style GEMM -- K outermost, the A K-chunks streamed once per super-chunk, weights split over the CTA pair --
+// after which all 16 epilogue warps DRAIN the accumulator: x = acc * 2^-k + bias goes to the slot's fp32 raw scratch,
+// stored column-major ([col][128 rows]: a warp's 32 rows of one column are one 128-byte line) while the thread that
+// owns (row, column group) keeps running shifted moments of its row.  The MMA issuer waits for the drain (acc_empty)
+// before it overwrites TMEM; the TMA producer meanwhile refills the operand rings for the next super-chunk.  After the
+// last super-chunk the row statistics are merged across the 4 column groups (Chan) and ONE pass over the raw scratch
+// normalises, activates, splits to fp16 hi/lo and sends the planes out through swizzled smem tiles + TMA stores.
+// Every thread reads back exactly the raw elements it wrote itself.
+struct WideCols { int cb, ncols; };
+__device__ __forceinline__ WideCols wide_cols(const LayerDev& ly, int sc, int grp) {
+  const int wsc = min(kFusedMaxN, ly.Npad - sc * kFusedMaxN);     // 128 .. 512, multiple of 128
+  const int nblocks = wsc / 64;
+  const int bpg = (nblocks + kEpiGroups - 1) / kEpiGroups;
+  WideCols w;
+  w.cb = grp * bpg * 64;
+  w.ncols = max(0, min(bpg * 64, wsc - w.cb));
+  return w;
+}
+
+template <int KIND>   // EPI_LN_MISH | EPI_LN_SIMNORM
+__device__ __forceinline__ void wide_pass2(const PlanParams& P, Ctx& c, const EpiThread& et, const LayerDev& ly, const EpiArgs& ea,
+                                           int nsc, float rstd, float nmr) {
+  const int N = ly.N;
+  const float* rawT = raw_ptr(P, c.slot) + et.row;
+  const bool planes = ea.dstbuf >= 0;
+  const bool use_tma = planes && (N % 32 == 0) && (ea.dst_col0 % 32 == 0);
+  uint8_t* stg = c.stage_base + kWRingOff + et.grp * (2 * kStgBuf);   // W ring: idle, every MMA of the layer has retired
+  const bool leader = (et.q == 0) && (c.lane == 0);
+  const CUtensorMap* tmD = (ea.dstbuf == BUF_X) ? &P.tmXs : &P.tmHs;
+  const uint32_t swz = static_cast<uint32_t>((et.row >> 1) & 3);
+  const int row_hi = planes ? plane_row0(P, c.slot, ea.dstbuf, 0) : 0, row_lo = planes ? plane_row0(P, c.slot, ea.dstbuf, 1) : 0;
+  __half* dhi = planes ? plane_ptr(P, c.slot, ea.dstbuf, 0) + static_cast<size_t>(et.row) * plane_pitch(P, ea.dstbuf) + ea.dst_col0 : nullptr;
+  __half* dlo = planes ? plane_ptr(P, c.slot, ea.dstbuf, 1) + static_cast<size_t>(et.row) * plane_pitch(P, ea.dstbuf) + ea.dst_col0 : nullptr;
+  const int orow = ea.rowmap ? ea.rowmap[et.row] : et.row;
+  float* po = (ea.out_f32 && orow >= 0) ? ea.out_f32 + static_cast<size_t>(orow) * ea.out_pitch : nullptr;
+  const float2 rstd2 = f2s(rstd), nmr2 = f2s(nmr);
+  int kb = 0;                                                       // staging-buffer parity (per group, uniform)
+  for (int sc = 0; sc < nsc; ++sc) {
+    const WideCols wc = wide_cols(ly, sc, et.grp);
+    for (int c0 = wc.cb; c0 < wc.cb + wc.ncols; c0 += 32) {
+      const int gcol = sc * kFusedMaxN + c0;
+      if (gcol >= N) break;                                         // zero-padding columns: nothing to emit
+      uint8_t* buf = stg + (kb & 1) * kStgBuf;
+      const uint32_t rowaddr = ptx::smem_u32(buf) + static_cast<uint32_t>(et.row) * 64u;
+      if (use_tma && kb >= 2) {                                     // buffer reuse: its previous store must have read it
+        if (leader) ptx::bulk_wait_read<1>();
+        group_bar_sync(et.grp);
+      }
+#pragma unroll
+      for (int sub = 0; sub < 32; sub += 16) {
+        float y[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) y[i] = __ldcg(rawT + static_cast<size_t>(gcol + sub + i) * kTileM);
+        const bool full = (gcol + sub + 16 <= N);
+#pragma unroll
+        for (int i4 = 0; i4 < 16; i4 += 4) {
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(ly.ln_g + gcol + sub + i4));
+          const float4 e4 = __ldg(reinterpret_cast<const float4*>(ly.ln_b + gcol + sub + i4));
+          float2 t0 = __ffma2_rn(__ffma2_rn(f2(y[i4], y[i4 + 1]), rstd2, nmr2), f2(g4.x, g4.y), f2(e4.x, e4.y));
+          float2 t1 = __ffma2_rn(__ffma2_rn(f2(y[i4 + 2], y[i4 + 3]), rstd2, nmr2), f2(g4.z, g4.w), f2(e4.z, e4.w));
+          if (KIND == EPI_LN_MISH) { t0 = mish_fast2(t0); t1 = mish_fast2(t1); }
+          y[i4] = t0.x; y[i4 + 1] = t0.y; y[i4 + 2] = t1.x; y[i4 + 3] = t1.y;
+        }
+        if (!full) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (gcol + sub + i >= N) y[i] = (KIND == EPI_LN_MISH) ? 0.f : -CUDART_INF_F;
+        }
+        if (KIND == EPI_LN_SIMNORM) {
+          // SimNorm: softmax over groups of 8 consecutive columns (layers.py:84-88)
+#pragma unroll
+          for (int g0 = 0; g0 < 16; g0 += 8) {
+            float m = y[g0];
+#pragma unroll
+            for (int i = 1; i < 8; ++i) m = fmaxf(m, y[g0 + i]);
+            float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { y[g0 + i] = exp_fast(y[g0 + i] - m); t += y[g0 + i]; }
+            const float rt = rcp_ftz(t);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) y[g0 + i] *= rt;
+          }
+        }
+        if (po) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (gcol + sub + i < N) po[gcol + sub + i] = y[i];
+        }
+        if (use_tma) {
+          uint32_t hw[8], lw[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float a0 = y[2 * i], a1 = y[2 * i + 1];
+            const __half2 h2 = __floats2half2_rn(a0, a1);
+            const float2 hf = __half22float2(h2);
+            const float2 df = __fadd2_rn(f2(a0, a1), f2(-hf.x, -hf.y));
+            const __half2 l2 = __floats2half2_rn(df.x, df.y);
+            hw[i] = *reinterpret_cast<const uint32_t*>(&h2);
+            lw[i] = *reinterpret_cast<const uint32_t*>(&l2);
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const uint32_t off = ((static_cast<uint32_t>((sub >> 3) + i) ^ swz) << 4);
+            ptx::st_shared_v4(rowaddr + off, hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
+            ptx::st_shared_v4(rowaddr + kStgPlane + off, lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]);
+          }
+        } else if (planes) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (gcol + sub + i < N) split_store(dhi + gcol + sub + i, dlo + gcol + sub + i, y[i]);
+        }
+      }
+      if (use_tma) {
+        ptx::fence_proxy_async_smem();
+        group_bar_sync(et.grp);
+        if (leader) {
+          ptx::tma_store_2d(tmD, buf, ea.dst_col0 + gcol, row_hi);
+          ptx::tma_store_2d(tmD, buf + kStgPlane, ea.dst_col0 + gcol, row_lo);
+          ptx::bulk_commit();
+        }
+        ++kb;
+      }
+    }
+  }
+  if (use_tma && leader) ptx::bulk_wait<0>();                      // stores performed before the layer is published
+}
+
+// Epilogue warps of a wide layer (EPI_LN_MISH | EPI_LN_SIMNORM | EPI_RAW).
+__device__ __forceinline__ void epi_wide(const PlanParams& P, Ctx& c, const LayerDev& ly, const EpiArgs& ea, int nsc, int nseg) {
+  const EpiThread et = epi_thread(c);
+  const int N = ly.N;
+  const float inv_scale = ly.inv_scale;
+  const bool is_ln = (ea.kind != EPI_RAW);
+  float* rawT = raw_ptr(P, c.slot) + et.row;                        // element (col, row) at rawT[col * 128]
+  // running shifted moments of this thread's row over the columns of its group (all super-chunks)
+  float x0 = 0.f, s = 0.f, q = 0.f;
+  float2 sa = f2s(0.f), sbb = f2s(0.f), qa = f2s(0.f), qb = f2s(0.f);
+  bool have_x0 = false;
+  const float2 inv2 = f2s(inv_scale);
+  for (int sc = 0; sc < nsc; ++sc) {
+   const WideCols wc = wide_cols(ly, sc, et.grp);
+   for (int seg = 0; seg < nseg; ++seg) {
+    // K-segments: the tensor core's fp32 accumulator rounds toward zero on every K = 16 step, an error that grows
+    // linearly with the reduction length; flushing the partial sum every P.kseg K-chunks and adding the segments here
+    // with round-to-nearest bounds it (at the price of one more drain per segment).
+    const bool last_seg = (seg == nseg - 1);
+    {
+      const long long tw = clock64();
+      ptx::mbar_wait_long(&c.facc[0], c.fph0 ^ static_cast<uint32_t>((sc * nseg + seg) & 1));
+      c.pf2 += clock64() - tw;
+    }
+    ptx::tc_fence_after();
+    for (int c0 = wc.cb; c0 < wc.cb + wc.ncols; c0 += 32) {
+      const int gcol = sc * kFusedMaxN + c0;
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(et.taddr + c0, v);
+      if (seg == 0) {
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i4 = 0; i4 < 32; i4 += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(ly.bias + gcol + i4));
+          const float2 xa = __ffma2_rn(f2(__uint_as_float(v[i4]), __uint_as_float(v[i4 + 1])), inv2, f2(b4.x, b4.y));
+          const float2 xb = __ffma2_rn(f2(__uint_as_float(v[i4 + 2]), __uint_as_float(v[i4 + 3])), inv2, f2(b4.z, b4.w));
+          v[i4] = __float_as_uint(xa.x); v[i4 + 1] = __float_as_uint(xa.y);
+          v[i4 + 2] = __float_as_uint(xb.x); v[i4 + 3] = __float_as_uint(xb.y);
+        }
+      } else {
+        float prev[32];                                            // this thread's own partial sums of the earlier segments
+#pragma unroll
+        for (int i = 0; i < 32; ++i) prev[i] = __ldcg(rawT + static_cast<size_t>(gcol + i) * kTileM);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(fmaf(__uint_as_float(v[i]), inv_scale, prev[i]));
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) __stcg(rawT + static_cast<size_t>(gcol + i) * kTileM, __uint_as_float(v[i]));
+      const int nv = last_seg ? max(0, min(32, N - gcol)) : 0;
+      if (is_ln && nv > 0) {
+        if (!have_x0) { x0 = __uint_as_float(v[0]); have_x0 = true; }
+        if (nv == 32) {
+          const float2 nx0 = f2s(-x0);
+#pragma unroll
+          for (int i4 = 0; i4 < 32; i4 += 4) {
+            const float2 da = __fadd2_rn(f2(__uint_as_float(v[i4]), __uint_as_float(v[i4 + 1])), nx0);
+            const float2 db = __fadd2_rn(f2(__uint_as_float(v[i4 + 2]), __uint_as_float(v[i4 + 3])), nx0);
+            sa = __fadd2_rn(sa, da); qa = __ffma2_rn(da, da, qa);
+            sbb = __fadd2_rn(sbb, db); qb = __ffma2_rn(db, db, qb);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < nv) { const float d = __uint_as_float(v[i]) - x0; s += d; q = fmaf(d, d, q); }
+        }
+      }
+    }
+    if (sc + 1 < nsc || !last_seg) {
+      // TMEM may be overwritten by the next segment's / super-chunk's MMAs once every epilogue warp (of both CTAs of a
+      // pair) has read its part
+      ptx::tc_fence_before();
+      epi_bar_sync();
+      if (threadIdx.x == kEpiWarp0 * 32) {
+        if (c.cg2) ptx::mbar_arrive_leader(&c.acc_empty[0]);
+        else ptx::mbar_arrive(&c.acc_empty[0]);
+      }
+    }
+   }
+  }
+  if (!is_ln) {
+    // EPI_RAW (diagnostics): plain Linear output rows; every thread copies out the columns it drained itself
+    const int orow = ea.rowmap ? ea.rowmap[et.row] : et.row;
+    if (orow >= 0)
+      for (int sc = 0; sc < nsc; ++sc) {
+        const WideCols wc = wide_cols(ly, sc, et.grp);
+        for (int c0 = wc.cb; c0 < wc.cb + wc.ncols; ++c0) {
+          const int gcol = sc * kFusedMaxN + c0;
+          if (gcol < N) ea.out_f32[static_cast<size_t>(orow) * ea.out_pitch + gcol] = __ldcg(rawT + static_cast<size_t>(gcol) * kTileM);
+        }
+      }
+    return;
+  }
+  // ---- merge the 4 column groups' statistics (Chan), as in epi_ln_fused
+  s += (sa.x + sa.y) + (sbb.x + sbb.y);
+  q += (qa.x + qa.y) + (qb.x + qb.y);
+  int cnt_g[kEpiGroups];
+#pragma unroll
+  for (int g = 0; g < kEpiGroups; ++g) {
+    int n = 0;
+    for (int sc = 0; sc < nsc; ++sc) {
+      const WideCols wc = wide_cols(ly, sc, g);
+      n += max(0, min(wc.ncols, N - (sc * kFusedMaxN + wc.cb)));
+    }
+    cnt_g[g] = n;
+  }
+  {
+    const float n_g = static_cast<float>(cnt_g[et.grp]);
+    c.part[et.grp * kTileM + et.row] = cnt_g[et.grp] > 0 ? x0 + s / n_g : 0.f;                       // group mean
+    c.part[(kEpiGroups + et.grp) * kTileM + et.row] = cnt_g[et.grp] > 0 ? q - s * s / n_g : 0.f;     // group M2
+  }
+  epi_bar_sync();
+  float mean = 0.f, rstd;
+  {
+    float m2 = 0.f, cnt = 0.f;
+#pragma unroll
+    for (int g = 0; g < kEpiGroups; ++g) {
+      const float ng = static_cast<float>(cnt_g[g]);
+      if (ng > 0.f) {
+        const float mg = c.part[g * kTileM + et.row], m2g = c.part[(kEpiGroups + g) * kTileM + et.row];
+        const float tot = cnt + ng, delta = mg - mean;
+        mean += delta * (ng / tot);
+        m2 += m2g + delta * delta * (cnt * ng / tot);
+        cnt = tot;
+      }
+    }
+    rstd = rsqrtf(m2 / static_cast<float>(N) + 1e-5f);            // nn.LayerNorm eps (layers.py:101), biased variance
+  }
+  const float nmr = -mean * rstd;
+  if (ea.kind == EPI_LN_MISH) wide_pass2<EPI_LN_MISH>(P, c, et, ly, ea, nsc, rstd, nmr);
+  else wide_pass2<EPI_LN_SIMNORM>(P, c, et, ly, ea, nsc, rstd, nmr);
+}
+
+// GEMM roles + epilogue of a wide layer; returns the number of accumulator hand-offs (= facc phases consumed).
+__device__ __forceinline__ int wide_layer_tc(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf, const EpiArgs& ea) {
+  const int nnc_all = (ly.Npad + kNch - 1) / kNch;
+  const int nsc = (nnc_all + 1) / 2;
+  const int nkc = ly.Kpad / kKch;
+  const int kseg = (P.kseg > 0 && P.kseg < nkc) ? P.kseg : nkc;
+  const int nseg = (nkc + kseg - 1) / kseg;
+  if (c.warp == 0) {
+    if (c.lane == 0)
+      for (int sc = 0; sc < nsc; ++sc)
+        for (int seg = 0; seg < nseg; ++seg) tc_producer(P, c, ly, srcbuf, nullptr, 2 * sc, 2, seg * kseg, kseg);
+  } else if (c.warp == 1) {
+    if (c.lane == 0 && (!c.cg2 || c.rank == 0))
+      for (int sc = 0; sc < nsc; ++sc)
+        for (int seg = 0; seg < nseg; ++seg) {
+          if (sc + seg > 0) {                           // the previous accumulator has been drained
+            const long long tw = clock64();
+            ptx::mbar_wait(&c.acc_empty[0], c.a_it & 1);
+            c.pf0 += clock64() - tw;
+            ++c.a_it;
+            ptx::tc_fence_after();
+          }
+          tc_mma(P, c, ly, 2 * sc, 2, seg * kseg, kseg);
+        }
+  } else if (c.warp >= kEpiWarp0) {
+    epi_wide(P, c, ly, ea, nsc, nseg);
+    ptx::tc_fence_before();
+  }
+  return nsc * nseg;
+}
+
 // Make generic-proxy global writes (activation planes) visible to the TMA unit
 // (async proxy) before the next layer's loads, and sync the CTA.
 __device__ __forceinline__ void publish_planes() {
@@ -1259,9 +1495,9 @@ __device__ __forceinline__ void run_layer(const PlanParams& P, Ctx& c, const Lay
     const long long tl = clock64();
     if (threadIdx.x == 0) TDMPC2_TRACE(P, c, 0);
     if (c.warp == 0) {
-      if (c.lane == 0) tc_producer<true>(P, c, ly, srcbuf, next);
+      if (c.lane == 0) tc_producer(P, c, ly, srcbuf, next);
     } else if (c.warp == 1) {
-      if (c.lane == 0 && (!c.cg2 || c.rank == 0)) tc_mma<true>(P, c, ly);
+      if (c.lane == 0 && (!c.cg2 || c.rank == 0)) tc_mma(P, c, ly);
     } else if (c.warp >= kEpiWarp0) {
       if (is_ln) epi_ln_fused(P, c, ly, ea);
       else epi_head_fused<EPISODIC>(P, c, ly, ea);
@@ -1269,21 +1505,27 @@ __device__ __forceinline__ void run_layer(const PlanParams& P, Ctx& c, const Lay
     }
     c.pf1 += clock64() - tl;
     c.fph0 ^= 1;                                      // every thread tracks the facc phase
+  } else if (ENGINE == ENGINE_TC) {
+    // LayerNorm layers (and the diagnostic raw mode) wider than TMEM; heads are never wider than one N-chunk
+    const long long tl = clock64();
+    if (threadIdx.x == 0) TDMPC2_TRACE(P, c, 0);
+    const int nph = wide_layer_tc(P, c, ly, srcbuf, ea);
+    c.pf1 += clock64() - tl;
+    c.fph0 ^= static_cast<uint32_t>(nph & 1);         // one facc phase per (super-chunk, K-segment)
   } else {
-    if (ENGINE == ENGINE_TC) gemm_tc_wide(P, c, ly, srcbuf);
-    else gemm_simt(P, c, ly, srcbuf);
+    gemm_simt(P, c, ly, srcbuf);
     if (is_ln) rows_ln_act(P, c, ly, ea);
     else rows_head<EPISODIC>(P, c, ly, ea);
   }
   const long long tp = clock64();
   // LN layers that went out through TMA stores wrote nothing through the generic proxy: the leaders have
   // waited for their bulk groups, so a CTA barrier is all the next layer's TMA loads need.
-  const bool tma_only = fused && is_ln && ea.dstbuf >= 0 && (ly.N % 32 == 0) && (ea.dst_col0 % 32 == 0) && !ea.out_f32;
+  const bool tma_only = (ENGINE == ENGINE_TC) && is_ln && ea.dstbuf >= 0 && (ly.N % 32 == 0) && (ea.dst_col0 % 32 == 0) && !ea.out_f32;
   if (tma_only) __syncthreads();
   else publish_planes();
   c.pf3 += clock64() - tp;
-  if (threadIdx.x == 64 && fused) TDMPC2_TRACE(P, c, 9);
-  if (fused) ptx::tc_fence_after();
+  if (threadIdx.x == 64 && ENGINE == ENGINE_TC) TDMPC2_TRACE(P, c, 9);
+  if (ENGINE == ENGINE_TC) ptx::tc_fence_after();
 }
 
 // ------------------------------------------------------------------------------------ top-k + MPPI refit
@@ -1446,7 +1688,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
       for (int s = 0; s < kWRingPair; ++s) { ptx::mbar_init(&c.w_full[s], 1); ptx::mbar_init(&c.w_empty[s], 1); }
       for (int s = 0; s < 2; ++s) {
         ptx::mbar_init(&c.acc_full[s], 1);
-        ptx::mbar_init(&c.acc_empty[s], 4 * 32);
+        ptx::mbar_init(&c.acc_empty[s], CG2 ? 2 : 1);   // wide layers: one arrival per CTA of the pair (its drain is done)
         ptx::mbar_init(&c.facc[s], 1);
       }
       ptx::fence_barrier_init();

@@ -172,6 +172,13 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
       : "memory");
 }
 
+// Arrive on the barrier at this smem offset in the LEADER CTA (rank 0) of the pair; release at cluster scope.
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(0));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(raddr) : "memory");
+}
+
 // ------------------------------------------------------------------ tcgen05: TMEM alloc
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {  // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_dst)),

@@ -24,6 +24,7 @@ from .config import Config, get_discount
 # GEMM engine of the CEM-iteration kernel (include/tdmpc2_b200.h, tdmpc2_engine).  "tcgen05pp" falls back to
 # "tcgen05x2" and that to "tcgen05" inside the library when a model / shape does not fit; TDMPC2_B200_ENGINE overrides.
 DEFAULT_ENGINE = os.environ.get("TDMPC2_B200_ENGINE", "tcgen05x2")
+DEFAULT_KSEG = 0
 
 
 @dataclass
@@ -171,6 +172,9 @@ class Planner:
         if self.l2_persist:
             with torch.cuda.device(self.device):
                 _cabi.check(self.lib.tdmpc2_planner_set_l2_persist(self.h, 1))
+        # wide presets: K elements accumulated in TMEM per segment (see include/tdmpc2_b200.h, tdmpc2_planner_set_kseg)
+        self.kseg = int(os.environ.get("TDMPC2_B200_KSEG", cfg.get("kseg", DEFAULT_KSEG)))
+        _cabi.check(self.lib.tdmpc2_planner_set_kseg(self.h, self.kseg))
         self._keep = []       # tensors referenced by in-flight async calls
         self.weights_version = None
         self._graphs = {}     # eval_mode -> captured launch chain + its static buffers

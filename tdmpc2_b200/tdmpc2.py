@@ -92,11 +92,31 @@ class TDMPC2(torch.nn.Module):
         if self.cfg.mpc:
             out = self._plan(obs, t0=t0, eval_mode=eval_mode, task=task)
             return out.cpu()
-        z = self.model.encode(obs, task)
-        action, info = self.model.pi(z, task)
-        if eval_mode:
-            action = info["mean"]
-        return (action if batched else action[0]).cpu()
+        out = self._policy_action(obs, eval_mode=eval_mode, task=task)           # tdmpc2.py:116-120
+        return (out if batched else out[0]).cpu()
+
+    @torch.no_grad()
+    def _policy_action(self, obs, eval_mode=False, task=None, eps: Optional[torch.Tensor] = None):
+        """The non-MPC branch of act() (tdmpc2.py:116-120): a = pi(encode(obs)), or its mean in eval_mode
+        (`info["mean"]` = tanh(mean), world_model.py:173).  Runs the encode + policy-prior kernel modes: trajectory 0,
+        step 0 of the prior rollout IS pi(encode(obs)) with noise eps (zero noise gives the mean)."""
+        cfg, E, dev = self.cfg, self.num_envs, self.device
+        if cfg.num_pi_trajs < 1:
+            raise NotImplementedError("the kernel policy path needs cfg.num_pi_trajs >= 1")
+        obs = obs.to(dev, torch.float32).reshape(E, -1).contiguous()
+        taskv = None
+        if cfg.multitask:
+            if task is None:
+                raise ValueError("multi-task model needs `task`")
+            taskv = torch.as_tensor(task, device=dev).reshape(-1).to(torch.int32)
+            taskv = taskv.expand(E).contiguous() if taskv.numel() == 1 else taskv.contiguous()
+        noise = torch.zeros(E, cfg.horizon, cfg.num_pi_trajs, cfg.action_dim, device=dev)
+        if not eval_mode:
+            noise[:, 0, 0] = torch.randn(E, cfg.action_dim, device=dev, generator=self.generator) if eps is None else eps.to(dev)
+        pl = self.planner
+        pl.prologue(obs, taskv, torch.ones(E, dtype=torch.uint8, device=dev),
+                    torch.zeros(E, cfg.horizon, cfg.action_dim, device=dev), noise)
+        return pl.get_state()["pi_actions"][:, 0, 0].clone()
 
     @torch.no_grad()
     def _plan(self, obs, t0=False, eval_mode=False, task=None, noise: Optional[Noise] = None, return_trace=False):

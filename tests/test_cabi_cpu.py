@@ -99,31 +99,6 @@ def test_world_model_state_dict_layout():
             assert torch.equal(m2.state_dict()[k], want[k]), k
 
 
-def test_world_model_forward_matches_oracle_model():
-    from oracle.plan_oracle import OracleModel
-    from tdmpc2_b200.config import workload
-    from tdmpc2_b200.synth import synth_state_dict
-    from tdmpc2_b200.world_model import WorldModel
-    cfg = workload("tiny-mt")
-    sd = synth_state_dict(cfg, seed=4, perturb=True, emb_scale=60.0)
-    m = WorldModel(cfg).eval()
-    m.load_state_dict(sd)
-    om = OracleModel(cfg, sd)
-    g = torch.Generator().manual_seed(0)
-    obs = torch.randn(5, cfg.obs_shape["state"][0], generator=g)
-    a = torch.rand(5, cfg.action_dim, generator=g)
-    eps = torch.randn(5, cfg.action_dim, generator=g)
-    task = torch.tensor([2])
-    with torch.no_grad():
-        z = m.encode(obs, task)
-        assert torch.allclose(z, om.encode(obs, 2), atol=1e-6)
-        assert torch.allclose(m.next(z, a, task), om.next(z, a, 2), atol=1e-6)
-        assert torch.allclose(m.reward(z, a, task), om.reward(z, a, 2), atol=1e-5)
-        assert torch.allclose(m.pi(z, task, eps=eps)[0], om.pi(z, 2, eps), atol=1e-6)
-        q = m.Q(z, a, task, return_type="avg", qidx=torch.tensor([3, 1]))
-        assert torch.allclose(q, om.Q_avg(z, a, 2, [3, 1]), atol=1e-5)
-
-
 def test_graft_entry_build():
     """The driver's build check: __graft_entry__.build() compiles (or finds) the library, loads it, imports the package."""
     import importlib

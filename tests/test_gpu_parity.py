@@ -10,7 +10,7 @@ from helpers import stable_positions, boundary_separated
 
 pytestmark = pytest.mark.gpu
 
-ENGINES = ["simt", "tcgen05"]
+ENGINES = ["simt", "tcgen05", "tcgen05x2"]
 
 
 def _planner(cfg, E, engine, sd):
@@ -43,7 +43,7 @@ def _layer_list(cfg):
 
 
 @pytest.mark.parametrize("engine", ENGINES)
-@pytest.mark.parametrize("wl", ["tiny", "tiny-mt", "c1", "tiny-wide", "tiny-episodic"])
+@pytest.mark.parametrize("wl", ["tiny", "tiny-mt", "c1", "tiny-wide", "tiny-wide2", "tiny-episodic"])
 def test_fused_layer_matches_fp64(engine, wl):
     """One packed layer (GEMM on split fp16 operands + bias + LN + Mish/SimNorm) vs float64.
     Tolerance: 1e-5 abs + 1e-5 rel -- fp32 round-off level (3-pass fp16 split carries ~22 bits)."""
@@ -102,7 +102,8 @@ CASES = [  # workload, E, perturb, emb_scale, eval_mode
     ("tiny-mt", 3, True, 60.0, False),
     ("tiny-mt", 3, True, 1.0, True),
     ("c1", 2, False, 1.0, False),
-    ("tiny-wide", 2, True, 1.0, False),     # hidden width 640 > 512 TMEM columns: drained-chunk path
+    ("tiny-wide", 2, True, 1.0, False),     # hidden width 640 > 512 TMEM columns: super-chunked wide path
+    ("tiny-wide2", 2, True, 1.0, False),    # 1152-wide hidden (3 super-chunks), 576-wide SimNorm latent, 640-wide encoder
 ]
 
 
