@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -35,6 +36,11 @@ static int fail(int code, const char* fmt, ...) {
     if (_e != cudaSuccess)                                                                          \
       return fail(TDMPC2_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
+
+static unsigned env_uint(const char* name, unsigned dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? static_cast<unsigned>(strtoul(v, nullptr, 10)) : dflt;
+}
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int pad_to(int x, int a) { return (x + a - 1) / a * a; }
@@ -129,6 +135,7 @@ struct tdmpc2_planner {
   int engine = TDMPC2_ENGINE_TCGEN05;
   bool bound = false, weights_ok = false, smem_attr_set[2] = {false, false}, smem_attr_pair = false, smem_attr_pp = false, all_fused = true;
   int64_t launches = 0;
+  unsigned wide_sleep_ns = 0;
   int kseg = 0;                     // wide layers: K-chunks per TMEM accumulation segment (0 = whole K)
   size_t l2_window_bytes = 0;       // > 0: launches carry a persisting-L2 access-policy window over the activation scratch
   float l2_hit_ratio = 1.f;
@@ -238,6 +245,7 @@ extern "C" int tdmpc2_planner_create(const tdmpc2_dims* dims, tdmpc2_planner** o
   p->Ppad = 1;
   while (p->Ppad < d.num_pi_trajs) p->Ppad <<= 1;
   p->tiles_per_env = (d.num_samples + kTileM - 1) / kTileM;
+  p->wide_sleep_ns = env_uint("TDMPC2_B200_WIDE_SLEEP_NS", 0);   // experiment knob
   p->pair_ok = true;   // fused layers and the super-chunked wide layers both run as cta_group::2
 
   // ---- packed blob layout
@@ -533,6 +541,7 @@ static int launch_plan(tdmpc2_planner* p, const PlanParams& prm, int ntiles, cud
   prm2.prof = p->prof;
   prm2.prof_slots = p->nslots;
   prm2.kseg = p->kseg;
+  prm2.wide_sleep_ns = p->wide_sleep_ns;
   // CTA-pair (cta_group::2) launch: CEM iterations only, whole pairs of tiles of one environment
   const bool pair_engine = (p->engine == TDMPC2_ENGINE_TCGEN05_2SM || p->engine == TDMPC2_ENGINE_TCGEN05_PP ||
                             p->engine == TDMPC2_ENGINE_TCGEN05_2SM_PF);

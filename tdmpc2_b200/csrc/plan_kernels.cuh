@@ -129,6 +129,7 @@ struct PlanParams {
   long long* prof;   // optional [prof_slots][4][12] cycle counters + [32][16] trace stamps of CTA 0 (diagnostics), or nullptr
   int prof_slots;    // = number of scratch slots (SM count)
   int li_term;       // first of the 3 termination-head layers (cfg.episodic, world_model.py:28), or -1
+  unsigned wide_sleep_ns;   // wide layers: nanosleep between polls of the 16 epilogue warps' accumulator wait (0 = spin)
   int kseg;          // wide layers: K-chunks (of 64) accumulated in TMEM before the partial sum is flushed to the fp32 raw
                      // scratch and added there with round-to-nearest (0 = the whole K in one go); see epi_wide
 };
@@ -1221,6 +1222,25 @@ __device__ __forceinline__ void wide_pass2(const PlanParams& P, Ctx& c, const Ep
   float* po = (ea.out_f32 && orow >= 0) ? ea.out_f32 + static_cast<size_t>(orow) * ea.out_pitch : nullptr;
   const float2 rstd2 = f2s(rstd), nmr2 = f2s(nmr);
   int kb = 0;                                                       // staging-buffer parity (per group, uniform)
+  // Software pipeline over this thread's 16-column sub-blocks (in the order they are visited below): the raw values of
+  // the NEXT sub-block are requested before the current one is processed -- the raw scratch of the 317M preset lives
+  // in HBM (2 MB per slot), a dependent load per sub-block would cost ~1 us each.
+  float nxt[16];
+  int nsc_i = 0, nc0_i = 0;                                         // cursor of the prefetch stream: (super-chunk, column)
+  auto advance = [&](int& sc_i, int& c_i) {                         // next valid 16-column sub-block, or sc_i = nsc at the end
+    for (;;) {
+      if (sc_i >= nsc) return;
+      const WideCols w = wide_cols(ly, sc_i, et.grp);
+      if (c_i < w.cb) c_i = w.cb;
+      if (c_i < w.cb + w.ncols && sc_i * kFusedMaxN + c_i < N) return;
+      ++sc_i; c_i = 0;
+    }
+  };
+  advance(nsc_i, nc0_i);
+  if (nsc_i < nsc) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) nxt[i] = __ldcg(rawT + static_cast<size_t>(nsc_i * kFusedMaxN + nc0_i + i) * kTileM);
+  }
   for (int sc = 0; sc < nsc; ++sc) {
     const WideCols wc = wide_cols(ly, sc, et.grp);
     for (int c0 = wc.cb; c0 < wc.cb + wc.ncols; c0 += 32) {
@@ -1236,7 +1256,13 @@ __device__ __forceinline__ void wide_pass2(const PlanParams& P, Ctx& c, const Ep
       for (int sub = 0; sub < 32; sub += 16) {
         float y[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) y[i] = __ldcg(rawT + static_cast<size_t>(gcol + sub + i) * kTileM);
+        for (int i = 0; i < 16; ++i) y[i] = nxt[i];                 // == raw[gcol + sub + i] (requested one sub-block ago)
+        nc0_i += 16;
+        advance(nsc_i, nc0_i);
+        if (nsc_i < nsc) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) nxt[i] = __ldcg(rawT + static_cast<size_t>(nsc_i * kFusedMaxN + nc0_i + i) * kTileM);
+        }
         const bool full = (gcol + sub + 16 <= N);
 #pragma unroll
         for (int i4 = 0; i4 < 16; i4 += 4) {
@@ -1323,6 +1349,7 @@ __device__ __forceinline__ void epi_wide(const PlanParams& P, Ctx& c, const Laye
   float2 sa = f2s(0.f), sbb = f2s(0.f), qa = f2s(0.f), qb = f2s(0.f);
   bool have_x0 = false;
   const float2 inv2 = f2s(inv_scale);
+  const bool tr0 = (et.grp == 0 && et.q == 0 && c.lane == 0);
   for (int sc = 0; sc < nsc; ++sc) {
    const WideCols wc = wide_cols(ly, sc, et.grp);
    for (int seg = 0; seg < nseg; ++seg) {
@@ -1332,10 +1359,12 @@ __device__ __forceinline__ void epi_wide(const PlanParams& P, Ctx& c, const Laye
     const bool last_seg = (seg == nseg - 1);
     {
       const long long tw = clock64();
-      ptx::mbar_wait_long(&c.facc[0], c.fph0 ^ static_cast<uint32_t>((sc * nseg + seg) & 1));
+      ptx::mbar_wait_sleep(&c.facc[0], c.fph0 ^ static_cast<uint32_t>((sc * nseg + seg) & 1), P.wide_sleep_ns);
       c.pf2 += clock64() - tw;
     }
     ptx::tc_fence_after();
+    if (tr0 && sc == 0 && seg == 0) TDMPC2_TRACE(P, c, 4);          // first accumulator ready
+    if (tr0 && sc == nsc - 1 && last_seg) TDMPC2_TRACE(P, c, 10);   // last accumulator ready
     for (int c0 = wc.cb; c0 < wc.cb + wc.ncols; c0 += 32) {
       const int gcol = sc * kFusedMaxN + c0;
       uint32_t v[32];
@@ -1351,12 +1380,15 @@ __device__ __forceinline__ void epi_wide(const PlanParams& P, Ctx& c, const Laye
           v[i4 + 2] = __float_as_uint(xb.x); v[i4 + 3] = __float_as_uint(xb.y);
         }
       } else {
-        float prev[32];                                            // this thread's own partial sums of the earlier segments
-#pragma unroll
-        for (int i = 0; i < 32; ++i) prev[i] = __ldcg(rawT + static_cast<size_t>(gcol + i) * kTileM);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(fmaf(__uint_as_float(v[i]), inv_scale, prev[i]));
+        for (int h = 0; h < 32; h += 8) {                          // this thread's own partial sums of the earlier segments
+          float prev[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) prev[i] = __ldcg(rawT + static_cast<size_t>(gcol + h + i) * kTileM);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[h + i] = __float_as_uint(fmaf(__uint_as_float(v[h + i]), inv_scale, prev[i]));
+        }
       }
 #pragma unroll
       for (int i = 0; i < 32; ++i) __stcg(rawT + static_cast<size_t>(gcol + i) * kTileM, __uint_as_float(v[i]));
@@ -1404,6 +1436,7 @@ __device__ __forceinline__ void epi_wide(const PlanParams& P, Ctx& c, const Laye
       }
     return;
   }
+  if (tr0) TDMPC2_TRACE(P, c, 5);                                   // every super-chunk drained
   // ---- merge the 4 column groups' statistics (Chan), as in epi_ln_fused
   s += (sa.x + sa.y) + (sbb.x + sbb.y);
   q += (qa.x + qa.y) + (qb.x + qb.y);
@@ -1440,8 +1473,10 @@ __device__ __forceinline__ void epi_wide(const PlanParams& P, Ctx& c, const Laye
     rstd = rsqrtf(m2 / static_cast<float>(N) + 1e-5f);            // nn.LayerNorm eps (layers.py:101), biased variance
   }
   const float nmr = -mean * rstd;
+  if (tr0) TDMPC2_TRACE(P, c, 6);
   if (ea.kind == EPI_LN_MISH) wide_pass2<EPI_LN_MISH>(P, c, et, ly, ea, nsc, rstd, nmr);
   else wide_pass2<EPI_LN_SIMNORM>(P, c, et, ly, ea, nsc, rstd, nmr);
+  if (tr0) TDMPC2_TRACE(P, c, 8);                                   // normalise pass done, stores performed
 }
 
 // GEMM roles + epilogue of a wide layer; returns the number of accumulator hand-offs (= facc phases consumed).

@@ -80,6 +80,20 @@ __device__ __forceinline__ void mbar_wait_long(uint64_t* bar, uint32_t parity) {
 #endif
 }
 
+// Run-time variant: `ns` > 0 sleeps between polls (a wide layer's GEMM keeps 16 epilogue warps waiting for 50 - 100 us;
+// spinning costs issue slots and power under the 1 kW cap).
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (ns) __nanosleep(ns);
+    if (++spins > (1u << 28)) {
+      printf("tdmpc2_b200: mbarrier wait timed out (block %d thread %d bar %p parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, (void*)bar, parity);
+      __trap();
+    }
+  }
+}
+
 // ------------------------------------------------------------------ proxies / fences
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() {

@@ -116,3 +116,29 @@ def test_agent_api_shapes_state_and_checkpoint(tmp_path):
     assert out.shape == (4, cfgb.action_dim) and b._prev_mean.shape == (4, cfgb.horizon, cfgb.action_dim)
     with pytest.raises(ValueError):
         b.act(torch.randn(3, cfgb.obs_shape["state"][0]))
+
+
+def test_non_mpc_act_runs_the_policy_through_the_kernels():
+    """cfg.mpc = False (tdmpc2.py:116-120): act() = pi(encode(obs)) with noise, or tanh(mean) in eval_mode -- both come
+    from the encode + policy-prior kernel modes and must match the oracle's encode/pi (1e-5, like the prior test)."""
+    from oracle.plan_oracle import OracleModel
+    from tdmpc2_b200.tdmpc2 import TDMPC2
+    E = 3
+    cfg = workload("tiny-mt", num_envs=E, mpc=False)
+    sd = synth_state_dict(cfg, seed=25, perturb=True, emb_scale=60.0)
+    agent = TDMPC2(cfg, device="cuda:0")
+    agent.load(sd)
+    g = torch.Generator().manual_seed(4)
+    obs = torch.randn(E, cfg.obs_shape["state"][0], generator=g)
+    eps = torch.randn(E, cfg.action_dim, generator=g)
+    task = [1, 3, 0]
+    om = OracleModel(cfg, sd)
+    want_eval = torch.stack([om.pi(om.encode(obs[e:e + 1], task[e]), task[e], torch.zeros(1, cfg.action_dim))[0] for e in range(E)])
+    want_eps = torch.stack([om.pi(om.encode(obs[e:e + 1], task[e]), task[e], eps[e:e + 1])[0] for e in range(E)])
+    got_eval = agent.act(obs, eval_mode=True, task=task)
+    assert got_eval.device.type == "cpu" and got_eval.shape == (E, cfg.action_dim)
+    assert torch.allclose(got_eval, want_eval, atol=1e-5, rtol=0), (got_eval - want_eval).abs().max()
+    got_eps = agent._policy_action(obs.cuda(), eval_mode=False, task=task, eps=eps).cpu()
+    assert torch.allclose(got_eps, want_eps, atol=1e-5, rtol=0), (got_eps - want_eps).abs().max()
+    for e in range(E):                                     # masked action dims are exactly 0 (world_model.py:158-162)
+        assert torch.all(got_eps[e, cfg.action_dims[task[e]]:] == 0)
