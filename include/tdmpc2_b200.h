@@ -143,6 +143,9 @@ int tdmpc2_planner_set_l2_persist(tdmpc2_planner* p, int enable);
  * flushed to fp32 every k_elems elements of K and added with round-to-nearest (one extra accumulator drain per
  * segment).  0 = whole K in one accumulation.  No reference counterpart. */
 int tdmpc2_planner_set_kseg(tdmpc2_planner* p, int k_elems);
+/* The same for the head layers (reward / Q / pi / termination outputs, which have no LayerNorm behind them to absorb
+ * the accumulator's toward-zero drift): default 512, 0 = whole K in one accumulation. */
+int tdmpc2_planner_set_head_kseg(tdmpc2_planner* p, int k_elems);
 /* Replaces: agent.load()/WorldModel.to(device) weight placement (tdmpc2.py:81-95).
  * Packs the state-dict tensors into the kernel layout: per Linear two fp16
  * planes (hi, lo) of weight * 2^k, K-major, zero-padded; applies the

@@ -9,7 +9,7 @@ that every deviation from the exact sum is the tensor core's own rounding:
 
     python scripts/micro/mma_rounding.py        (GPU box)
 """
-import os, sys
+import math, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from tdmpc2_b200.config import workload
@@ -34,7 +34,7 @@ def run(W, X, engine="tcgen05"):
 
 
 def ulps(y, ref):            # deviation in units of the fp32 ulp of the exact value
-    u = torch.tensor([2.0 ** (torch.floor(torch.log2(abs(r))).item() - 23) if r != 0 else 1.0 for r in ref.tolist()], dtype=torch.float64)
+    u = torch.tensor([2.0 ** (math.floor(math.log2(abs(r))) - 23) if r != 0 else 1.0 for r in ref.tolist()], dtype=torch.float64)
     return (y - ref) / u
 
 

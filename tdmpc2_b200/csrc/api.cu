@@ -133,9 +133,11 @@ struct tdmpc2_planner {
   uint8_t* ws = nullptr;
   PlanParams base;
   int engine = TDMPC2_ENGINE_TCGEN05;
-  bool bound = false, weights_ok = false, smem_attr_set[2] = {false, false}, smem_attr_pair = false, smem_attr_pp = false, all_fused = true;
+  bool bound = false, weights_ok = false, smem_attr_pp = false, all_fused = true;
+  bool attr_done[16] = {};          // dynamic-smem opt-in done, per plan_kernel instantiation
   int64_t launches = 0;
   unsigned wide_sleep_ns = 0;
+  int head_kseg = 8;                // heads: 512 elements of K per TMEM accumulation (the 5M preset's whole K)
   int kseg = 0;                     // wide layers: K-chunks per TMEM accumulation segment (0 = whole K)
   size_t l2_window_bytes = 0;       // > 0: launches carry a persisting-L2 access-policy window over the activation scratch
   float l2_hit_ratio = 1.f;
@@ -323,6 +325,13 @@ extern "C" int tdmpc2_planner_set_engine(tdmpc2_planner* p, int engine) {
 extern "C" int tdmpc2_planner_set_kseg(tdmpc2_planner* p, int k_elems) {
   if (!p || k_elems < 0) return fail(TDMPC2_ERR_INVALID, "bad kseg");
   p->kseg = (k_elems + kKch - 1) / kKch;
+  return 0;
+}
+// The same for the head layers (reward / Q / pi / termination outputs): their partial sums alternate between two TMEM
+// buffers and are added in registers, at no measurable cost.  Default 512; 0 = whole K in one accumulation.
+extern "C" int tdmpc2_planner_set_head_kseg(tdmpc2_planner* p, int k_elems) {
+  if (!p || k_elems < 0) return fail(TDMPC2_ERR_INVALID, "bad head kseg");
+  p->head_kseg = (k_elems + kKch - 1) / kKch;
   return 0;
 }
 
@@ -522,26 +531,29 @@ static int launch_one(tdmpc2_planner* p, K kernel, int grid, size_t smem, cudaSt
   return 0;
 }
 
+template <class K>
+static int launch_big(tdmpc2_planner* p, K kernel, bool* attr_done, int grid, cudaStream_t st, bool cluster2, const PlanParams& prm) {
+  if (!*attr_done) {     // > 48 KiB of dynamic shared memory needs the opt-in, once per kernel instantiation
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    *attr_done = true;
+  }
+  return launch_one(p, kernel, grid, kSmemBytes, st, cluster2, prm);
+}
+
 static int launch_plan(tdmpc2_planner* p, const PlanParams& prm, int ntiles, cudaStream_t st) {
-  const int eng = p->engine == TDMPC2_ENGINE_SIMT ? 1 : 0;
+  const bool simt = p->engine == TDMPC2_ENGINE_SIMT;
   // episodic models: the rollout modes run the instantiations that carry the termination head
   const bool epi = p->d.episodic && (prm.mode == MODE_ITER || prm.mode == MODE_VALUE);
-  if (!p->smem_attr_set[eng]) {
-    if (eng == 0) {
-      CUDA_TRY(cudaFuncSetAttribute(plan_kernel<ENGINE_TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-      CUDA_TRY(cudaFuncSetAttribute(plan_kernel<ENGINE_TC, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    } else {
-      CUDA_TRY(cudaFuncSetAttribute(plan_kernel<ENGINE_SIMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-      CUDA_TRY(cudaFuncSetAttribute(plan_kernel<ENGINE_SIMT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    }
-    p->smem_attr_set[eng] = true;
-  }
+  // models with layers wider than TMEM (and the one-layer diagnostic mode, whose raw output may be) take the WIDE kernels
+  const bool wide = !p->all_fused || prm.mode == MODE_LAYER;
   int grid = std::min(ntiles, p->nslots);
   PlanParams prm2 = prm;
   prm2.prof = p->prof;
   prm2.prof_slots = p->nslots;
   prm2.kseg = p->kseg;
+  prm2.head_kseg = p->head_kseg;
   prm2.wide_sleep_ns = p->wide_sleep_ns;
+  static_assert(sizeof(p->attr_done) / sizeof(bool) >= 16, "attr_done slots");
   // CTA-pair (cta_group::2) launch: CEM iterations only, whole pairs of tiles of one environment
   const bool pair_engine = (p->engine == TDMPC2_ENGINE_TCGEN05_2SM || p->engine == TDMPC2_ENGINE_TCGEN05_PP ||
                             p->engine == TDMPC2_ENGINE_TCGEN05_2SM_PF);
@@ -554,26 +566,29 @@ static int launch_plan(tdmpc2_planner* p, const PlanParams& prm, int ntiles, cud
     }
     return launch_one(p, plan_pp_kernel, grid & ~1, kPPSmemBytes, st, true, prm2);
   }
+  bool* ad = p->attr_done;
+  if (simt) {
+    if (epi) return launch_big(p, plan_kernel<ENGINE_SIMT, false, true>, &ad[0], grid, st, false, prm2);
+    return launch_big(p, plan_kernel<ENGINE_SIMT>, &ad[1], grid, st, false, prm2);
+  }
   const bool pair = pair_engine && prm.mode == MODE_ITER && (p->tiles_per_env % 2 == 0) && (ntiles % 2 == 0) && p->pair_ok;
   if (pair) {
-    if (!p->smem_attr_pair) {
-      CUDA_TRY(cudaFuncSetAttribute(plan_kernel<ENGINE_TC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-      CUDA_TRY(cudaFuncSetAttribute(plan_kernel<ENGINE_TC, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-      CUDA_TRY(cudaFuncSetAttribute(plan_kernel<ENGINE_TC, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-      p->smem_attr_pair = true;
-    }
     grid &= ~1;
-    if (epi) return launch_one(p, plan_kernel<ENGINE_TC, true, true>, grid, kSmemBytes, st, true, prm2);
+    if (wide) {
+      if (epi) return launch_big(p, plan_kernel<ENGINE_TC, true, true, false, true>, &ad[2], grid, st, true, prm2);
+      return launch_big(p, plan_kernel<ENGINE_TC, true, false, false, true>, &ad[3], grid, st, true, prm2);
+    }
+    if (epi) return launch_big(p, plan_kernel<ENGINE_TC, true, true>, &ad[4], grid, st, true, prm2);
     if (p->engine == TDMPC2_ENGINE_TCGEN05_2SM_PF && wpf_eligible(p))
-      return launch_one(p, plan_kernel<ENGINE_TC, true, false, true>, grid, kSmemBytes, st, true, prm2);
-    return launch_one(p, plan_kernel<ENGINE_TC, true>, grid, kSmemBytes, st, true, prm2);
+      return launch_big(p, plan_kernel<ENGINE_TC, true, false, true>, &ad[5], grid, st, true, prm2);
+    return launch_big(p, plan_kernel<ENGINE_TC, true>, &ad[6], grid, st, true, prm2);
   }
-  if (eng == 0) {
-    if (epi) return launch_one(p, plan_kernel<ENGINE_TC, false, true>, grid, kSmemBytes, st, false, prm2);
-    return launch_one(p, plan_kernel<ENGINE_TC>, grid, kSmemBytes, st, false, prm2);
+  if (wide) {
+    if (epi) return launch_big(p, plan_kernel<ENGINE_TC, false, true, false, true>, &ad[7], grid, st, false, prm2);
+    return launch_big(p, plan_kernel<ENGINE_TC, false, false, false, true>, &ad[8], grid, st, false, prm2);
   }
-  if (epi) return launch_one(p, plan_kernel<ENGINE_SIMT, false, true>, grid, kSmemBytes, st, false, prm2);
-  return launch_one(p, plan_kernel<ENGINE_SIMT>, grid, kSmemBytes, st, false, prm2);
+  if (epi) return launch_big(p, plan_kernel<ENGINE_TC, false, true>, &ad[9], grid, st, false, prm2);
+  return launch_big(p, plan_kernel<ENGINE_TC>, &ad[10], grid, st, false, prm2);
 }
 
 LaunchCfg::LaunchCfg(tdmpc2_planner* p, int grid, size_t smem, cudaStream_t st, bool cluster2) {

@@ -129,6 +129,7 @@ struct PlanParams {
   long long* prof;   // optional [prof_slots][4][12] cycle counters + [32][16] trace stamps of CTA 0 (diagnostics), or nullptr
   int prof_slots;    // = number of scratch slots (SM count)
   int li_term;       // first of the 3 termination-head layers (cfg.episodic, world_model.py:28), or -1
+  int head_kseg;     // head layers: K-chunks per accumulator hand-off (0 = whole K in one accumulation)
   unsigned wide_sleep_ns;   // wide layers: nanosleep between polls of the 16 epilogue warps' accumulator wait (0 = spin)
   int kseg;          // wide layers: K-chunks (of 64) accumulated in TMEM before the partial sum is flushed to the fp32 raw
                      // scratch and added there with round-to-nearest (0 = the whole K in one go); see epi_wide
@@ -222,6 +223,7 @@ struct Ctx {
   uint64_t* acc_full;       // [2]  wide path: accumulator slot ready
   uint64_t* acc_empty;      // [2]  wide path: accumulator slot drained
   uint64_t* facc;           // [2]  fused path: accumulator chunk ready
+  uint64_t* rawb;           // [4 groups][2] wide layers, normalise pass: raw block landed in the group's input buffer
   uint32_t* tmem_ptr;
   float* rowbuf;            // [kWarps][kMaxHeadCols]
   float* vec;               // [3][kFusedMaxN]  bias, ln_g, ln_b (fused path)
@@ -239,6 +241,7 @@ struct Ctx {
   uint32_t w_ring, w_stride, w_lo_off;   // W ring geometry: 2 x 64 KiB (lo plane at +32 KiB) or, in pair mode, 4 x 32 KiB (+16 KiB)
   // pipeline counters (each role keeps its own; persist across layers / tiles)
   uint32_t pa_it, pw_it, ma_it, mw_it, a_it, d_it;
+  uint32_t rb_it;           // wide layers: raw blocks consumed so far by this thread's column group (buffer = it & 1)
   uint32_t fph0, fph1;      // fused path: phase parity of facc[0|1] (tracked identically by every thread)
   long long pf0, pf1, pf2, pf3, pf4, pf5, pf6, pf7;   // per-thread cycle accumulators (diagnostics)
   int trace_step;
@@ -471,6 +474,43 @@ __device__ __forceinline__ void tc_mma(const PlanParams& P, Ctx& c, const LayerD
   if (c.cg2) ptx::umma_commit_2sm(&c.facc[0]);
   else ptx::umma_commit(&c.facc[0]);
   TDMPC2_TRACE(P, c, 3);
+}
+
+// Head layers (plain Linear outputs, Npad <= 256) with a long reduction: the accumulator is handed to the epilogue every
+// `kseg` K-chunks, alternating between two TMEM buffers (columns [0,256) and [256,512)), and the epilogue adds the
+// segments in fp32 registers with round-to-nearest.  Why: tcgen05's accumulate step rounds TOWARD ZERO (measured:
+// scripts/micro/mma_rounding.py), which shrinks a long accumulation by ~n_MMA * 2^-25 relative; LayerNorm removes a
+// uniform shrink from the hidden layers, but the heads' logits have no LayerNorm behind them.
+__device__ __forceinline__ int head_segments(const PlanParams& P, const LayerDev& ly) {
+  const int nkc = ly.Kpad / kKch;
+  return (P.head_kseg > 0 && nkc > P.head_kseg) ? (nkc + P.head_kseg - 1) / P.head_kseg : 1;
+}
+__device__ __forceinline__ void tc_mma_head_seg(const PlanParams& P, Ctx& c, const LayerDev& ly, int nseg) {
+  const int nkc = ly.Kpad / kKch;
+  const uint32_t sbase = ptx::smem_u32(c.stage_base);
+  const uint32_t idesc = ptx::make_idesc_f16(c.cg2 ? 2 * kTileM : kTileM, ly.Npad);
+  for (int seg = 0; seg < nseg; ++seg) {
+    const int b = seg & 1;
+    if (seg >= 2) {                                    // buffer b was drained (segment seg - 2)
+      uint32_t& it = b ? c.d_it : c.a_it;
+      ptx::mbar_wait(&c.acc_empty[b], it & 1);
+      ++it;
+      ptx::tc_fence_after();
+    }
+    const int kc0 = seg * P.head_kseg, kc1 = min(nkc, kc0 + P.head_kseg);
+    for (int kc = kc0; kc < kc1; ++kc) {
+      const uint32_t as = mma_wait_a(c);
+      const uint32_t ws = mma_wait_w(c);
+      ptx::tc_fence_after();
+      mma_stage(c.tmem_base + b * kNch, sbase + as * kASlotBytes, sbase + kWRingOff + ws * c.w_stride, c.w_lo_off, idesc,
+                kc == kc0, c.cg2 != 0);
+      if (c.cg2) { ptx::umma_commit_2sm(&c.w_empty[ws]); ptx::umma_commit_2sm(&c.a_empty[as]); }
+      else { ptx::umma_commit(&c.w_empty[ws]); ptx::umma_commit(&c.a_empty[as]); }
+      ++c.mw_it; ++c.ma_it;
+    }
+    if (c.cg2) ptx::umma_commit_2sm(&c.facc[b]);
+    else ptx::umma_commit(&c.facc[b]);
+  }
 }
 
 // ------------------------------------------------------------------------------------ SIMT engine: GEMM -> raw scratch
@@ -1031,8 +1071,17 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
 // Head epilogues (plain Linear outputs, Npad <= 256 so the accumulator is chunk 0 only).
 // Two-hot heads with <= 128 bins and pi heads with <= 64 action dims are spread over all four column groups
 // (32 bins / 16 action dims per group); anything larger runs on column group 0 alone.
+// Can this head's epilogue take K-segmented accumulators (segments summed in registers)?  The common shapes only:
+// two-hot heads with <= 128 bins, pi heads with <= 64 action dims, the termination head.
+__device__ __forceinline__ bool head_seg_ok(const PlanParams& P, int kind) {
+  return (kind == EPI_TWOHOT && P.B <= 32 * kEpiGroups) || (kind == EPI_PI && P.A <= 16 * kEpiGroups) || kind == EPI_TERM;
+}
+
+// `nseg` > 1: the accumulator arrives in K-segments alternating between TMEM buffers 0 / 1 (tc_mma_head_seg); each
+// thread adds the segments of its own columns in registers.  v[0..32): this thread's 32 columns at column offset col0
+// (two-hot: bins 32*grp..; pi: 16 mean logits then 16 log_std logits; termination: column 0).
 template <bool EPISODIC>
-__device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, const LayerDev& ly, const EpiArgs& ea) {
+__device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, const LayerDev& ly, const EpiArgs& ea, int nseg) {
   const EpiThread et = epi_thread(c);
   const float inv_scale = ly.inv_scale;
   epi_stage_vectors(c, ly, false);
@@ -1044,22 +1093,63 @@ __device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, cons
   }
   const bool wide_twohot = (ea.kind == EPI_TWOHOT) && (P.B <= 32 * kEpiGroups);
   const bool wide_pi = (ea.kind == EPI_PI) && (P.A <= 16 * kEpiGroups);
-  if (!wide_twohot && !wide_pi && et.grp != 0) return;
-  {
-    const long long tw = clock64();
-    ptx::mbar_wait_long(&c.facc[0], c.fph0);
-    c.pf2 += clock64() - tw;
+  uint32_t v[32];
+  if (nseg > 1) {
+    // every epilogue warp takes part in the hand-off protocol, whether or not it owns columns of this head
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    const bool mine = wide_twohot || wide_pi || et.grp == 0;
+    for (int seg = 0; seg < nseg; ++seg) {
+      const int b = seg & 1;
+      const uint32_t ph = (b ? c.fph1 : c.fph0) ^ static_cast<uint32_t>((seg >> 1) & 1);
+      ptx::mbar_wait_long(&c.facc[b], ph);
+      ptx::tc_fence_after();
+      if (mine) {
+        const uint32_t ta = et.taddr + b * kNch;
+        // two 16-column loads (keeps the live registers at acc[32] + 16): columns [c_lo, +16) and [c_hi, +16)
+        const uint32_t c_lo = wide_pi ? 16 * et.grp : (wide_twohot ? 32 * et.grp : 0);
+        const uint32_t c_hi = wide_pi ? P.Apad + 16 * et.grp : c_lo + 16;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t a0[16];
+          ptx::tmem_ld_32x16(ta + (h ? c_hi : c_lo), a0);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[16 * h + i] += __uint_as_float(a0[i]);
+        }
+      }
+      if (seg + 2 < nseg) {                            // the buffer is reused: tell the MMA issuer it has been read
+        ptx::tc_fence_before();
+        epi_bar_sync();
+        if (threadIdx.x == kEpiWarp0 * 32) {
+          if (c.cg2) ptx::mbar_arrive_leader(&c.acc_empty[b]);
+          else ptx::mbar_arrive(&c.acc_empty[b]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(acc[i]);
+    if (!mine) return;
+  } else {
+    if (!wide_twohot && !wide_pi && et.grp != 0) return;
+    {
+      const long long tw = clock64();
+      ptx::mbar_wait_long(&c.facc[0], c.fph0);
+      c.pf2 += clock64() - tw;
+    }
+    ptx::tc_fence_after();
   }
-  ptx::tc_fence_after();
   if (wide_twohot) {
     // two_hot_inv (math.py:74-83) with the 4 groups each owning 32 bins: max, then exp-sum and bin-weighted sum,
     // exchanged through smem (part: [0,4) max, [4,8) sum; third array in the unused LN-beta vector slot).
     const float* bins = c.vec + kFusedMaxN;
     float* xch = c.vec + 2 * kFusedMaxN;                // [kEpiGroups][128]
     const int B = P.B, c0 = 32 * et.grp;
-    uint32_t v[32];
-    ptx::tmem_ld_32x32(et.taddr + c0, v);
-    ptx::tmem_ld_wait();
+    if (nseg == 1) {
+      ptx::tmem_ld_32x32(et.taddr + c0, v);
+      ptx::tmem_ld_wait();
+    }
     float x[32];
     float m = -CUDART_INF_F;
 #pragma unroll
@@ -1089,9 +1179,12 @@ __device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, cons
     }
   } else if (EPISODIC && ea.kind == EPI_TERM) {
     // termination head (one output column): group 0's thread of each row updates the row's sticky flag
-    uint32_t v[16];
-    ptx::tmem_ld_32x16(et.taddr, v);
-    ptx::tmem_ld_wait();
+    if (nseg == 1) {
+      uint32_t t16[16];
+      ptx::tmem_ld_32x16(et.taddr, t16);
+      ptx::tmem_ld_wait();
+      v[0] = t16[0];
+    }
     term_commit(c, et.row, fmaf(__uint_as_float(v[0]), inv_scale, sb[0]));
   } else if (ea.kind == EPI_TWOHOT) {
     const float* bins = c.vec + kFusedMaxN;
@@ -1130,9 +1223,14 @@ __device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, cons
     const int a_end = wide_pi ? min(P.A, a_begin + 16) : P.A;
     for (int a0 = a_begin; a0 < a_end; a0 += 16) {
       uint32_t vm[16], vs[16];
-      ptx::tmem_ld_32x16(et.taddr + a0, vm);            // mean logits, columns [a0, a0+16)
-      ptx::tmem_ld_32x16(et.taddr + P.Apad + a0, vs);   // log_std logits, columns [Apad+a0, Apad+a0+16) (aligned)
-      ptx::tmem_ld_wait();
+      if (nseg > 1) {                                   // wide_pi only: one 16-column block per thread, already summed
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { vm[i] = v[i]; vs[i] = v[16 + i]; }
+      } else {
+        ptx::tmem_ld_32x16(et.taddr + a0, vm);            // mean logits, columns [a0, a0+16)
+        ptx::tmem_ld_32x16(et.taddr + P.Apad + a0, vs);   // log_std logits, columns [Apad+a0, Apad+a0+16) (aligned)
+        ptx::tmem_ld_wait();
+      }
       // 16 action columns = 32 B per plane: two 16-byte stores when the whole span lies inside the row
       // (columns past A are zero-weight padding of X, so writing zeros there is harmless)
       const bool vec = (((P.L + P.T) & 7) == 0) && (P.L + P.T + a0 + 16 <= P.KpadX);
@@ -1204,14 +1302,22 @@ __device__ __forceinline__ WideCols wide_cols(const LayerDev& ly, int sc, int gr
   return w;
 }
 
+// The normalise pass of a wide layer.  Both operand rings are idle by now (every MMA of the layer has retired), so the
+// whole 192 KiB of operand smem serve as staging: per column group two 16 KiB INPUT buffers in the W ring -- 32 raw
+// columns x 128 rows fp32, exactly one contiguous block of the column-major raw scratch, fetched with one bulk copy
+// (cp.async.bulk, mbarrier completion) two blocks ahead of its use, which hides the HBM latency of the 317M preset's
+// raw scratch (2 MB per slot) -- and one 16 KiB OUTPUT tile (hi | lo planes, 64-byte swizzle) in the A ring that leaves
+// through TMA stores.
 template <int KIND>   // EPI_LN_MISH | EPI_LN_SIMNORM
 __device__ __forceinline__ void wide_pass2(const PlanParams& P, Ctx& c, const EpiThread& et, const LayerDev& ly, const EpiArgs& ea,
                                            int nsc, float rstd, float nmr) {
   const int N = ly.N;
-  const float* rawT = raw_ptr(P, c.slot) + et.row;
+  const float* rawT = raw_ptr(P, c.slot);                            // block of 32 columns at rawT + gcol * 128
   const bool planes = ea.dstbuf >= 0;
   const bool use_tma = planes && (N % 32 == 0) && (ea.dst_col0 % 32 == 0);
-  uint8_t* stg = c.stage_base + kWRingOff + et.grp * (2 * kStgBuf);   // W ring: idle, every MMA of the layer has retired
+  uint8_t* inb = c.stage_base + kWRingOff + et.grp * (2 * kStgBuf);  // 2 x 16 KiB raw blocks
+  uint8_t* stg = c.stage_base + et.grp * kStgBuf;                    // 16 KiB output tile (hi 8 KiB | lo 8 KiB)
+  uint64_t* bars = c.rawb + et.grp * 2;
   const bool leader = (et.q == 0) && (c.lane == 0);
   const CUtensorMap* tmD = (ea.dstbuf == BUF_X) ? &P.tmXs : &P.tmHs;
   const uint32_t swz = static_cast<uint32_t>((et.row >> 1) & 3);
@@ -1221,13 +1327,9 @@ __device__ __forceinline__ void wide_pass2(const PlanParams& P, Ctx& c, const Ep
   const int orow = ea.rowmap ? ea.rowmap[et.row] : et.row;
   float* po = (ea.out_f32 && orow >= 0) ? ea.out_f32 + static_cast<size_t>(orow) * ea.out_pitch : nullptr;
   const float2 rstd2 = f2s(rstd), nmr2 = f2s(nmr);
-  int kb = 0;                                                       // staging-buffer parity (per group, uniform)
-  // Software pipeline over this thread's 16-column sub-blocks (in the order they are visited below): the raw values of
-  // the NEXT sub-block are requested before the current one is processed -- the raw scratch of the 317M preset lives
-  // in HBM (2 MB per slot), a dependent load per sub-block would cost ~1 us each.
-  float nxt[16];
-  int nsc_i = 0, nc0_i = 0;                                         // cursor of the prefetch stream: (super-chunk, column)
-  auto advance = [&](int& sc_i, int& c_i) {                         // next valid 16-column sub-block, or sc_i = nsc at the end
+  const uint32_t rowaddr = ptx::smem_u32(stg) + static_cast<uint32_t>(et.row) * 64u;
+  // The group's blocks in visiting order: (super-chunk, column) cursors for the consumer and for the leader's prefetch.
+  auto next_block = [&](int& sc_i, int& c_i) {       // advance to the next block with valid columns; sc_i = nsc at the end
     for (;;) {
       if (sc_i >= nsc) return;
       const WideCols w = wide_cols(ly, sc_i, et.grp);
@@ -1236,103 +1338,102 @@ __device__ __forceinline__ void wide_pass2(const PlanParams& P, Ctx& c, const Ep
       ++sc_i; c_i = 0;
     }
   };
-  advance(nsc_i, nc0_i);
-  if (nsc_i < nsc) {
+  int psc = 0, pc = 0;                               // prefetch cursor (leader)
+  uint32_t issued = c.rb_it;                         // blocks requested so far (leader); block k uses buffer k & 1
+  auto prefetch = [&]() {
+    next_block(psc, pc);
+    if (psc >= nsc) return;
+    const uint32_t b = issued & 1u;
+    ptx::mbar_expect_tx(&bars[b], kStgBuf);
+    ptx::bulk_load(inb + b * kStgBuf, rawT + static_cast<size_t>(psc * kFusedMaxN + pc) * kTileM, kStgBuf, &bars[b]);
+    ++issued;
+    pc += 32;
+  };
+  if (leader) { prefetch(); prefetch(); }
+  int sc = 0, c0 = 0;
+  for (next_block(sc, c0); sc < nsc; c0 += 32, next_block(sc, c0)) {
+    const int gcol = sc * kFusedMaxN + c0;
+    const uint32_t b = c.rb_it & 1u;
+    ptx::mbar_wait(&bars[b], (c.rb_it >> 1) & 1u);
+    const float* blk = reinterpret_cast<const float*>(inb + b * kStgBuf) + et.row;     // element (col, row) at blk[col * 128]
+    uint32_t hw[16], lw[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) nxt[i] = __ldcg(rawT + static_cast<size_t>(nsc_i * kFusedMaxN + nc0_i + i) * kTileM);
-  }
-  for (int sc = 0; sc < nsc; ++sc) {
-    const WideCols wc = wide_cols(ly, sc, et.grp);
-    for (int c0 = wc.cb; c0 < wc.cb + wc.ncols; c0 += 32) {
-      const int gcol = sc * kFusedMaxN + c0;
-      if (gcol >= N) break;                                         // zero-padding columns: nothing to emit
-      uint8_t* buf = stg + (kb & 1) * kStgBuf;
-      const uint32_t rowaddr = ptx::smem_u32(buf) + static_cast<uint32_t>(et.row) * 64u;
-      if (use_tma && kb >= 2) {                                     // buffer reuse: its previous store must have read it
-        if (leader) ptx::bulk_wait_read<1>();
-        group_bar_sync(et.grp);
+    for (int sub = 0; sub < 32; sub += 16) {
+      float y[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) y[i] = blk[(sub + i) * kTileM];
+      const bool full = (gcol + sub + 16 <= N);
+#pragma unroll
+      for (int i4 = 0; i4 < 16; i4 += 4) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(ly.ln_g + gcol + sub + i4));
+        const float4 e4 = __ldg(reinterpret_cast<const float4*>(ly.ln_b + gcol + sub + i4));
+        float2 t0 = __ffma2_rn(__ffma2_rn(f2(y[i4], y[i4 + 1]), rstd2, nmr2), f2(g4.x, g4.y), f2(e4.x, e4.y));
+        float2 t1 = __ffma2_rn(__ffma2_rn(f2(y[i4 + 2], y[i4 + 3]), rstd2, nmr2), f2(g4.z, g4.w), f2(e4.z, e4.w));
+        if (KIND == EPI_LN_MISH) { t0 = mish_fast2(t0); t1 = mish_fast2(t1); }
+        y[i4] = t0.x; y[i4 + 1] = t0.y; y[i4 + 2] = t1.x; y[i4 + 3] = t1.y;
       }
+      if (!full) {
 #pragma unroll
-      for (int sub = 0; sub < 32; sub += 16) {
-        float y[16];
+        for (int i = 0; i < 16; ++i)
+          if (gcol + sub + i >= N) y[i] = (KIND == EPI_LN_MISH) ? 0.f : -CUDART_INF_F;
+      }
+      if (KIND == EPI_LN_SIMNORM) {
+        // SimNorm: softmax over groups of 8 consecutive columns (layers.py:84-88)
 #pragma unroll
-        for (int i = 0; i < 16; ++i) y[i] = nxt[i];                 // == raw[gcol + sub + i] (requested one sub-block ago)
-        nc0_i += 16;
-        advance(nsc_i, nc0_i);
-        if (nsc_i < nsc) {
+        for (int g0 = 0; g0 < 16; g0 += 8) {
+          float m = y[g0];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) nxt[i] = __ldcg(rawT + static_cast<size_t>(nsc_i * kFusedMaxN + nc0_i + i) * kTileM);
+          for (int i = 1; i < 8; ++i) m = fmaxf(m, y[g0 + i]);
+          float t = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { y[g0 + i] = exp_fast(y[g0 + i] - m); t += y[g0 + i]; }
+          const float rt = rcp_ftz(t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[g0 + i] *= rt;
         }
-        const bool full = (gcol + sub + 16 <= N);
+      }
+      if (po) {
 #pragma unroll
-        for (int i4 = 0; i4 < 16; i4 += 4) {
-          const float4 g4 = __ldg(reinterpret_cast<const float4*>(ly.ln_g + gcol + sub + i4));
-          const float4 e4 = __ldg(reinterpret_cast<const float4*>(ly.ln_b + gcol + sub + i4));
-          float2 t0 = __ffma2_rn(__ffma2_rn(f2(y[i4], y[i4 + 1]), rstd2, nmr2), f2(g4.x, g4.y), f2(e4.x, e4.y));
-          float2 t1 = __ffma2_rn(__ffma2_rn(f2(y[i4 + 2], y[i4 + 3]), rstd2, nmr2), f2(g4.z, g4.w), f2(e4.z, e4.w));
-          if (KIND == EPI_LN_MISH) { t0 = mish_fast2(t0); t1 = mish_fast2(t1); }
-          y[i4] = t0.x; y[i4 + 1] = t0.y; y[i4 + 2] = t1.x; y[i4 + 3] = t1.y;
-        }
-        if (!full) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (gcol + sub + i >= N) y[i] = (KIND == EPI_LN_MISH) ? 0.f : -CUDART_INF_F;
-        }
-        if (KIND == EPI_LN_SIMNORM) {
-          // SimNorm: softmax over groups of 8 consecutive columns (layers.py:84-88)
-#pragma unroll
-          for (int g0 = 0; g0 < 16; g0 += 8) {
-            float m = y[g0];
-#pragma unroll
-            for (int i = 1; i < 8; ++i) m = fmaxf(m, y[g0 + i]);
-            float t = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { y[g0 + i] = exp_fast(y[g0 + i] - m); t += y[g0 + i]; }
-            const float rt = rcp_ftz(t);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) y[g0 + i] *= rt;
-          }
-        }
-        if (po) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (gcol + sub + i < N) po[gcol + sub + i] = y[i];
-        }
-        if (use_tma) {
-          uint32_t hw[8], lw[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float a0 = y[2 * i], a1 = y[2 * i + 1];
-            const __half2 h2 = __floats2half2_rn(a0, a1);
-            const float2 hf = __half22float2(h2);
-            const float2 df = __fadd2_rn(f2(a0, a1), f2(-hf.x, -hf.y));
-            const __half2 l2 = __floats2half2_rn(df.x, df.y);
-            hw[i] = *reinterpret_cast<const uint32_t*>(&h2);
-            lw[i] = *reinterpret_cast<const uint32_t*>(&l2);
-          }
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const uint32_t off = ((static_cast<uint32_t>((sub >> 3) + i) ^ swz) << 4);
-            ptx::st_shared_v4(rowaddr + off, hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
-            ptx::st_shared_v4(rowaddr + kStgPlane + off, lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]);
-          }
-        } else if (planes) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (gcol + sub + i < N) split_store(dhi + gcol + sub + i, dlo + gcol + sub + i, y[i]);
-        }
+        for (int i = 0; i < 16; ++i)
+          if (gcol + sub + i < N) po[gcol + sub + i] = y[i];
       }
       if (use_tma) {
-        ptx::fence_proxy_async_smem();
-        group_bar_sync(et.grp);
-        if (leader) {
-          ptx::tma_store_2d(tmD, buf, ea.dst_col0 + gcol, row_hi);
-          ptx::tma_store_2d(tmD, buf + kStgPlane, ea.dst_col0 + gcol, row_lo);
-          ptx::bulk_commit();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float a0 = y[2 * i], a1 = y[2 * i + 1];
+          const __half2 h2 = __floats2half2_rn(a0, a1);
+          const float2 hf = __half22float2(h2);
+          const float2 df = __fadd2_rn(f2(a0, a1), f2(-hf.x, -hf.y));
+          const __half2 l2 = __floats2half2_rn(df.x, df.y);
+          hw[(sub >> 1) + i] = *reinterpret_cast<const uint32_t*>(&h2);
+          lw[(sub >> 1) + i] = *reinterpret_cast<const uint32_t*>(&l2);
         }
-        ++kb;
+      } else if (planes) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (gcol + sub + i < N) split_store(dhi + gcol + sub + i, dlo + gcol + sub + i, y[i]);
       }
     }
+    // every thread of the group has read raw buffer b; the previous block's TMA store has read the output tile
+    if (use_tma && leader) ptx::bulk_wait_read<0>();
+    group_bar_sync(et.grp);
+    if (leader) prefetch();                            // block (current + 2) into the buffer just released
+    if (use_tma) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t off = ((static_cast<uint32_t>(i) ^ swz) << 4);
+        ptx::st_shared_v4(rowaddr + off, hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
+        ptx::st_shared_v4(rowaddr + kStgPlane + off, lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]);
+      }
+      ptx::fence_proxy_async_smem();
+      group_bar_sync(et.grp);
+      if (leader) {
+        ptx::tma_store_2d(tmD, stg, ea.dst_col0 + gcol, row_hi);
+        ptx::tma_store_2d(tmD, stg + kStgPlane, ea.dst_col0 + gcol, row_lo);
+        ptx::bulk_commit();
+      }
+    }
+    ++c.rb_it;
   }
   if (use_tma && leader) ptx::bulk_wait<0>();                      // stores performed before the layer is published
 }
@@ -1455,6 +1556,9 @@ __device__ __forceinline__ void epi_wide(const PlanParams& P, Ctx& c, const Laye
     c.part[et.grp * kTileM + et.row] = cnt_g[et.grp] > 0 ? x0 + s / n_g : 0.f;                       // group mean
     c.part[(kEpiGroups + et.grp) * kTileM + et.row] = cnt_g[et.grp] > 0 ? q - s * s / n_g : 0.f;     // group M2
   }
+  // the raw scratch was written through the generic proxy; pass 2 fetches it with bulk copies (async proxy)
+  __threadfence();
+  ptx::fence_proxy_async_all();
   epi_bar_sync();
   float mean = 0.f, rstd;
   {
@@ -1520,7 +1624,7 @@ __device__ __forceinline__ void publish_planes() {
 
 // ------------------------------------------------------------------------------------ one layer
 // GEMM + epilogue; on return the epilogue's outputs are published (CTA-synchronised, TMA-visible).
-template <int ENGINE, bool EPISODIC>
+template <int ENGINE, bool EPISODIC, bool WIDE>
 __device__ __forceinline__ void run_layer(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf, const EpiArgs& ea,
                                           const LayerDev* next) {
   const bool is_ln = (ea.kind == EPI_LN_MISH || ea.kind == EPI_LN_SIMNORM);
@@ -1529,29 +1633,35 @@ __device__ __forceinline__ void run_layer(const PlanParams& P, Ctx& c, const Lay
   if (fused) {
     const long long tl = clock64();
     if (threadIdx.x == 0) TDMPC2_TRACE(P, c, 0);
+    const int hseg = (WIDE && !is_ln && head_seg_ok(P, ea.kind)) ? head_segments(P, ly) : 1;   // K <= 512 unless the model is wide
     if (c.warp == 0) {
       if (c.lane == 0) tc_producer(P, c, ly, srcbuf, next);
     } else if (c.warp == 1) {
-      if (c.lane == 0 && (!c.cg2 || c.rank == 0)) tc_mma(P, c, ly);
+      if (c.lane == 0 && (!c.cg2 || c.rank == 0)) {
+        if (hseg > 1) tc_mma_head_seg(P, c, ly, hseg);
+        else tc_mma(P, c, ly);
+      }
     } else if (c.warp >= kEpiWarp0) {
       if (is_ln) epi_ln_fused(P, c, ly, ea);
-      else epi_head_fused<EPISODIC>(P, c, ly, ea);
+      else epi_head_fused<EPISODIC>(P, c, ly, ea, hseg);
       ptx::tc_fence_before();
     }
     c.pf1 += clock64() - tl;
-    c.fph0 ^= 1;                                      // every thread tracks the facc phase
-  } else if (ENGINE == ENGINE_TC) {
+    // every thread tracks the facc phases: buffer 0 completed ceil(hseg / 2) times, buffer 1 floor(hseg / 2) times
+    c.fph0 ^= static_cast<uint32_t>(((hseg + 1) >> 1) & 1);
+    c.fph1 ^= static_cast<uint32_t>((hseg >> 1) & 1);
+  } else if (ENGINE == ENGINE_TC && WIDE) {
     // LayerNorm layers (and the diagnostic raw mode) wider than TMEM; heads are never wider than one N-chunk
     const long long tl = clock64();
     if (threadIdx.x == 0) TDMPC2_TRACE(P, c, 0);
     const int nph = wide_layer_tc(P, c, ly, srcbuf, ea);
     c.pf1 += clock64() - tl;
     c.fph0 ^= static_cast<uint32_t>(nph & 1);         // one facc phase per (super-chunk, K-segment)
-  } else {
+  } else if (ENGINE == ENGINE_SIMT) {
     gemm_simt(P, c, ly, srcbuf);
     if (is_ln) rows_ln_act(P, c, ly, ea);
     else rows_head<EPISODIC>(P, c, ly, ea);
-  }
+  }                                                   // (a tcgen05 kernel without WIDE is never launched on a model with wide layers)
   const long long tp = clock64();
   // LN layers that went out through TMA stores wrote nothing through the generic proxy: the leaders have
   // waited for their bulk groups, so a CTA barrier is all the next layer's TMA loads need.
@@ -1671,9 +1781,11 @@ __device__ __forceinline__ void refit_env(const PlanParams& P, uint8_t* scratch,
 // environment and every layer on the fused path is launched this way.
 // EPISODIC (cfg.episodic, single-task models): every rollout step gains the 3-layer termination head on z_{t+1}
 // and the value bookkeeping its sticky (1 - termination) factor (tdmpc2.py:126-136); compiled out otherwise.
+// WIDE: the model has layers wider than the 512 TMEM columns (48M / 317M presets): adds the super-chunked wide-layer path and
+// the K-segmented heads; compiled out of the kernels the 5M preset runs (their register allocation is untouched by it).
 // WPF (CEM iterations of fully fused models): the TMA producer prefetches the next layer's first weight chunks into
 // the W ring while the epilogue runs; the epilogue stages its output in the A ring instead.  Same arithmetic.
-template <int ENGINE, bool CG2 = false, bool EPISODIC = false, bool WPF = false>
+template <int ENGINE, bool CG2 = false, bool EPISODIC = false, bool WPF = false, bool WIDE = false>
 __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant__ PlanParams P) {
   constexpr int SPT = EPISODIC ? 9 : 6;      // layer steps per rollout time step (ITER / VALUE)
   extern __shared__ uint8_t smem_raw[];
@@ -1691,6 +1803,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
     c.facc = c.acc_empty + 2;
     c.tmem_ptr = reinterpret_cast<uint32_t*>(c.facc + 2);
     c.flags = reinterpret_cast<int*>(c.tmem_ptr + 1);          // [8]
+    c.rawb = reinterpret_cast<uint64_t*>(ctrl + 184);           // [8]  (ends at ctrl + 248)
     c.G = reinterpret_cast<float*>(ctrl + 256);                 // [128]  (18 mbarriers + tmem ptr + flags live below 256)
     c.q1 = c.G + kTileM;                                        // [128]  (ends at ctrl + 1280)
     c.term = c.q1 + kTileM;                                     // [128]  (ends at ctrl + 1792 <= kSmemCtrl)
@@ -1711,6 +1824,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
   c.lane = threadIdx.x & 31;
   c.pa_it = c.pw_it = c.ma_it = c.mw_it = c.a_it = c.d_it = 0;
   c.fph0 = c.fph1 = 0;
+  c.rb_it = 0;
   c.pf0 = c.pf1 = c.pf2 = c.pf3 = c.pf4 = c.pf5 = c.pf6 = c.pf7 = 0;
   c.trace_step = 1 << 30;
   const long long t_kernel0 = clock64();
@@ -1726,6 +1840,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
         ptx::mbar_init(&c.acc_empty[s], CG2 ? 2 : 1);   // wide layers: one arrival per CTA of the pair (its drain is done)
         ptx::mbar_init(&c.facc[s], 1);
       }
+      for (int s = 0; s < 2 * kEpiGroups; ++s) ptx::mbar_init(&c.rawb[s], 1);
       ptx::fence_barrier_init();
       ptx::prefetch_tensormap(&P.tmX);
       ptx::prefetch_tensormap(&P.tmH);
@@ -1940,7 +2055,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
                           : mlp1 == 0 ? P.li_rew : mlp1 == 1 ? P.li_dyn : mlp1 == 2 ? P.li_pi : P.li_q + 3 * qi[mlp1 - 3];
         next = &LY[base1 + l1];
       }
-      run_layer<ENGINE, EPISODIC>(P, c, LY[li], src, ea, next);
+      run_layer<ENGINE, EPISODIC, WIDE>(P, c, LY[li], src, ea, next);
     }
 
     const long long t_refit = clock64();

@@ -175,6 +175,9 @@ class Planner:
         # wide presets: K elements accumulated in TMEM per segment (see include/tdmpc2_b200.h, tdmpc2_planner_set_kseg)
         self.kseg = int(os.environ.get("TDMPC2_B200_KSEG", cfg.get("kseg", DEFAULT_KSEG)))
         _cabi.check(self.lib.tdmpc2_planner_set_kseg(self.h, self.kseg))
+        if "TDMPC2_B200_HEAD_KSEG" in os.environ or cfg.get("head_kseg", None) is not None:
+            _cabi.check(self.lib.tdmpc2_planner_set_head_kseg(
+                self.h, int(os.environ.get("TDMPC2_B200_HEAD_KSEG", cfg.get("head_kseg", 512) or 0))))
         self._keep = []       # tensors referenced by in-flight async calls
         self.weights_version = None
         self._graphs = {}     # eval_mode -> captured launch chain + its static buffers
