@@ -523,8 +523,10 @@ struct LaunchCfg {
 };
 
 template <class K>
-static int launch_one(tdmpc2_planner* p, K kernel, int grid, size_t smem, cudaStream_t st, bool cluster2, const PlanParams& prm) {
+static int launch_one(tdmpc2_planner* p, K kernel, int grid, size_t smem, cudaStream_t st, bool cluster2, const PlanParams& prm,
+                      int threads = kThreads) {
   LaunchCfg lc(p, grid, smem, st, cluster2);
+  lc.cfg.blockDim = dim3(threads);
   CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, kernel, prm));
   CUDA_TRY(cudaGetLastError());
   p->launches += 1;
@@ -564,7 +566,7 @@ static int launch_plan(tdmpc2_planner* p, const PlanParams& prm, int ntiles, cud
       CUDA_TRY(cudaFuncSetAttribute(plan_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPPSmemBytes));
       p->smem_attr_pp = true;
     }
-    return launch_one(p, plan_pp_kernel, grid & ~1, kPPSmemBytes, st, true, prm2);
+    return launch_one(p, plan_pp_kernel, grid & ~1, kPPSmemBytes, st, true, prm2, kPPThreads);
   }
   bool* ad = p->attr_done;
   if (simt) {

@@ -64,9 +64,9 @@ static_assert(kARing * kASlotBytes + kWRing * kWSlotBytes == kStages * kStageByt
 // each, 64-byte-swizzled; the 128 KiB alias the W ring (idle once every MMA of the layer has retired).
 constexpr int kStgPlane = kTileM * 64;                    // 8 KiB
 constexpr int kStgBuf = 2 * kStgPlane;                    // 16 KiB
-constexpr int kThreads = 640;
+constexpr int kThreads = 576;                   // 18 warps: 65536 / 576 = 113 -> 112 registers per thread
 constexpr int kWarps = kThreads / 32;
-constexpr int kEpiWarp0 = 4;                    // warps 4..19 are the epilogue warps: 4 column groups x 4 lane quarters
+constexpr int kEpiWarp0 = 2;                    // warps 2..17 are the epilogue warps: 4 column groups x 4 lane quarters
 constexpr int kEpiGroups = 4;
 constexpr int kEpiThreads = kEpiGroups * 128;
 constexpr int kMaxWMaps = 8;
@@ -134,6 +134,22 @@ struct PlanParams {
   int kseg;          // wide layers: K-chunks (of 64) accumulated in TMEM before the partial sum is flushed to the fp32 raw
                      // scratch and added there with round-to-nearest (0 = the whole K in one go); see epi_wide
 };
+
+// The layer table lives in global memory; role loops are full of asm volatile(... "memory") (TMA issue, mbarrier waits,
+// fences), each of which would force the compiler to re-read any field it needs afterwards -- a dependent global load
+// in the single-thread producer / MMA loops and in the epilogue's inner loops.  Roles therefore work on a by-value copy.
+struct LayerRec {
+  int K, Kpad, N, Npad, wmap, wrow;
+  float inv_scale;
+  const float* bias; const float* ln_g; const float* ln_b;
+  const __half* w_hi; const __half* w_lo;
+};
+__device__ __forceinline__ LayerRec layer_rec(const LayerDev& l) {
+  LayerRec r;
+  r.K = l.K; r.Kpad = l.Kpad; r.N = l.N; r.Npad = l.Npad; r.wmap = l.wmap; r.wrow = l.wrow; r.inv_scale = l.inv_scale;
+  r.bias = l.bias; r.ln_g = l.ln_g; r.ln_b = l.ln_b; r.w_hi = l.w_hi; r.w_lo = l.w_lo;
+  return r;
+}
 
 // What a layer's epilogue has to do besides the activation itself.
 struct EpiArgs {
@@ -206,11 +222,20 @@ __device__ __forceinline__ void epi_bar_sync() {   // named barrier among the 8 
   asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
 }
 
-// Diagnostics: raw clock stamps of CTA 0 (events x layers) appended after the per-CTA counters.
+// Diagnostics (cycle counters per role, clock stamps per layer of CTA 0) exist only in builds with -DTDMPC2_PROF
+// (tdmpc2_b200.build.build_variant("prof", ["TDMPC2_PROF=1"]), loaded through TDMPC2_B200_LIB): in the product build
+// they compile to nothing -- the 8 per-thread 64-bit counters alone cost 16 registers of a 96-register budget.
+#ifdef TDMPC2_PROF
+constexpr bool kProf = true;
+#else
+constexpr bool kProf = false;
+#endif
+__device__ __forceinline__ long long prof_clock() { return kProf ? clock64() : 0ll; }
+// Raw clock stamps of CTA 0 (events x layers) appended after the per-CTA counters.
 #define TDMPC2_TRACE(P_, c_, ev_)                                                                         \
   do {                                                                                                    \
-    if ((P_).prof && blockIdx.x == 0 && (c_).trace_step < 32)                                              \
-      (P_).prof[static_cast<size_t>((P_).prof_slots) * 4 * 12 + (c_).trace_step * 16 + (ev_)] = clock64();                                  \
+    if (kProf && (P_).prof && blockIdx.x == 0 && (c_).trace_step < 32)                                              \
+      (P_).prof[static_cast<size_t>((P_).prof_slots) * 4 * 12 + (c_).trace_step * 16 + (ev_)] = prof_clock();                                  \
   } while (0)
 
 // ------------------------------------------------------------------------------------ CTA context
@@ -340,9 +365,9 @@ __device__ __forceinline__ float pi_action(const PlanParams& P, float mu, float 
 //                 (acc_full / acc_empty) and A is re-streamed per chunk.
 __device__ __forceinline__ void prod_load_a(const PlanParams& P, Ctx& c, const CUtensorMap* tmA, int kc, int arow_hi, int arow_lo) {
   const uint32_t s = c.pa_it % kARing, ph = (c.pa_it / kARing) & 1;
-  const long long tw = clock64();
+  const long long tw = prof_clock();
   ptx::mbar_wait(&c.a_empty[s], ph ^ 1);
-  c.pf0 += clock64() - tw;
+  c.pf0 += prof_clock() - tw;
   uint8_t* st = c.stage_base + s * kASlotBytes;
   if (c.cg2) {
     // both CTAs of the pair stream their own 128 rows; the bytes of both land on the leader's barrier
@@ -356,26 +381,26 @@ __device__ __forceinline__ void prod_load_a(const PlanParams& P, Ctx& c, const C
   }
   ++c.pa_it;
 }
-__device__ __forceinline__ void prod_load_w(Ctx& c, const CUtensorMap* tmW, const LayerDev& ly, int kc, int nc) {
-  const int ncols = min(kNch, ly.Npad - nc * kNch);   // 128 or 256
+__device__ __forceinline__ void prod_load_w(Ctx& c, const CUtensorMap* tmW, int Npad, int wrow, int kc, int nc) {
+  const int ncols = min(kNch, Npad - nc * kNch);   // 128 or 256
   const uint32_t s = c.pw_it % c.w_ring, ph = (c.pw_it / c.w_ring) & 1;
-  const long long tw = clock64();
+  const long long tw = prof_clock();
   ptx::mbar_wait(&c.w_empty[s], ph ^ 1);
-  c.pf0 += clock64() - tw;
+  c.pf0 += prof_clock() - tw;
   uint8_t* st = c.stage_base + kWRingOff + s * c.w_stride;
   if (c.cg2) {
     // each CTA streams HALF of the N-chunk's weight rows (one 128-row box per plane; for a 128-column chunk only
     // its first 64 rows are consumed): the pair MMA reads B rows [0, N/2) from the leader and [N/2, N) from the peer
     if (c.rank == 0) ptx::mbar_expect_tx(&c.w_full[s], 2 * (2 * 128 * 128));
-    const int wr = ly.wrow + nc * kNch + c.rank * (ncols / 2);
+    const int wr = wrow + nc * kNch + c.rank * (ncols / 2);
     ptx::tma_load_2d_2sm(tmW, &c.w_full[s], st, kc * kKch, wr);
-    ptx::tma_load_2d_2sm(tmW, &c.w_full[s], st + c.w_lo_off, kc * kKch, wr + ly.Npad);
+    ptx::tma_load_2d_2sm(tmW, &c.w_full[s], st + c.w_lo_off, kc * kKch, wr + Npad);
   } else {
     ptx::mbar_expect_tx(&c.w_full[s], 2 * ncols * 128);
     for (int b = 0; b < ncols / 128; ++b) {
-      const int wr = ly.wrow + nc * kNch + b * 128;
+      const int wr = wrow + nc * kNch + b * 128;
       ptx::tma_load_2d(tmW, &c.w_full[s], st + b * (128 * 128), kc * kKch, wr);
-      ptx::tma_load_2d(tmW, &c.w_full[s], st + kWPlane + b * (128 * 128), kc * kKch, wr + ly.Npad);
+      ptx::tma_load_2d(tmW, &c.w_full[s], st + kWPlane + b * (128 * 128), kc * kKch, wr + Npad);
     }
   }
   ++c.pw_it;
@@ -383,7 +408,7 @@ __device__ __forceinline__ void prod_load_w(Ctx& c, const CUtensorMap* tmW, cons
 
 // N-chunks [nc0, nc0 + nnc_lim) of the layer (default: all of them): K-chunks outermost, each A chunk is loaded once
 // and multiplied with every N-chunk of the range; layers wider than TMEM call this once per 512-column super-chunk.
-__device__ __forceinline__ void tc_producer(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf, const LayerDev* next,
+__device__ __forceinline__ void tc_producer(const PlanParams& P, Ctx& c, const LayerRec& ly, int srcbuf, const LayerDev* next,
                                             int nc0 = 0, int nnc_lim = 1 << 30, int kc0 = 0, int kc_lim = 1 << 30) {
   const int nkc = min(ly.Kpad / kKch, kc0 + kc_lim);
   const int nnc = min((ly.Npad + kNch - 1) / kNch - nc0, nnc_lim);
@@ -396,7 +421,7 @@ __device__ __forceinline__ void tc_producer(const PlanParams& P, Ctx& c, const L
     prod_load_a(P, c, tmA, kc, arow_hi, arow_lo);
     for (int nc = nc0; nc < nc0 + nnc; ++nc) {
       if (skip) --skip;
-      else prod_load_w(c, tmW, ly, kc, nc);
+      else prod_load_w(c, tmW, ly.Npad, ly.wrow, kc, nc);
     }
   }
   if (c.wpf) {
@@ -407,7 +432,7 @@ __device__ __forceinline__ void tc_producer(const PlanParams& P, Ctx& c, const L
       const CUtensorMap* tmW2 = &P.tmW[next->wmap];
       const int nkc2 = next->Kpad / kKch, nnc2 = (next->Npad + kNch - 1) / kNch;
       for (int kc = 0; kc < nkc2 && n < c.w_ring; ++kc)
-        for (int nc = 0; nc < nnc2 && n < c.w_ring; ++nc) { prod_load_w(c, tmW2, *next, kc, nc); ++n; }
+        for (int nc = 0; nc < nnc2 && n < c.w_ring; ++nc) { prod_load_w(c, tmW2, next->Npad, next->wrow, kc, nc); ++n; }
     }
     c.w_pref = n;
   }
@@ -434,22 +459,22 @@ __device__ __forceinline__ void mma_stage(uint32_t d, uint32_t sa, uint32_t sw, 
 }
 __device__ __forceinline__ uint32_t mma_wait_a(Ctx& c) {
   const uint32_t s = c.ma_it % kARing, ph = (c.ma_it / kARing) & 1;
-  const long long tw = clock64();
+  const long long tw = prof_clock();
   ptx::mbar_wait(&c.a_full[s], ph);
-  c.pf0 += clock64() - tw;
+  c.pf0 += prof_clock() - tw;
   return s;
 }
 __device__ __forceinline__ uint32_t mma_wait_w(Ctx& c) {
   const uint32_t s = c.mw_it % c.w_ring, ph = (c.mw_it / c.w_ring) & 1;
-  const long long tw = clock64();
+  const long long tw = prof_clock();
   ptx::mbar_wait(&c.w_full[s], ph);
-  c.pf0 += clock64() - tw;
+  c.pf0 += prof_clock() - tw;
   return s;
 }
 
 // Accumulates N-chunks [nc0, nc0 + nnc_lim) of the layer into TMEM columns [0, 256 * nnc); facc[0] fires when all of
 // them are complete.
-__device__ __forceinline__ void tc_mma(const PlanParams& P, Ctx& c, const LayerDev& ly, int nc0 = 0, int nnc_lim = 1 << 30,
+__device__ __forceinline__ void tc_mma(const PlanParams& P, Ctx& c, const LayerRec& ly, int nc0 = 0, int nnc_lim = 1 << 30,
                                        int kc0 = 0, int kc_lim = 1 << 30) {
   const int nkc = min(ly.Kpad / kKch, kc0 + kc_lim);
   const int nnc = min((ly.Npad + kNch - 1) / kNch - nc0, nnc_lim);
@@ -481,11 +506,11 @@ __device__ __forceinline__ void tc_mma(const PlanParams& P, Ctx& c, const LayerD
 // segments in fp32 registers with round-to-nearest.  Why: tcgen05's accumulate step rounds TOWARD ZERO (measured:
 // scripts/micro/mma_rounding.py), which shrinks a long accumulation by ~n_MMA * 2^-25 relative; LayerNorm removes a
 // uniform shrink from the hidden layers, but the heads' logits have no LayerNorm behind them.
-__device__ __forceinline__ int head_segments(const PlanParams& P, const LayerDev& ly) {
+__device__ __forceinline__ int head_segments(const PlanParams& P, const LayerRec& ly) {
   const int nkc = ly.Kpad / kKch;
   return (P.head_kseg > 0 && nkc > P.head_kseg) ? (nkc + P.head_kseg - 1) / P.head_kseg : 1;
 }
-__device__ __forceinline__ void tc_mma_head_seg(const PlanParams& P, Ctx& c, const LayerDev& ly, int nseg) {
+__device__ __forceinline__ void tc_mma_head_seg(const PlanParams& P, Ctx& c, const LayerRec& ly, int nseg) {
   const int nkc = ly.Kpad / kKch;
   const uint32_t sbase = ptx::smem_u32(c.stage_base);
   const uint32_t idesc = ptx::make_idesc_f16(c.cg2 ? 2 * kTileM : kTileM, ly.Npad);
@@ -515,7 +540,7 @@ __device__ __forceinline__ void tc_mma_head_seg(const PlanParams& P, Ctx& c, con
 
 // ------------------------------------------------------------------------------------ SIMT engine: GEMM -> raw scratch
 // Same operands, plain fp32 FFMA on CUDA cores (exact products of the split operands).
-__device__ __forceinline__ void gemm_simt(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf) {
+__device__ __forceinline__ void gemm_simt(const PlanParams& P, Ctx& c, const LayerRec& ly, int srcbuf) {
   constexpr int BN = 64, BK = 32;
   float* sA = reinterpret_cast<float*>(c.stage_base);          // [BK][128+4]
   float* sW = sA + BK * (kTileM + 4);                          // [BK][BN+4]
@@ -587,7 +612,7 @@ __device__ __forceinline__ float ln_act_lane(float y, bool valid, int act) {
 }
 
 // LayerNorm (+ Mish | SimNorm) over raw rows; one warp per row, lane-strided columns; raw re-read from L2 per pass.
-__device__ __forceinline__ void rows_ln_act(const PlanParams& P, Ctx& c, const LayerDev& ly, const EpiArgs& ea) {
+__device__ __forceinline__ void rows_ln_act(const PlanParams& P, Ctx& c, const LayerRec& ly, const EpiArgs& ea) {
   const float* rawbase = raw_ptr(P, c.slot);
   const int N = ly.N;
   const float invN = 1.f / static_cast<float>(N);
@@ -626,7 +651,7 @@ __device__ __forceinline__ void rows_ln_act(const PlanParams& P, Ctx& c, const L
 }
 
 // Head output row -> smem row buffer: out[col] = raw*inv_scale + bias (plain Linear, no LN).
-__device__ __forceinline__ void head_row_to_smem(const PlanParams& P, Ctx& c, const LayerDev& ly, int r, float* buf) {
+__device__ __forceinline__ void head_row_to_smem(const PlanParams& P, Ctx& c, const LayerRec& ly, int r, float* buf) {
   const float* rr = raw_ptr(P, c.slot) + static_cast<size_t>(r) * P.NpadMax;
   for (int col = c.lane; col < ly.N; col += 32) buf[col] = fmaf(__ldcg(rr + col), ly.inv_scale, ly.bias[col]);
   __syncwarp();
@@ -647,7 +672,7 @@ __device__ __forceinline__ float two_hot_inv_row(const PlanParams& P, Ctx& c, co
 }
 
 template <bool EPISODIC>
-__device__ __forceinline__ void rows_head(const PlanParams& P, Ctx& c, const LayerDev& ly, const EpiArgs& ea) {
+__device__ __forceinline__ void rows_head(const PlanParams& P, Ctx& c, const LayerRec& ly, const EpiArgs& ea) {
   float* myrow = c.rowbuf + c.warp * kMaxHeadCols;
   __half* xhi = plane_ptr(P, c.slot, BUF_X, 0);
   __half* xlo = plane_ptr(P, c.slot, BUF_X, 1);
@@ -692,11 +717,12 @@ struct EpiThread {
 __device__ __forceinline__ EpiThread epi_thread(const Ctx& c) {
   EpiThread t;
   const int e = c.warp - kEpiWarp0;
-  t.q = e & 3; t.grp = e >> 2; t.row = t.q * 32 + c.lane;
+  t.q = c.warp & 3;                   // a warp may only touch the TMEM lane quarter (warp id % 4)
+  t.grp = e >> 2; t.row = t.q * 32 + c.lane;
   t.taddr = c.tmem_base + (static_cast<uint32_t>(t.q * 32) << 16);
   return t;
 }
-__device__ __forceinline__ void epi_stage_vectors(Ctx& c, const LayerDev& ly, bool with_ln) {
+__device__ __forceinline__ void epi_stage_vectors(Ctx& c, const LayerRec& ly, bool with_ln) {
   const int t = threadIdx.x - kEpiWarp0 * 32;
   for (int i = t; i < ly.Npad; i += kEpiThreads) {
     c.vec[i] = ly.bias[i];
@@ -838,7 +864,7 @@ __device__ __forceinline__ void epi_pass2_fast(const PlanParams& P, Ctx& c, cons
 // column groups; a group owns whole 64-column blocks (the TMA-store granule).
 // Pass 1 reads the accumulator row once for shifted first/second moments (groups merged with Chan's
 // parallel-variance formula), pass 2 re-reads it 16 columns at a time, normalises, activates and emits.
-__device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const LayerDev& ly, const EpiArgs& ea) {
+__device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const LayerRec& ly, const EpiArgs& ea) {
   const EpiThread et = epi_thread(c);
   const int N = ly.N;
   const int nblocks = ly.Npad / 64;
@@ -850,9 +876,9 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
   epi_stage_vectors(c, ly, true);
   const float* sb = c.vec; const float* sg = c.vec + kFusedMaxN; const float* sbe = c.vec + 2 * kFusedMaxN;
   if (nvalid > 0) {
-    const long long tw = clock64();
+    const long long tw = prof_clock();
     ptx::mbar_wait_long(&c.facc[0], c.fph0);
-    c.pf2 += clock64() - tw;
+    c.pf2 += prof_clock() - tw;
   }
   const bool tr0 = (et.grp == 0 && et.q == 0 && c.lane == 0), tr3 = (et.grp == 3 && et.q == 0 && c.lane == 0);
   if (tr0) TDMPC2_TRACE(P, c, 4);
@@ -919,7 +945,7 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
   }
   if (tr0) TDMPC2_TRACE(P, c, 5);
   epi_bar_sync();
-  if (tr0) { float dummy = c.part[et.row]; if (dummy == 123.456f) c.pf7++; TDMPC2_TRACE(P, c, 6); }
+  if (tr0) TDMPC2_TRACE(P, c, 6);
   float mean = 0.f, rstd;
   {
     float m2 = 0.f, cnt = 0.f;
@@ -1081,7 +1107,7 @@ __device__ __forceinline__ bool head_seg_ok(const PlanParams& P, int kind) {
 // thread adds the segments of its own columns in registers.  v[0..32): this thread's 32 columns at column offset col0
 // (two-hot: bins 32*grp..; pi: 16 mean logits then 16 log_std logits; termination: column 0).
 template <bool EPISODIC>
-__device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, const LayerDev& ly, const EpiArgs& ea, int nseg) {
+__device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, const LayerRec& ly, const EpiArgs& ea, int nseg) {
   const EpiThread et = epi_thread(c);
   const float inv_scale = ly.inv_scale;
   epi_stage_vectors(c, ly, false);
@@ -1093,12 +1119,11 @@ __device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, cons
   }
   const bool wide_twohot = (ea.kind == EPI_TWOHOT) && (P.B <= 32 * kEpiGroups);
   const bool wide_pi = (ea.kind == EPI_PI) && (P.A <= 16 * kEpiGroups);
-  uint32_t v[32];
+  float v[32];                                         // this thread's accumulator values (scaled domain)
   if (nseg > 1) {
     // every epilogue warp takes part in the hand-off protocol, whether or not it owns columns of this head
-    float acc[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 32; ++i) v[i] = 0.f;
     const bool mine = wide_twohot || wide_pi || et.grp == 0;
     for (int seg = 0; seg < nseg; ++seg) {
       const int b = seg & 1;
@@ -1116,7 +1141,7 @@ __device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, cons
           ptx::tmem_ld_32x16(ta + (h ? c_hi : c_lo), a0);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) acc[16 * h + i] += __uint_as_float(a0[i]);
+          for (int i = 0; i < 16; ++i) v[16 * h + i] += __uint_as_float(a0[i]);
         }
       }
       if (seg + 2 < nseg) {                            // the buffer is reused: tell the MMA issuer it has been read
@@ -1128,15 +1153,13 @@ __device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, cons
         }
       }
     }
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(acc[i]);
     if (!mine) return;
   } else {
     if (!wide_twohot && !wide_pi && et.grp != 0) return;
     {
-      const long long tw = clock64();
+      const long long tw = prof_clock();
       ptx::mbar_wait_long(&c.facc[0], c.fph0);
-      c.pf2 += clock64() - tw;
+      c.pf2 += prof_clock() - tw;
     }
     ptx::tc_fence_after();
   }
@@ -1147,14 +1170,17 @@ __device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, cons
     float* xch = c.vec + 2 * kFusedMaxN;                // [kEpiGroups][128]
     const int B = P.B, c0 = 32 * et.grp;
     if (nseg == 1) {
-      ptx::tmem_ld_32x32(et.taddr + c0, v);
+      uint32_t t32[32];
+      ptx::tmem_ld_32x32(et.taddr + c0, t32);
       ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(t32[i]);
     }
-    float x[32];
+    float (&x)[32] = v;                                // logits, in place
     float m = -CUDART_INF_F;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      x[i] = (c0 + i < B) ? fmaf(__uint_as_float(v[i]), inv_scale, sb[min(c0 + i, B - 1)]) : -CUDART_INF_F;
+      x[i] = (c0 + i < B) ? fmaf(v[i], inv_scale, sb[min(c0 + i, B - 1)]) : -CUDART_INF_F;
       m = fmaxf(m, x[i]);
     }
     c.part[et.grp * kTileM + et.row] = m;
@@ -1183,9 +1209,9 @@ __device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, cons
       uint32_t t16[16];
       ptx::tmem_ld_32x16(et.taddr, t16);
       ptx::tmem_ld_wait();
-      v[0] = t16[0];
+      v[0] = __uint_as_float(t16[0]);
     }
-    term_commit(c, et.row, fmaf(__uint_as_float(v[0]), inv_scale, sb[0]));
+    term_commit(c, et.row, fmaf(v[0], inv_scale, sb[0]));
   } else if (ea.kind == EPI_TWOHOT) {
     const float* bins = c.vec + kFusedMaxN;
     const int B = P.B;
@@ -1225,7 +1251,7 @@ __device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, cons
       uint32_t vm[16], vs[16];
       if (nseg > 1) {                                   // wide_pi only: one 16-column block per thread, already summed
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { vm[i] = v[i]; vs[i] = v[16 + i]; }
+        for (int i = 0; i < 16; ++i) { vm[i] = __float_as_uint(v[i]); vs[i] = __float_as_uint(v[16 + i]); }
       } else {
         ptx::tmem_ld_32x16(et.taddr + a0, vm);            // mean logits, columns [a0, a0+16)
         ptx::tmem_ld_32x16(et.taddr + P.Apad + a0, vs);   // log_std logits, columns [Apad+a0, Apad+a0+16) (aligned)
@@ -1292,7 +1318,7 @@ __device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, cons
 // normalises, activates, splits to fp16 hi/lo and sends the planes out through swizzled smem tiles + TMA stores.
 // Every thread reads back exactly the raw elements it wrote itself.
 struct WideCols { int cb, ncols; };
-__device__ __forceinline__ WideCols wide_cols(const LayerDev& ly, int sc, int grp) {
+__device__ __forceinline__ WideCols wide_cols(const LayerRec& ly, int sc, int grp) {
   const int wsc = min(kFusedMaxN, ly.Npad - sc * kFusedMaxN);     // 128 .. 512, multiple of 128
   const int nblocks = wsc / 64;
   const int bpg = (nblocks + kEpiGroups - 1) / kEpiGroups;
@@ -1302,144 +1328,151 @@ __device__ __forceinline__ WideCols wide_cols(const LayerDev& ly, int sc, int gr
   return w;
 }
 
-// The normalise pass of a wide layer.  Both operand rings are idle by now (every MMA of the layer has retired), so the
-// whole 192 KiB of operand smem serve as staging: per column group two 16 KiB INPUT buffers in the W ring -- 32 raw
-// columns x 128 rows fp32, exactly one contiguous block of the column-major raw scratch, fetched with one bulk copy
-// (cp.async.bulk, mbarrier completion) two blocks ahead of its use, which hides the HBM latency of the 317M preset's
-// raw scratch (2 MB per slot) -- and one 16 KiB OUTPUT tile (hi | lo planes, 64-byte swizzle) in the A ring that leaves
-// through TMA stores.
+// LayerNorm affine + activation of 16 consecutive columns (x already holds acc * 2^-k + bias), in place.
+template <int KIND>
+__device__ __forceinline__ void wide_norm16(float (&y)[16], const float* __restrict__ g, const float* __restrict__ be,
+                                            float2 rstd2, float2 nmr2, int nvalid) {
+#pragma unroll
+  for (int i4 = 0; i4 < 16; i4 += 4) {
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(g + i4));
+    const float4 e4 = __ldg(reinterpret_cast<const float4*>(be + i4));
+    float2 t0 = __ffma2_rn(__ffma2_rn(f2(y[i4], y[i4 + 1]), rstd2, nmr2), f2(g4.x, g4.y), f2(e4.x, e4.y));
+    float2 t1 = __ffma2_rn(__ffma2_rn(f2(y[i4 + 2], y[i4 + 3]), rstd2, nmr2), f2(g4.z, g4.w), f2(e4.z, e4.w));
+    if (KIND == EPI_LN_MISH) { t0 = mish_fast2(t0); t1 = mish_fast2(t1); }
+    y[i4] = t0.x; y[i4 + 1] = t0.y; y[i4 + 2] = t1.x; y[i4 + 3] = t1.y;
+  }
+  if (nvalid < 16) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i >= nvalid) y[i] = (KIND == EPI_LN_MISH) ? 0.f : -CUDART_INF_F;
+  }
+  if (KIND == EPI_LN_SIMNORM) {
+    // SimNorm: softmax over groups of 8 consecutive columns (layers.py:84-88)
+#pragma unroll
+    for (int g0 = 0; g0 < 16; g0 += 8) {
+      float m = y[g0];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) m = fmaxf(m, y[g0 + i]);
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { y[g0 + i] = exp_fast(y[g0 + i] - m); t += y[g0 + i]; }
+      const float rt = rcp_ftz(t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[g0 + i] *= rt;
+    }
+  }
+}
+
+// The normalise pass of a wide layer, common case (planes out through TMA stores, whole 32-column blocks).  Both operand
+// rings are idle by now (every MMA of the layer has retired), so the whole 192 KiB of operand smem serve as staging:
+// per column group two 16 KiB INPUT buffers in the W ring -- 32 raw columns x 128 rows fp32, exactly one contiguous
+// block of the column-major raw scratch, fetched with one bulk copy (cp.async.bulk, mbarrier completion) two blocks
+// ahead of its use, which hides the HBM latency of the 317M preset's raw scratch (2 MB per slot) -- and one 16 KiB
+// OUTPUT tile (hi | lo planes, 64-byte swizzle) in the A ring that leaves through TMA stores.
+// Block b (columns [32 b, 32 b + 32)) belongs to column group b % 4: the raw scratch is global memory, so the
+// assignment need not follow the drain's (the stats-merge barrier has made every drained value visible).
 template <int KIND>   // EPI_LN_MISH | EPI_LN_SIMNORM
-__device__ __forceinline__ void wide_pass2(const PlanParams& P, Ctx& c, const EpiThread& et, const LayerDev& ly, const EpiArgs& ea,
-                                           int nsc, float rstd, float nmr) {
-  const int N = ly.N;
-  const float* rawT = raw_ptr(P, c.slot);                            // block of 32 columns at rawT + gcol * 128
-  const bool planes = ea.dstbuf >= 0;
-  const bool use_tma = planes && (N % 32 == 0) && (ea.dst_col0 % 32 == 0);
+__device__ __forceinline__ void wide_pass2_tma(const PlanParams& P, Ctx& c, const EpiThread& et, const LayerRec& ly, const EpiArgs& ea,
+                                               float rstd, float nmr) {
+  const int nblk = ly.N >> 5;                                         // N % 32 == 0 on this path
+  const float* rawT = raw_ptr(P, c.slot);                            // block b at rawT + b * 32 * 128
   uint8_t* inb = c.stage_base + kWRingOff + et.grp * (2 * kStgBuf);  // 2 x 16 KiB raw blocks
   uint8_t* stg = c.stage_base + et.grp * kStgBuf;                    // 16 KiB output tile (hi 8 KiB | lo 8 KiB)
   uint64_t* bars = c.rawb + et.grp * 2;
   const bool leader = (et.q == 0) && (c.lane == 0);
   const CUtensorMap* tmD = (ea.dstbuf == BUF_X) ? &P.tmXs : &P.tmHs;
   const uint32_t swz = static_cast<uint32_t>((et.row >> 1) & 3);
-  const int row_hi = planes ? plane_row0(P, c.slot, ea.dstbuf, 0) : 0, row_lo = planes ? plane_row0(P, c.slot, ea.dstbuf, 1) : 0;
-  __half* dhi = planes ? plane_ptr(P, c.slot, ea.dstbuf, 0) + static_cast<size_t>(et.row) * plane_pitch(P, ea.dstbuf) + ea.dst_col0 : nullptr;
-  __half* dlo = planes ? plane_ptr(P, c.slot, ea.dstbuf, 1) + static_cast<size_t>(et.row) * plane_pitch(P, ea.dstbuf) + ea.dst_col0 : nullptr;
-  const int orow = ea.rowmap ? ea.rowmap[et.row] : et.row;
-  float* po = (ea.out_f32 && orow >= 0) ? ea.out_f32 + static_cast<size_t>(orow) * ea.out_pitch : nullptr;
+  const int row_hi = plane_row0(P, c.slot, ea.dstbuf, 0), row_lo = plane_row0(P, c.slot, ea.dstbuf, 1);
   const float2 rstd2 = f2s(rstd), nmr2 = f2s(nmr);
   const uint32_t rowaddr = ptx::smem_u32(stg) + static_cast<uint32_t>(et.row) * 64u;
-  // The group's blocks in visiting order: (super-chunk, column) cursors for the consumer and for the leader's prefetch.
-  auto next_block = [&](int& sc_i, int& c_i) {       // advance to the next block with valid columns; sc_i = nsc at the end
-    for (;;) {
-      if (sc_i >= nsc) return;
-      const WideCols w = wide_cols(ly, sc_i, et.grp);
-      if (c_i < w.cb) c_i = w.cb;
-      if (c_i < w.cb + w.ncols && sc_i * kFusedMaxN + c_i < N) return;
-      ++sc_i; c_i = 0;
+  uint32_t it = c.rb_it;                              // blocks consumed by this group so far: buffer = it & 1
+  if (leader) {
+    for (int j = 0; j < 2; ++j) {
+      const int b = et.grp + 4 * j;
+      if (b < nblk) {
+        const uint32_t ib = (it + j) & 1u;
+        ptx::mbar_expect_tx(&bars[ib], kStgBuf);
+        ptx::bulk_load(inb + ib * kStgBuf, rawT + static_cast<size_t>(b) * 32 * kTileM, kStgBuf, &bars[ib]);
+      }
     }
-  };
-  int psc = 0, pc = 0;                               // prefetch cursor (leader)
-  uint32_t issued = c.rb_it;                         // blocks requested so far (leader); block k uses buffer k & 1
-  auto prefetch = [&]() {
-    next_block(psc, pc);
-    if (psc >= nsc) return;
-    const uint32_t b = issued & 1u;
-    ptx::mbar_expect_tx(&bars[b], kStgBuf);
-    ptx::bulk_load(inb + b * kStgBuf, rawT + static_cast<size_t>(psc * kFusedMaxN + pc) * kTileM, kStgBuf, &bars[b]);
-    ++issued;
-    pc += 32;
-  };
-  if (leader) { prefetch(); prefetch(); }
-  int sc = 0, c0 = 0;
-  for (next_block(sc, c0); sc < nsc; c0 += 32, next_block(sc, c0)) {
-    const int gcol = sc * kFusedMaxN + c0;
-    const uint32_t b = c.rb_it & 1u;
-    ptx::mbar_wait(&bars[b], (c.rb_it >> 1) & 1u);
-    const float* blk = reinterpret_cast<const float*>(inb + b * kStgBuf) + et.row;     // element (col, row) at blk[col * 128]
-    uint32_t hw[16], lw[16];
+  }
+  for (int b = et.grp; b < nblk; b += kEpiGroups, ++it) {
+    const uint32_t ib = it & 1u;
+    // the previous block's TMA store has finished reading the output tile
+    if (leader) ptx::bulk_wait_read<0>();
+    group_bar_sync(et.grp);
+    ptx::mbar_wait(&bars[ib], (it >> 1) & 1u);
+    const float* blk = reinterpret_cast<const float*>(inb + ib * kStgBuf) + et.row;     // element (col, row) at blk[col * 128]
 #pragma unroll
     for (int sub = 0; sub < 32; sub += 16) {
       float y[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) y[i] = blk[(sub + i) * kTileM];
-      const bool full = (gcol + sub + 16 <= N);
+      wide_norm16<KIND>(y, ly.ln_g + b * 32 + sub, ly.ln_b + b * 32 + sub, rstd2, nmr2, 16);
+      uint32_t hw[8], lw[8];
 #pragma unroll
-      for (int i4 = 0; i4 < 16; i4 += 4) {
-        const float4 g4 = __ldg(reinterpret_cast<const float4*>(ly.ln_g + gcol + sub + i4));
-        const float4 e4 = __ldg(reinterpret_cast<const float4*>(ly.ln_b + gcol + sub + i4));
-        float2 t0 = __ffma2_rn(__ffma2_rn(f2(y[i4], y[i4 + 1]), rstd2, nmr2), f2(g4.x, g4.y), f2(e4.x, e4.y));
-        float2 t1 = __ffma2_rn(__ffma2_rn(f2(y[i4 + 2], y[i4 + 3]), rstd2, nmr2), f2(g4.z, g4.w), f2(e4.z, e4.w));
-        if (KIND == EPI_LN_MISH) { t0 = mish_fast2(t0); t1 = mish_fast2(t1); }
-        y[i4] = t0.x; y[i4 + 1] = t0.y; y[i4 + 2] = t1.x; y[i4 + 3] = t1.y;
+      for (int i = 0; i < 8; ++i) {
+        const float a0 = y[2 * i], a1 = y[2 * i + 1];
+        const __half2 h2 = __floats2half2_rn(a0, a1);
+        const float2 hf = __half22float2(h2);
+        const float2 df = __fadd2_rn(f2(a0, a1), f2(-hf.x, -hf.y));
+        const __half2 l2 = __floats2half2_rn(df.x, df.y);
+        hw[i] = *reinterpret_cast<const uint32_t*>(&h2);
+        lw[i] = *reinterpret_cast<const uint32_t*>(&l2);
       }
-      if (!full) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (gcol + sub + i >= N) y[i] = (KIND == EPI_LN_MISH) ? 0.f : -CUDART_INF_F;
-      }
-      if (KIND == EPI_LN_SIMNORM) {
-        // SimNorm: softmax over groups of 8 consecutive columns (layers.py:84-88)
-#pragma unroll
-        for (int g0 = 0; g0 < 16; g0 += 8) {
-          float m = y[g0];
-#pragma unroll
-          for (int i = 1; i < 8; ++i) m = fmaxf(m, y[g0 + i]);
-          float t = 0.f;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { y[g0 + i] = exp_fast(y[g0 + i] - m); t += y[g0 + i]; }
-          const float rt = rcp_ftz(t);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) y[g0 + i] *= rt;
-        }
-      }
-      if (po) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (gcol + sub + i < N) po[gcol + sub + i] = y[i];
-      }
-      if (use_tma) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float a0 = y[2 * i], a1 = y[2 * i + 1];
-          const __half2 h2 = __floats2half2_rn(a0, a1);
-          const float2 hf = __half22float2(h2);
-          const float2 df = __fadd2_rn(f2(a0, a1), f2(-hf.x, -hf.y));
-          const __half2 l2 = __floats2half2_rn(df.x, df.y);
-          hw[(sub >> 1) + i] = *reinterpret_cast<const uint32_t*>(&h2);
-          lw[(sub >> 1) + i] = *reinterpret_cast<const uint32_t*>(&l2);
-        }
-      } else if (planes) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (gcol + sub + i < N) split_store(dhi + gcol + sub + i, dlo + gcol + sub + i, y[i]);
-      }
-    }
-    // every thread of the group has read raw buffer b; the previous block's TMA store has read the output tile
-    if (use_tma && leader) ptx::bulk_wait_read<0>();
-    group_bar_sync(et.grp);
-    if (leader) prefetch();                            // block (current + 2) into the buffer just released
-    if (use_tma) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t off = ((static_cast<uint32_t>(i) ^ swz) << 4);
+      for (int i = 0; i < 2; ++i) {
+        const uint32_t off = ((static_cast<uint32_t>((sub >> 3) + i) ^ swz) << 4);
         ptx::st_shared_v4(rowaddr + off, hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
         ptx::st_shared_v4(rowaddr + kStgPlane + off, lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]);
       }
-      ptx::fence_proxy_async_smem();
-      group_bar_sync(et.grp);
-      if (leader) {
-        ptx::tma_store_2d(tmD, stg, ea.dst_col0 + gcol, row_hi);
-        ptx::tma_store_2d(tmD, stg + kStgPlane, ea.dst_col0 + gcol, row_lo);
-        ptx::bulk_commit();
+    }
+    ptx::fence_proxy_async_smem();
+    group_bar_sync(et.grp);                            // tile complete; every thread of the group is done with raw buffer ib
+    if (leader) {
+      ptx::tma_store_2d(tmD, stg, ea.dst_col0 + b * 32, row_hi);
+      ptx::tma_store_2d(tmD, stg + kStgPlane, ea.dst_col0 + b * 32, row_lo);
+      ptx::bulk_commit();
+      const int nb = b + 2 * kEpiGroups;               // refill the buffer just released, two blocks ahead
+      if (nb < nblk) {
+        ptx::mbar_expect_tx(&bars[ib], kStgBuf);
+        ptx::bulk_load(inb + ib * kStgBuf, rawT + static_cast<size_t>(nb) * 32 * kTileM, kStgBuf, &bars[ib]);
       }
     }
-    ++c.rb_it;
   }
-  if (use_tma && leader) ptx::bulk_wait<0>();                      // stores performed before the layer is published
+  c.rb_it = it;
+  if (leader) ptx::bulk_wait<0>();                                 // stores performed before the layer is published
+}
+
+// General fallback of the normalise pass (fp32 row output, ragged N, unaligned destination): plain loads of the raw
+// scratch, scalar stores.  Only the encoder's last layer and the diagnostic mode come here.
+template <int KIND>
+__device__ __forceinline__ void wide_pass2_general(const PlanParams& P, Ctx& c, const EpiThread& et, const LayerRec& ly, const EpiArgs& ea,
+                                                   float rstd, float nmr) {
+  const int N = ly.N;
+  const float* rawT = raw_ptr(P, c.slot) + et.row;
+  const bool planes = ea.dstbuf >= 0;
+  __half* dhi = planes ? plane_ptr(P, c.slot, ea.dstbuf, 0) + static_cast<size_t>(et.row) * plane_pitch(P, ea.dstbuf) + ea.dst_col0 : nullptr;
+  __half* dlo = planes ? plane_ptr(P, c.slot, ea.dstbuf, 1) + static_cast<size_t>(et.row) * plane_pitch(P, ea.dstbuf) + ea.dst_col0 : nullptr;
+  const int orow = ea.rowmap ? ea.rowmap[et.row] : et.row;
+  float* po = (ea.out_f32 && orow >= 0) ? ea.out_f32 + static_cast<size_t>(orow) * ea.out_pitch : nullptr;
+  const float2 rstd2 = f2s(rstd), nmr2 = f2s(nmr);
+  for (int c0 = 16 * et.grp; c0 < N; c0 += 16 * kEpiGroups) {        // N <= Npad, the parameter vectors are padded to Npad
+    float y[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) y[i] = (c0 + i < ly.Npad) ? __ldcg(rawT + static_cast<size_t>(c0 + i) * kTileM) : 0.f;
+    wide_norm16<KIND>(y, ly.ln_g + c0, ly.ln_b + c0, rstd2, nmr2, min(16, N - c0));
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (c0 + i < N) {
+        if (po) po[c0 + i] = y[i];
+        if (planes) split_store(dhi + c0 + i, dlo + c0 + i, y[i]);
+      }
+  }
 }
 
 // Epilogue warps of a wide layer (EPI_LN_MISH | EPI_LN_SIMNORM | EPI_RAW).
-__device__ __forceinline__ void epi_wide(const PlanParams& P, Ctx& c, const LayerDev& ly, const EpiArgs& ea, int nsc, int nseg) {
+__device__ __forceinline__ void epi_wide(const PlanParams& P, Ctx& c, const LayerRec& ly, const EpiArgs& ea, int nsc, int nseg) {
   const EpiThread et = epi_thread(c);
   const int N = ly.N;
   const float inv_scale = ly.inv_scale;
@@ -1459,9 +1492,9 @@ __device__ __forceinline__ void epi_wide(const PlanParams& P, Ctx& c, const Laye
     // with round-to-nearest bounds it (at the price of one more drain per segment).
     const bool last_seg = (seg == nseg - 1);
     {
-      const long long tw = clock64();
+      const long long tw = prof_clock();
       ptx::mbar_wait_sleep(&c.facc[0], c.fph0 ^ static_cast<uint32_t>((sc * nseg + seg) & 1), P.wide_sleep_ns);
-      c.pf2 += clock64() - tw;
+      c.pf2 += prof_clock() - tw;
     }
     ptx::tc_fence_after();
     if (tr0 && sc == 0 && seg == 0) TDMPC2_TRACE(P, c, 4);          // first accumulator ready
@@ -1578,13 +1611,19 @@ __device__ __forceinline__ void epi_wide(const PlanParams& P, Ctx& c, const Laye
   }
   const float nmr = -mean * rstd;
   if (tr0) TDMPC2_TRACE(P, c, 6);
-  if (ea.kind == EPI_LN_MISH) wide_pass2<EPI_LN_MISH>(P, c, et, ly, ea, nsc, rstd, nmr);
-  else wide_pass2<EPI_LN_SIMNORM>(P, c, et, ly, ea, nsc, rstd, nmr);
+  const bool tma_out = ea.dstbuf >= 0 && !ea.out_f32 && (N % 32 == 0) && (ea.dst_col0 % 32 == 0);   // == run_layer's tma_only
+  if (tma_out) {
+    if (ea.kind == EPI_LN_MISH) wide_pass2_tma<EPI_LN_MISH>(P, c, et, ly, ea, rstd, nmr);
+    else wide_pass2_tma<EPI_LN_SIMNORM>(P, c, et, ly, ea, rstd, nmr);
+  } else {
+    if (ea.kind == EPI_LN_MISH) wide_pass2_general<EPI_LN_MISH>(P, c, et, ly, ea, rstd, nmr);
+    else wide_pass2_general<EPI_LN_SIMNORM>(P, c, et, ly, ea, rstd, nmr);
+  }
   if (tr0) TDMPC2_TRACE(P, c, 8);                                   // normalise pass done, stores performed
 }
 
 // GEMM roles + epilogue of a wide layer; returns the number of accumulator hand-offs (= facc phases consumed).
-__device__ __forceinline__ int wide_layer_tc(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf, const EpiArgs& ea) {
+__device__ __forceinline__ int wide_layer_tc(const PlanParams& P, Ctx& c, const LayerRec& ly, int srcbuf, const EpiArgs& ea) {
   const int nnc_all = (ly.Npad + kNch - 1) / kNch;
   const int nsc = (nnc_all + 1) / 2;
   const int nkc = ly.Kpad / kKch;
@@ -1599,9 +1638,9 @@ __device__ __forceinline__ int wide_layer_tc(const PlanParams& P, Ctx& c, const 
       for (int sc = 0; sc < nsc; ++sc)
         for (int seg = 0; seg < nseg; ++seg) {
           if (sc + seg > 0) {                           // the previous accumulator has been drained
-            const long long tw = clock64();
+            const long long tw = prof_clock();
             ptx::mbar_wait(&c.acc_empty[0], c.a_it & 1);
-            c.pf0 += clock64() - tw;
+            c.pf0 += prof_clock() - tw;
             ++c.a_it;
             ptx::tc_fence_after();
           }
@@ -1625,13 +1664,14 @@ __device__ __forceinline__ void publish_planes() {
 // ------------------------------------------------------------------------------------ one layer
 // GEMM + epilogue; on return the epilogue's outputs are published (CTA-synchronised, TMA-visible).
 template <int ENGINE, bool EPISODIC, bool WIDE>
-__device__ __forceinline__ void run_layer(const PlanParams& P, Ctx& c, const LayerDev& ly, int srcbuf, const EpiArgs& ea,
+__device__ __forceinline__ void run_layer(const PlanParams& P, Ctx& c, const LayerDev& ly_global, int srcbuf, const EpiArgs& ea,
                                           const LayerDev* next) {
+  const LayerRec ly = layer_rec(ly_global);          // registers: see LayerRec
   const bool is_ln = (ea.kind == EPI_LN_MISH || ea.kind == EPI_LN_SIMNORM);
   const bool fused = (ENGINE == ENGINE_TC) && (ly.Npad <= kFusedMaxN) && (is_ln || ly.Npad <= kNch) &&
                      (ea.kind != EPI_RAW || ly.Npad <= kNch);
   if (fused) {
-    const long long tl = clock64();
+    const long long tl = prof_clock();
     if (threadIdx.x == 0) TDMPC2_TRACE(P, c, 0);
     const int hseg = (WIDE && !is_ln && head_seg_ok(P, ea.kind)) ? head_segments(P, ly) : 1;   // K <= 512 unless the model is wide
     if (c.warp == 0) {
@@ -1646,29 +1686,29 @@ __device__ __forceinline__ void run_layer(const PlanParams& P, Ctx& c, const Lay
       else epi_head_fused<EPISODIC>(P, c, ly, ea, hseg);
       ptx::tc_fence_before();
     }
-    c.pf1 += clock64() - tl;
+    c.pf1 += prof_clock() - tl;
     // every thread tracks the facc phases: buffer 0 completed ceil(hseg / 2) times, buffer 1 floor(hseg / 2) times
     c.fph0 ^= static_cast<uint32_t>(((hseg + 1) >> 1) & 1);
     c.fph1 ^= static_cast<uint32_t>((hseg >> 1) & 1);
   } else if (ENGINE == ENGINE_TC && WIDE) {
     // LayerNorm layers (and the diagnostic raw mode) wider than TMEM; heads are never wider than one N-chunk
-    const long long tl = clock64();
+    const long long tl = prof_clock();
     if (threadIdx.x == 0) TDMPC2_TRACE(P, c, 0);
     const int nph = wide_layer_tc(P, c, ly, srcbuf, ea);
-    c.pf1 += clock64() - tl;
+    c.pf1 += prof_clock() - tl;
     c.fph0 ^= static_cast<uint32_t>(nph & 1);         // one facc phase per (super-chunk, K-segment)
   } else if (ENGINE == ENGINE_SIMT) {
     gemm_simt(P, c, ly, srcbuf);
     if (is_ln) rows_ln_act(P, c, ly, ea);
     else rows_head<EPISODIC>(P, c, ly, ea);
   }                                                   // (a tcgen05 kernel without WIDE is never launched on a model with wide layers)
-  const long long tp = clock64();
+  const long long tp = prof_clock();
   // LN layers that went out through TMA stores wrote nothing through the generic proxy: the leaders have
   // waited for their bulk groups, so a CTA barrier is all the next layer's TMA loads need.
   const bool tma_only = (ENGINE == ENGINE_TC) && is_ln && ea.dstbuf >= 0 && (ly.N % 32 == 0) && (ea.dst_col0 % 32 == 0) && !ea.out_f32;
   if (tma_only) __syncthreads();
   else publish_planes();
-  c.pf3 += clock64() - tp;
+  c.pf3 += prof_clock() - tp;
   if (threadIdx.x == 64 && ENGINE == ENGINE_TC) TDMPC2_TRACE(P, c, 9);
   if (ENGINE == ENGINE_TC) ptx::tc_fence_after();
 }
@@ -1791,8 +1831,16 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   Ctx c;
   {
-    uintptr_t base = (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023);
-    c.stage_base = reinterpret_cast<uint8_t*>(base);
+    // The operand tiles need 1024-byte alignment (128-byte swizzle atoms).  The kernel has no static shared memory, so
+    // the dynamic window starts right after the 1 KiB the system reserves per CTA: it IS 1024-aligned, which is checked
+    // here instead of being fixed up -- every smem pointer below is then the array symbol plus a compile-time constant
+    // (no register, nothing to spill; the round-up through uintptr_t used before cost a 64-bit base that ptxas spilled
+    // and reloaded at ~100 sites).
+    if ((ptx::smem_u32(smem_raw) & 1023u) != 0u) {
+      if (threadIdx.x == 0) printf("tdmpc2_b200: dynamic shared memory is not 1024-byte aligned (0x%x)\n", ptx::smem_u32(smem_raw));
+      __trap();
+    }
+    c.stage_base = smem_raw;
     uint8_t* ctrl = c.stage_base + kStages * kStageBytes;
     c.a_full = reinterpret_cast<uint64_t*>(ctrl);
     c.a_empty = c.a_full + kARing;
@@ -1827,7 +1875,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
   c.rb_it = 0;
   c.pf0 = c.pf1 = c.pf2 = c.pf3 = c.pf4 = c.pf5 = c.pf6 = c.pf7 = 0;
   c.trace_step = 1 << 30;
-  const long long t_kernel0 = clock64();
+  const long long t_kernel0 = prof_clock();
   c.tmem_base = 0;
   int* rowenv = c.rowenv;
 
@@ -1846,7 +1894,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
       ptx::prefetch_tensormap(&P.tmH);
     }
     if (CG2) ptx::cluster_sync();          // the peer's barriers are initialised before anything can signal them
-    if (c.warp == 2) { if (CG2) ptx::tmem_alloc_2sm(c.tmem_ptr, 512); else ptx::tmem_alloc(c.tmem_ptr, 512); }
+    if (c.warp == 1) { if (CG2) ptx::tmem_alloc_2sm(c.tmem_ptr, 512); else ptx::tmem_alloc(c.tmem_ptr, 512); }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -1859,7 +1907,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
   for (int tile = CG2 ? 2 * (static_cast<int>(blockIdx.x) >> 1) + c.rank : static_cast<int>(blockIdx.x); tile < P.ntiles;
        tile += gridDim.x) {
     // ---------------- tile set-up: fill the input planes of X ----------------
-    const long long t_setup = clock64();
+    const long long t_setup = prof_clock();
     for (int r = threadIdx.x; r < kTileM; r += kThreads) {
       rowenv[r] = map_row(P, tile, r).env; c.G[r] = 0.f; c.q1[r] = 0.f;
       if (EPISODIC) c.term[r] = 0.f;
@@ -1936,7 +1984,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
       }
     }
     publish_planes();
-    c.pf4 += clock64() - t_setup;
+    c.pf4 += prof_clock() - t_setup;
 
     // ---------------- the tile's layer program: ONE run_layer call site ----------------
     //   ENCODE : enc.0 .. enc.(n-1)
@@ -1975,7 +2023,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
           mlp = l < 3 ? 0 : ((EPISODIC && l >= 6) ? 5 : 1); l %= 3;
           if (mlp == 0 && l == 0) {
             // X action columns <- a_t  (tdmpc2.py:176-181)
-            const long long t_act = clock64();
+            const long long t_act = prof_clock();
             if (P.actions_explicit) {
               for (int i = threadIdx.x; i < kTileM * P.A; i += kThreads) {
                 const int r = i / P.A, a = i % P.A;
@@ -2012,7 +2060,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
               }
             }
             publish_planes();
-            c.pf5 += clock64() - t_act;
+            c.pf5 += prof_clock() - t_act;
           }
         } else {
           const int u = sidx - SPT * P.H;
@@ -2058,7 +2106,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
       run_layer<ENGINE, EPISODIC, WIDE>(P, c, LY[li], src, ea, next);
     }
 
-    const long long t_refit = clock64();
+    const long long t_refit = prof_clock();
     if (P.mode == MODE_ITER) {
       // last CTA to finish a tile of this environment refits its mean/std
       __threadfence();
@@ -2075,17 +2123,17 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
       }
       publish_planes();     // refit_env wrote the stage smem through the generic proxy; TMA reuses it next tile
     }
-    c.pf6 += clock64() - t_refit;
+    c.pf6 += prof_clock() - t_refit;
   }
 
-  if (P.prof) {
+  if (kProf && P.prof) {
     // rows: 0 producer (warp 0 lane 0), 1 MMA issuer (warp 1 lane 0), 2 epilogue thread (warp 4 lane 0), 3 idle warp 2
     // cols: 0 barrier-wait cycles (empty | full), 1 cycles inside fused layers, 2 facc wait, 3 publish, 5 whole kernel
     const int who = (threadIdx.x == 0) ? 0 : (threadIdx.x == 32) ? 1 : (threadIdx.x == kEpiWarp0 * 32) ? 2
                     : (threadIdx.x == 64) ? 3 : -1;
     if (who >= 0) {
       long long* o = P.prof + (static_cast<size_t>(blockIdx.x) * 4 + who) * 12;
-      o[0] = c.pf0; o[1] = c.pf1; o[2] = c.pf2; o[3] = c.pf3; o[4] = c.pf4; o[5] = clock64() - t_kernel0;
+      o[0] = c.pf0; o[1] = c.pf1; o[2] = c.pf2; o[3] = c.pf3; o[4] = c.pf4; o[5] = prof_clock() - t_kernel0;
       o[6] = c.pf5; o[7] = c.pf6; o[8] = c.pf7;
     }
   }
@@ -2093,7 +2141,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
     ptx::tc_fence_before();
     __syncthreads();
     if (CG2) ptx::cluster_sync();          // neither CTA may retire while the pair's MMAs / barriers are in use
-    if (c.warp == 2) { if (CG2) ptx::tmem_dealloc_2sm(c.tmem_base, 512); else ptx::tmem_dealloc(c.tmem_base, 512); }
+    if (c.warp == 1) { if (CG2) ptx::tmem_dealloc_2sm(c.tmem_base, 512); else ptx::tmem_dealloc(c.tmem_base, 512); }
   }
 }
 

@@ -24,6 +24,10 @@
 
 namespace tdmpc2 {
 
+// This kernel keeps the 20-warp layout it was validated with (plan_kernel moved to 18 warps for register headroom).
+constexpr int kPPThreads = 640;
+constexpr int kPPEpiWarp0 = 4;                  // warps 4..19: epilogue
+struct GroupEpiPP { static constexpr int N = kEpiThreads; __device__ static int tid() { return threadIdx.x - kPPEpiWarp0 * 32; } __device__ static void sync() { epi_bar_sync(); } };
 constexpr int kPPHalf = 64;
 constexpr int kPPAPlane = kPPHalf * 128;               // 8 KiB: 64 rows x 64 fp16
 constexpr int kPPASlot = 2 * kPPAPlane;                // hi | lo
@@ -49,7 +53,7 @@ static_assert(kPPSmemBytes <= 232448, "ping-pong kernel shared memory");
 // Diagnostics: clock stamps of CTA 0's first tile, [step][event] after the per-CTA counters (see TDMPC2_TRACE).
 #define PP_TRACE(P_, on_, s_, ev_)                                                           \
   do {                                                                                      \
-    if ((P_).prof && (on_) && (s_) < 32) (P_).prof[static_cast<size_t>((P_).prof_slots) * 4 * 12 + (s_) * 16 + (ev_)] = clock64(); \
+    if (kProf && (P_).prof && (on_) && (s_) < 32) (P_).prof[static_cast<size_t>((P_).prof_slots) * 4 * 12 + (s_) * 16 + (ev_)] = prof_clock(); \
   } while (0)
 
 struct PPStep {
@@ -98,7 +102,7 @@ __device__ __forceinline__ void pp_head_commit(const PlanParams& P, PPCtx& c, co
 // X action columns of rows [r0, r0 + nrows) <- a_t (tdmpc2.py:176-181); epilogue threads only
 __device__ __forceinline__ void pp_write_actions(const PlanParams& P, PPCtx& c, int tile, int env, int task, int t, int r0,
                                                  int nrows, bool stage) {
-  const int tid = threadIdx.x - kEpiWarp0 * 32;
+  const int tid = threadIdx.x - kPPEpiWarp0 * 32;
   float* sm_mean = c.actv; float* sm_std = c.actv + kMaxHeadCols; float* sm_mask = c.actv + 2 * kMaxHeadCols;
   if (stage) {
     for (int a = tid; a < P.A; a += kEpiThreads) {
@@ -355,7 +359,7 @@ __device__ __forceinline__ void pp_epi_pi(const PlanParams& P, PPCtx& c, const P
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
-__global__ void __launch_bounds__(kThreads, 1) plan_pp_kernel(const __grid_constant__ PlanParams P) {
+__global__ void __launch_bounds__(kPPThreads, 1) plan_pp_kernel(const __grid_constant__ PlanParams P) {
   extern __shared__ uint8_t smem_raw[];
   PPCtx c;
   {
@@ -495,16 +499,16 @@ __global__ void __launch_bounds__(kThreads, 1) plan_pp_kernel(const __grid_const
         }
       }
     }
-  } else if (c.warp >= kEpiWarp0) {
+  } else if (c.warp >= kPPEpiWarp0) {
     // =================================================================== epilogue + glue (16 warps, both CTAs)
     PPThread et;
     {
-      const int e = c.warp - kEpiWarp0;
+      const int e = c.warp - kPPEpiWarp0;
       et.q = e & 3; et.grp = e >> 2; et.row = (et.q & 1) * 32 + c.lane; et.colhalf = et.q >> 1;
       et.bg = et.colhalf * 4 + et.grp;
       et.taddr = static_cast<uint32_t>(et.q * 32) << 16;
     }
-    const int tid = threadIdx.x - kEpiWarp0 * 32;
+    const int tid = threadIdx.x - kPPEpiWarp0 * 32;
     uint32_t fph[2] = {0, 0};
     int tcount = 0;
     for (int tile = tile0; tile < P.ntiles; tile += gridDim.x, ++tcount) {
@@ -617,7 +621,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_pp_kernel(const __grid_const
       epi_bar_sync();
       if (c.flags[0]) {
         __threadfence();
-        refit_env<GroupEpi>(P, c.base, static_cast<size_t>(kPPOperandBytes), env, task);
+        refit_env<GroupEpiPP>(P, c.base, static_cast<size_t>(kPPOperandBytes), env, task);
       }
       ptx::fence_proxy_async_all();         // refit wrote ring / staging smem through the generic proxy
       epi_bar_sync();

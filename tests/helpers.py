@@ -81,12 +81,13 @@ def slice_noise(nz, envs):
                  None if nz.final is None else nz.final[idx].contiguous())
 
 
-def compare_with_oracle(cfg, tr, action, new_mean, want, on, envs, value_tol=5e-5, gap=None):
+def compare_with_oracle(cfg, tr, action, new_mean, want, on, envs, value_atol=5e-5, value_rtol=1e-5, gap=None):
     """Kernel trace of environments `envs` (rows of the big batch) against oracle rows 0..len(envs)-1.
-    values within value_tol; top-k indices exact where the oracle's sorted values are separated by > gap (default
-    1e-4, never below 2*value_tol); refit mean/std and final action within 1e-4 (north-star tolerance) while the
-    elite set is unambiguous.  Returns counters so that callers can assert that the comparisons really ran."""
-    gap = max(1e-4, 2 * value_tol) if gap is None else gap
+    values: |got - want| <= value_atol + value_rtol * |want| (the tolerance of tests/test_gpu_parity.py: fp32 round-off
+    level -- the fp32 oracle itself is only that close to float64); top-k indices exact where the oracle's sorted values
+    are separated by > gap (default 2 x the value tolerance at that magnitude, at least 1e-4); refit mean/std and final
+    action within 1e-4 (north-star tolerance) while the elite set is unambiguous.  Returns counters so that callers can
+    assert that the comparisons really ran."""
     K = cfg.num_elites
     n = dict(values=0, topk=0, refit=0, actions=0, max_value_err=0.0)
     for j, e in enumerate(envs):
@@ -95,12 +96,13 @@ def compare_with_oracle(cfg, tr, action, new_mean, want, on, envs, value_tol=5e-
             v_got, v_want = tr["values"][e, it].cpu(), want.values[j, it]
             err = float((v_got - v_want).abs().max())
             n["max_value_err"] = max(n["max_value_err"], err)
-            assert err < value_tol, f"values env={e} it={it} err={err:.3e}"
+            assert torch.allclose(v_got, v_want, atol=value_atol, rtol=value_rtol), f"values env={e} it={it} err={err:.3e}"
             n["values"] += v_want.numel()
-            stable = stable_positions(v_want, K, gap)
+            gap_it = gap if gap is not None else max(1e-4, 2 * (value_atol + value_rtol * float(v_want.abs().max())))
+            stable = stable_positions(v_want, K, gap_it)
             assert torch.equal(tr["elite_idx"][e, it].cpu()[stable], want.elite_idx[j, it][stable]), f"top-k env={e} it={it}"
             n["topk"] += int(stable.sum())
-            if not bool(boundary_separated(v_want, K, gap)):
+            if not bool(boundary_separated(v_want, K, gap_it)):
                 clean = False
                 break
             assert torch.allclose(tr["iter_mean"][e, it].cpu(), want.iter_mean[j, it], atol=1e-4, rtol=0), f"mean env={e} it={it}"

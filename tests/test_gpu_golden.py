@@ -12,10 +12,10 @@ CASES = ["tiny", "tiny_mt", "c1_dog5m", "c3_humanoid48m_e1", "c4_mt80_317m_e1", 
 # A termination decision flips a trajectory value by O(1): samples whose termination logit lies within this margin
 # of the 0.5 boundary (by the oracle, which is bit-identical to the reference) are not compared.
 TERM_MARGIN = 2e-5
-# Absolute tolerance on O(1) trajectory values.  The 3-pass fp16-split GEMM carries ~22 bits per product, but the
-# tensor core's fp32 accumulator truncates on every K=16 step, so the error grows with the reduction length:
-# K <= 1792 (5M/48M presets): observed <= 1e-5; K = 4096 (317M): observed 1.1e-4.
-VALUE_TOL = {"c4_mt80_317m_e1": 3e-4}
+# Trajectory values: |got - golden| <= 5e-5 + 1e-5 |golden| for EVERY preset (the 317M preset's values reach ~17).  The
+# 3-pass fp16-split GEMM carries ~22 bits per product; the tensor core's toward-zero accumulate drift over long
+# reductions (K = 4096) is bounded by handing partial sums off every 512 / 1024 elements of K (see test_gpu_multitrip).
+VALUE_ATOL, VALUE_RTOL = 5e-5, 1e-5
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -53,9 +53,10 @@ def test_agent_matches_reference_golden(name):
         for it in range(cfg.iterations):
             if not clean:
                 break
-            tol = VALUE_TOL.get(name, 5e-5)
+            tol = VALUE_ATOL + VALUE_RTOL * float(c["values"][it].abs().max())
             err = (values[it] - c["values"][it]).abs()[decided[it]].max().item()
-            assert err < tol, f"{name}: values it={it} err={err:.3e}"
+            assert torch.allclose(values[it][decided[it]], c["values"][it][decided[it]], atol=VALUE_ATOL, rtol=VALUE_RTOL), \
+                f"{name}: values it={it} err={err:.3e}"
             if not bool(decided[it].all()):
                 clean = False                    # a knife-edge termination may have moved one sample across the elite set
                 continue

@@ -120,12 +120,12 @@ def test_c5_planner_shape_on_5m_model():
     print(f"[c5-shape] {n}")
 
 
-# Value tolerance of the wide presets.  K <= 1792 (48M): 5e-5 like every other test.  K = 4096 (317M): the tensor
-# core's fp32 accumulator loses low bits on every K=16 step, observed 1.1e-4 on O(1) values -> 3e-4 here; the
-# north-star quantities (refit mean/std, final action: 1e-4; top-k indices exact where separated by > 2*tol) keep
-# their tolerances and the test FAILS if none of them was actually compared.
-@pytest.mark.parametrize("wl,value_tol", [("c3", 5e-5), ("c4", 3e-4)])
-def test_wide_presets_multi_env(wl, value_tol):
+# The wide presets keep the tolerance of every other parity test (values: 5e-5 + 1e-5 |v|; their values reach 8 / 17).
+# What makes that possible on tensor cores: tcgen05's fp32 accumulate step rounds toward zero, a drift that grows with
+# the reduction length (K = 1792 / 4096 here); the heads' and the wide layers' partial sums are therefore handed off
+# every 512 / 1024 elements of K and added with round-to-nearest (planner.DEFAULT_KSEG, tdmpc2_planner_set_head_kseg).
+@pytest.mark.parametrize("wl", ["c3", "c4"])
+def test_wide_presets_multi_env(wl):
     """humanoid-walk 48M (M=1792) and mt80 317M (M=4096, multi-task) at E=3: 12 tiles on the wide-layer path, one
     environment checked against the oracle (the oracle needs 0.6 / 2.2 TFLOP per environment on the host)."""
     from oracle.plan_oracle import plan_oracle
@@ -142,7 +142,7 @@ def test_wide_presets_multi_env(wl, value_tol):
     sel = torch.tensor(oracle_envs)
     want = plan_oracle(cfg, sd, obs[sel], task=None if task is None else [int(task[e]) for e in oracle_envs],
                        t0=[bool(t0[e]) for e in oracle_envs], prev_mean=prev[sel], noise=on)
-    n = compare_with_oracle(cfg, tr, a, m, want, on, oracle_envs, value_tol=value_tol)
+    n = compare_with_oracle(cfg, tr, a, m, want, on, oracle_envs)
     assert n["topk"] > 0 and n["refit"] > 0, f"{wl}: nothing beyond the values was compared: {n}"
     print(f"[{wl} E=3] {n}")
     if cfg.multitask:
