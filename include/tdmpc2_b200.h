@@ -141,7 +141,7 @@ int tdmpc2_planner_set_l2_persist(tdmpc2_planner* p, int enable);
 /* Accuracy knob of layers wider than 512 outputs (48M / 317M presets).  The tensor core's fp32 accumulator rounds toward
  * zero on every K = 16 step, so its error grows with the reduction length K; with k_elems > 0 the partial sums are
  * flushed to fp32 every k_elems elements of K and added with round-to-nearest (one extra accumulator drain per
- * segment).  0 = whole K in one accumulation.  No reference counterpart. */
+ * segment).  Default 2048; 0 = whole K in one accumulation.  No reference counterpart. */
 int tdmpc2_planner_set_kseg(tdmpc2_planner* p, int k_elems);
 /* The same for the head layers (reward / Q / pi / termination outputs, which have no LayerNorm behind them to absorb
  * the accumulator's toward-zero drift): default 512, 0 = whole K in one accumulation. */

@@ -138,7 +138,7 @@ struct tdmpc2_planner {
   int64_t launches = 0;
   unsigned wide_sleep_ns = 0;
   int head_kseg = 8;                // heads: 512 elements of K per TMEM accumulation (the 5M preset's whole K)
-  int kseg = 0;                     // wide layers: K-chunks per TMEM accumulation segment (0 = whole K)
+  int kseg = 32;                    // wide layers: K-chunks per TMEM accumulation segment (2048 elements; 0 = whole K)
   size_t l2_window_bytes = 0;       // > 0: launches carry a persisting-L2 access-policy window over the activation scratch
   float l2_hit_ratio = 1.f;
   bool pair_ok = true;              // every layer of the CEM iteration can run as cta_group::2
