@@ -35,7 +35,8 @@
 extern "C" {
 #endif
 
-#define TDMPC2_B200_ABI_VERSION 3   /* 2: tdmpc2_weights.termination, dims.episodic = 1 accepted; 3: tdmpc2_planner_set_l2_persist */
+#define TDMPC2_B200_ABI_VERSION 4   /* 2: tdmpc2_weights.termination, dims.episodic = 1 accepted; 3: tdmpc2_planner_set_l2_persist;
+                                       4: tdmpc2_planner_set_passes (declared non-parity fast mode) */
 #define TDMPC2_MAX_ENC_LAYERS 8
 
 typedef enum tdmpc2_status {
@@ -146,6 +147,12 @@ int tdmpc2_planner_set_kseg(tdmpc2_planner* p, int k_elems);
 /* The same for the head layers (reward / Q / pi / termination outputs, which have no LayerNorm behind them to absorb
  * the accumulator's toward-zero drift): default 512, 0 = whole K in one accumulation. */
 int tdmpc2_planner_set_head_kseg(tdmpc2_planner* p, int k_elems);
+/* Arithmetic of the tcgen05 engines 0 / 2 / 4.  passes = 3 (default): every product is three fp16 MMAs over the hi / lo
+ * operand planes -- the mode whose results match the reference's fp32 plan() (tdmpc2.py:138-206) within 1e-4.
+ * passes = 1: DECLARED NON-PARITY fast mode -- hi planes only (one fp16 MMA per product, fp32 accumulate; ~1e-3
+ * value error, elite sets differ from the reference's): for throughput studies, never the headline number.
+ * Engines 1 (SIMT) and 3 (ping-pong) ignore it. */
+int tdmpc2_planner_set_passes(tdmpc2_planner* p, int passes);
 /* Replaces: agent.load()/WorldModel.to(device) weight placement (tdmpc2.py:81-95).
  * Packs the state-dict tensors into the kernel layout: per Linear two fp16
  * planes (hi, lo) of weight * 2^k, K-major, zero-padded; applies the

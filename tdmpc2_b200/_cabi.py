@@ -11,13 +11,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TDMPC2_B200_LIB") or os.path.join(HERE, "libtdmpc2_b200.so")
 MAX_ENC_LAYERS = 8
 ENGINE_TCGEN05, ENGINE_SIMT, ENGINE_TCGEN05_2SM, ENGINE_TCGEN05_PP, ENGINE_TCGEN05_2SM_PF = 0, 1, 2, 3, 4
-ABI_VERSION = 3            # TDMPC2_B200_ABI_VERSION of include/tdmpc2_b200.h this binding was written against
+ABI_VERSION = 4            # TDMPC2_B200_ABI_VERSION of include/tdmpc2_b200.h this binding was written against
 
 # every symbol include/tdmpc2_b200.h declares
 SYMBOLS = [
     "tdmpc2_abi_version", "tdmpc2_last_error", "tdmpc2_planner_create", "tdmpc2_planner_destroy",
     "tdmpc2_planner_packed_bytes", "tdmpc2_planner_workspace_bytes", "tdmpc2_planner_bind",
-    "tdmpc2_planner_set_engine", "tdmpc2_planner_set_l2_persist", "tdmpc2_planner_set_kseg", "tdmpc2_planner_set_head_kseg", "tdmpc2_pack_weights", "tdmpc2_plan_prologue", "tdmpc2_plan_iter",
+    "tdmpc2_planner_set_engine", "tdmpc2_planner_set_l2_persist", "tdmpc2_planner_set_kseg", "tdmpc2_planner_set_head_kseg", "tdmpc2_planner_set_passes", "tdmpc2_pack_weights", "tdmpc2_plan_prologue", "tdmpc2_plan_iter",
     "tdmpc2_plan_epilogue", "tdmpc2_plan_get_state", "tdmpc2_estimate_value", "tdmpc2_debug_layer",
     "tdmpc2_planner_layer_count", "tdmpc2_planner_launch_count", "tdmpc2_planner_set_profile",
 ]
@@ -77,6 +77,7 @@ def load():
     lib.tdmpc2_planner_set_l2_persist.argtypes = [vp, C.c_int]
     lib.tdmpc2_planner_set_kseg.argtypes = [vp, C.c_int]
     lib.tdmpc2_planner_set_head_kseg.argtypes = [vp, C.c_int]
+    lib.tdmpc2_planner_set_passes.argtypes = [vp, C.c_int]
     lib.tdmpc2_pack_weights.argtypes = [vp, C.POINTER(Weights), vp]
     lib.tdmpc2_plan_prologue.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.tdmpc2_plan_iter.argtypes = [vp, vp, vp, vp, vp, vp, vp]

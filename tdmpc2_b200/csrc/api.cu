@@ -128,7 +128,7 @@ struct tdmpc2_planner {
   size_t off_table = 0, off_absmax = 0, off_emb = 0, off_masks = 0, off_disc = 0, off_bins = 0, packed_bytes = 0;
   // workspace offsets
   size_t off_X = 0, off_H = 0, off_raw = 0, off_z = 0, off_pia = 0, off_mean = 0, off_std = 0, off_values = 0,
-         off_counter = 0, off_score = 0, off_eact = 0, off_eidx = 0, ws_bytes = 0;
+         off_counter = 0, off_score = 0, off_eact = 0, off_eidx = 0, off_zbias = 0, ws_bytes = 0;
   uint8_t* packed = nullptr;
   uint8_t* ws = nullptr;
   PlanParams base;
@@ -142,6 +142,8 @@ struct tdmpc2_planner {
   size_t l2_window_bytes = 0;       // > 0: launches carry a persisting-L2 access-policy window over the activation scratch
   float l2_hit_ratio = 1.f;
   bool pair_ok = true;              // every layer of the CEM iteration can run as cta_group::2
+  int passes = 3;                   // 3 = fp32-parity arithmetic, 1 = declared non-parity fast mode (PlanParams::passes)
+  int zb_kc0 = 0, zb_pitch = 0;     // shared-latent fold (PlanParams::zbias): K-chunks of [z | emb] folded into a per-env bias
   const int32_t* cur_task = nullptr;
   long long* prof = nullptr;
 };
@@ -288,6 +290,10 @@ extern "C" int tdmpc2_planner_create(const tdmpc2_dims* dims, tdmpc2_planner** o
   p->off_score = off; off = align_up(off + E * K * 4, 256);
   p->off_eact = off; off = align_up(off + E * K * A * 4, 256);
   p->off_eidx = off; off = align_up(off + E * K * 4, 256);
+  // shared-latent fold: whole 64-column chunks of [z | emb] (TDMPC2_B200_ZFOLD=0 turns it off: A/B knob)
+  p->zb_pitch = p->layers[p->li_rew].Npad;
+  p->zb_kc0 = env_uint("TDMPC2_B200_ZFOLD", 1) ? (L + T) / kKch : 0;
+  p->off_zbias = off; off = align_up(off + 2 * E * static_cast<size_t>(p->zb_pitch) * 4, 256);
   p->ws_bytes = align_up(off, 1024);
   *out = p;
   return 0;
@@ -332,6 +338,12 @@ extern "C" int tdmpc2_planner_set_kseg(tdmpc2_planner* p, int k_elems) {
 extern "C" int tdmpc2_planner_set_head_kseg(tdmpc2_planner* p, int k_elems) {
   if (!p || k_elems < 0) return fail(TDMPC2_ERR_INVALID, "bad head kseg");
   p->head_kseg = (k_elems + kKch - 1) / kKch;
+  return 0;
+}
+
+extern "C" int tdmpc2_planner_set_passes(tdmpc2_planner* p, int passes) {
+  if (!p || (passes != 1 && passes != 3)) return fail(TDMPC2_ERR_INVALID, "passes must be 3 (fp32 parity) or 1 (non-parity fast mode)");
+  p->passes = passes;
   return 0;
 }
 
@@ -424,6 +436,8 @@ extern "C" int tdmpc2_planner_bind(tdmpc2_planner* p, void* packed, void* worksp
   B.score = reinterpret_cast<float*>(p->ws + p->off_score);
   B.elite_act0 = reinterpret_cast<float*>(p->ws + p->off_eact);
   B.elite_idx32 = reinterpret_cast<int*>(p->ws + p->off_eidx);
+  B.zbias = reinterpret_cast<const float*>(p->ws + p->off_zbias);
+  B.zb_kc0 = 0; B.zb_pitch = p->zb_pitch;       // zb_kc0 is set on the CEM-iteration launches only
   p->bound = true;
   p->weights_ok = false;
   return 0;
@@ -555,6 +569,7 @@ static int launch_plan(tdmpc2_planner* p, const PlanParams& prm, int ntiles, cud
   prm2.kseg = p->kseg;
   prm2.head_kseg = p->head_kseg;
   prm2.wide_sleep_ns = p->wide_sleep_ns;
+  prm2.passes = p->passes;
   static_assert(sizeof(p->attr_done) / sizeof(bool) >= 16, "attr_done slots");
   // CTA-pair (cta_group::2) launch: CEM iterations only, whole pairs of tiles of one environment
   const bool pair_engine = (p->engine == TDMPC2_ENGINE_TCGEN05_2SM || p->engine == TDMPC2_ENGINE_TCGEN05_PP ||
@@ -659,6 +674,15 @@ extern "C" int tdmpc2_plan_prologue(tdmpc2_planner* p, const float* obs, const i
   prm.mode = MODE_ENCODE;
   prm.ntiles = (d.num_envs + kTileM - 1) / kTileM;
   if ((rc = launch_plan(p, prm, prm.ntiles, st))) return rc;
+  if (p->zb_kc0 > 0) {
+    // shared-latent fold: [z | emb] . W of reward.0 / dynamics.0, once per plan() (z is the same in every CEM iteration)
+    const dim3 grid((p->zb_pitch + kZbCols - 1) / kZbCols, (d.num_envs + kZbEnvs - 1) / kZbEnvs, 2);
+    zbias_kernel<<<grid, 256, 0, st>>>(p->base.layers, p->li_rew, p->li_dyn, p->base.z, p->base.emb, p->cur_task, d.num_envs,
+                                       d.latent_dim, d.task_dim, p->zb_kc0 * kKch, reinterpret_cast<float*>(p->ws + p->off_zbias),
+                                       p->zb_pitch);
+    CUDA_TRY(cudaGetLastError());
+    p->launches += 1;
+  }
   if (d.num_pi_trajs > 0) {
     prm.mode = MODE_PRIOR;
     prm.noise_prior = noise_prior;
@@ -682,6 +706,7 @@ extern "C" int tdmpc2_plan_iter(tdmpc2_planner* p, const float* noise_r, const f
   prm.values_out = values_out;
   prm.elite_idx_out = reinterpret_cast<long long*>(elite_idx_out);
   prm.ntiles = d.num_envs * p->tiles_per_env;
+  prm.zb_kc0 = p->zb_kc0;
   return launch_plan(p, prm, prm.ntiles, static_cast<cudaStream_t>(stream_));
 }
 

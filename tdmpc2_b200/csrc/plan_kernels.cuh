@@ -133,6 +133,16 @@ struct PlanParams {
   unsigned wide_sleep_ns;   // wide layers: nanosleep between polls of the 16 epilogue warps' accumulator wait (0 = spin)
   int kseg;          // wide layers: K-chunks (of 64) accumulated in TMEM before the partial sum is flushed to the fp32 raw
                      // scratch and added there with round-to-nearest (0 = the whole K in one go); see epi_wide
+  // Shared-latent fold (MODE_ITER, rollout step t = 0): every sample row of an environment carries the SAME [z | emb]
+  // (z.repeat(N), tdmpc2.py:163), so the [z | emb] part of reward.0 / dynamics.0 is a per-environment vector.  The
+  // prologue computes zbias[mlp][e][n] = bias[n] + sum_{k < 64 zb_kc0} [z | emb]_e[k] W[n][k] once per plan()
+  // (zbias_kernel) and the t = 0 GEMMs of those two layers start at K-chunk zb_kc0 (the action columns) with that
+  // vector as their bias.  zb_kc0 == 0: fold off.
+  const float* zbias;   // [2 (0 reward, 1 dynamics)][E][zb_pitch]
+  int zb_kc0, zb_pitch;
+  // 3 = fp32-parity arithmetic (A_lo W_hi + A_hi W_lo + A_hi W_hi); 1 = the DECLARED NON-PARITY fast mode: hi planes only
+  // (one fp16 MMA per product, fp32 accumulate), half the operand bytes, no lo planes written.  tdmpc2_planner_set_passes.
+  int passes;
 };
 
 // The layer table lives in global memory; role loops are full of asm volatile(... "memory") (TMA issue, mbarrier waits,
@@ -369,19 +379,20 @@ __device__ __forceinline__ void prod_load_a(const PlanParams& P, Ctx& c, const C
   ptx::mbar_wait(&c.a_empty[s], ph ^ 1);
   c.pf0 += prof_clock() - tw;
   uint8_t* st = c.stage_base + s * kASlotBytes;
+  const bool lo = P.passes != 1;                 // fast mode streams the hi planes only
   if (c.cg2) {
     // both CTAs of the pair stream their own 128 rows; the bytes of both land on the leader's barrier
-    if (c.rank == 0) ptx::mbar_expect_tx(&c.a_full[s], 2 * kASlotBytes);
+    if (c.rank == 0) ptx::mbar_expect_tx(&c.a_full[s], lo ? 2 * kASlotBytes : 2 * kAPlane);
     ptx::tma_load_2d_2sm(tmA, &c.a_full[s], st, kc * kKch, arow_hi);
-    ptx::tma_load_2d_2sm(tmA, &c.a_full[s], st + kAPlane, kc * kKch, arow_lo);
+    if (lo) ptx::tma_load_2d_2sm(tmA, &c.a_full[s], st + kAPlane, kc * kKch, arow_lo);
   } else {
-    ptx::mbar_expect_tx(&c.a_full[s], kASlotBytes);
+    ptx::mbar_expect_tx(&c.a_full[s], lo ? kASlotBytes : kAPlane);
     ptx::tma_load_2d(tmA, &c.a_full[s], st, kc * kKch, arow_hi);
-    ptx::tma_load_2d(tmA, &c.a_full[s], st + kAPlane, kc * kKch, arow_lo);
+    if (lo) ptx::tma_load_2d(tmA, &c.a_full[s], st + kAPlane, kc * kKch, arow_lo);
   }
   ++c.pa_it;
 }
-__device__ __forceinline__ void prod_load_w(Ctx& c, const CUtensorMap* tmW, int Npad, int wrow, int kc, int nc) {
+__device__ __forceinline__ void prod_load_w(Ctx& c, const CUtensorMap* tmW, int Npad, int wrow, int kc, int nc, bool lo = true) {
   const int ncols = min(kNch, Npad - nc * kNch);   // 128 or 256
   const uint32_t s = c.pw_it % c.w_ring, ph = (c.pw_it / c.w_ring) & 1;
   const long long tw = prof_clock();
@@ -391,16 +402,16 @@ __device__ __forceinline__ void prod_load_w(Ctx& c, const CUtensorMap* tmW, int 
   if (c.cg2) {
     // each CTA streams HALF of the N-chunk's weight rows (one 128-row box per plane; for a 128-column chunk only
     // its first 64 rows are consumed): the pair MMA reads B rows [0, N/2) from the leader and [N/2, N) from the peer
-    if (c.rank == 0) ptx::mbar_expect_tx(&c.w_full[s], 2 * (2 * 128 * 128));
+    if (c.rank == 0) ptx::mbar_expect_tx(&c.w_full[s], (lo ? 2 : 1) * (2 * 128 * 128));
     const int wr = wrow + nc * kNch + c.rank * (ncols / 2);
     ptx::tma_load_2d_2sm(tmW, &c.w_full[s], st, kc * kKch, wr);
-    ptx::tma_load_2d_2sm(tmW, &c.w_full[s], st + c.w_lo_off, kc * kKch, wr + Npad);
+    if (lo) ptx::tma_load_2d_2sm(tmW, &c.w_full[s], st + c.w_lo_off, kc * kKch, wr + Npad);
   } else {
-    ptx::mbar_expect_tx(&c.w_full[s], 2 * ncols * 128);
+    ptx::mbar_expect_tx(&c.w_full[s], (lo ? 2 : 1) * ncols * 128);
     for (int b = 0; b < ncols / 128; ++b) {
       const int wr = wrow + nc * kNch + b * 128;
       ptx::tma_load_2d(tmW, &c.w_full[s], st + b * (128 * 128), kc * kKch, wr);
-      ptx::tma_load_2d(tmW, &c.w_full[s], st + kWPlane + b * (128 * 128), kc * kKch, wr + Npad);
+      if (lo) ptx::tma_load_2d(tmW, &c.w_full[s], st + kWPlane + b * (128 * 128), kc * kKch, wr + Npad);
     }
   }
   ++c.pw_it;
@@ -409,7 +420,7 @@ __device__ __forceinline__ void prod_load_w(Ctx& c, const CUtensorMap* tmW, int 
 // N-chunks [nc0, nc0 + nnc_lim) of the layer (default: all of them): K-chunks outermost, each A chunk is loaded once
 // and multiplied with every N-chunk of the range; layers wider than TMEM call this once per 512-column super-chunk.
 __device__ __forceinline__ void tc_producer(const PlanParams& P, Ctx& c, const LayerRec& ly, int srcbuf, const LayerDev* next,
-                                            int nc0 = 0, int nnc_lim = 1 << 30, int kc0 = 0, int kc_lim = 1 << 30) {
+                                            int nc0 = 0, int nnc_lim = 1 << 30, int kc0 = 0, int kc_lim = 1 << 30, int next_kc0 = 0) {
   const int nkc = min(ly.Kpad / kKch, kc0 + kc_lim);
   const int nnc = min((ly.Npad + kNch - 1) / kNch - nc0, nnc_lim);
   const CUtensorMap* tmA = (srcbuf == BUF_X) ? &P.tmX : &P.tmH;
@@ -421,7 +432,7 @@ __device__ __forceinline__ void tc_producer(const PlanParams& P, Ctx& c, const L
     prod_load_a(P, c, tmA, kc, arow_hi, arow_lo);
     for (int nc = nc0; nc < nc0 + nnc; ++nc) {
       if (skip) --skip;
-      else prod_load_w(c, tmW, ly.Npad, ly.wrow, kc, nc);
+      else prod_load_w(c, tmW, ly.Npad, ly.wrow, kc, nc, P.passes != 1);
     }
   }
   if (c.wpf) {
@@ -431,15 +442,26 @@ __device__ __forceinline__ void tc_producer(const PlanParams& P, Ctx& c, const L
     if (next) {
       const CUtensorMap* tmW2 = &P.tmW[next->wmap];
       const int nkc2 = next->Kpad / kKch, nnc2 = (next->Npad + kNch - 1) / kNch;
-      for (int kc = 0; kc < nkc2 && n < c.w_ring; ++kc)
-        for (int nc = 0; nc < nnc2 && n < c.w_ring; ++nc) { prod_load_w(c, tmW2, next->Npad, next->wrow, kc, nc); ++n; }
+      for (int kc = next_kc0; kc < nkc2 && n < c.w_ring; ++kc)      // next_kc0: the next layer's first K-chunk (shared-latent fold)
+        for (int nc = 0; nc < nnc2 && n < c.w_ring; ++nc) { prod_load_w(c, tmW2, next->Npad, next->wrow, kc, nc, P.passes != 1); ++n; }
     }
     c.w_pref = n;
   }
 }
 
 // 12 MMAs of one (A K-chunk, W K-chunk x N-chunk) pair: A_lo*W_hi + A_hi*W_lo + A_hi*W_hi, 4 K-steps of 16.
-__device__ __forceinline__ void mma_stage(uint32_t d, uint32_t sa, uint32_t sw, uint32_t w_lo_off, uint32_t idesc, bool first, bool cg2) {
+__device__ __forceinline__ void mma_stage(uint32_t d, uint32_t sa, uint32_t sw, uint32_t w_lo_off, uint32_t idesc, bool first, bool cg2,
+                                          bool one_pass = false) {
+  if (one_pass) {                                   // declared non-parity fast mode: A_hi * W_hi only
+#pragma unroll
+    for (int ks = 0; ks < kKch / 16; ++ks) {
+      const uint64_t a_hi = ptx::make_sw128_kmajor_desc(sa + ks * 32);
+      const uint64_t w_hi = ptx::make_sw128_kmajor_desc(sw + ks * 32);
+      if (cg2) ptx::umma_f16_2sm(d, a_hi, w_hi, idesc, !(first && ks == 0));
+      else ptx::umma_f16(d, a_hi, w_hi, idesc, !(first && ks == 0));
+    }
+    return;
+  }
 #pragma unroll
   for (int ks = 0; ks < kKch / 16; ++ks) {
     const uint64_t a_hi = ptx::make_sw128_kmajor_desc(sa + ks * 32);
@@ -487,7 +509,7 @@ __device__ __forceinline__ void tc_mma(const PlanParams& P, Ctx& c, const LayerR
       ptx::tc_fence_after();
       const int ncols = min(kNch, ly.Npad - nc * kNch);
       mma_stage(c.tmem_base + (nc - nc0) * kNch, sbase + as * kASlotBytes, sbase + kWRingOff + ws * c.w_stride, c.w_lo_off,
-                ptx::make_idesc_f16(c.cg2 ? 2 * kTileM : kTileM, ncols), kc == kc0, c.cg2 != 0);
+                ptx::make_idesc_f16(c.cg2 ? 2 * kTileM : kTileM, ncols), kc == kc0, c.cg2 != 0, P.passes == 1);
       if (c.cg2) ptx::umma_commit_2sm(&c.w_empty[ws]);
       else ptx::umma_commit(&c.w_empty[ws]);     // frees the W slot when these MMAs retire
       ++c.mw_it;
@@ -528,7 +550,7 @@ __device__ __forceinline__ void tc_mma_head_seg(const PlanParams& P, Ctx& c, con
       const uint32_t ws = mma_wait_w(c);
       ptx::tc_fence_after();
       mma_stage(c.tmem_base + b * kNch, sbase + as * kASlotBytes, sbase + kWRingOff + ws * c.w_stride, c.w_lo_off, idesc,
-                kc == kc0, c.cg2 != 0);
+                kc == kc0, c.cg2 != 0, P.passes == 1);
       if (c.cg2) { ptx::umma_commit_2sm(&c.w_empty[ws]); ptx::umma_commit_2sm(&c.a_empty[as]); }
       else { ptx::umma_commit(&c.w_empty[ws]); ptx::umma_commit(&c.a_empty[as]); }
       ++c.mw_it; ++c.ma_it;
@@ -540,7 +562,7 @@ __device__ __forceinline__ void tc_mma_head_seg(const PlanParams& P, Ctx& c, con
 
 // ------------------------------------------------------------------------------------ SIMT engine: GEMM -> raw scratch
 // Same operands, plain fp32 FFMA on CUDA cores (exact products of the split operands).
-__device__ __forceinline__ void gemm_simt(const PlanParams& P, Ctx& c, const LayerRec& ly, int srcbuf) {
+__device__ __forceinline__ void gemm_simt(const PlanParams& P, Ctx& c, const LayerRec& ly, int srcbuf, int kc0 = 0) {
   constexpr int BN = 64, BK = 32;
   float* sA = reinterpret_cast<float*>(c.stage_base);          // [BK][128+4]
   float* sW = sA + BK * (kTileM + 4);                          // [BK][BN+4]
@@ -556,7 +578,7 @@ __device__ __forceinline__ void gemm_simt(const PlanParams& P, Ctx& c, const Lay
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k0 = 0; k0 < ly.Kpad; k0 += BK) {
+    for (int k0 = kc0 * kKch; k0 < ly.Kpad; k0 += BK) {
       for (int i = tid; i < kTileM * BK; i += kThreads) {
         const int r = i / BK, k = i % BK;
         const size_t o = static_cast<size_t>(r) * pitch + k0 + k;
@@ -769,7 +791,7 @@ __device__ __forceinline__ float mish_fast(float x) {
 // Pass 2 of the fused LayerNorm epilogue, specialised for the common case (whole 32-column blocks, planes out
 // through TMA stores, no fp32 side output): one block = two x16 TMEM loads, packed fp32x2 math, four 16-byte
 // swizzled smem stores per plane, then the block is handed to the TMA unit.
-template <int KIND>
+template <int KIND, bool FAST = false>   // FAST: single-pass mode (PlanParams::passes == 1), the lo plane is neither computed nor stored
 __device__ __forceinline__ void epi_pass2_fast(const PlanParams& P, Ctx& c, const EpiThread& et, const EpiArgs& ea, int cb,
                                                int nvalid, float inv_scale, float rstd, float nmr) {
   const float* sb = c.vec; const float* sg = c.vec + kFusedMaxN; const float* sbe = c.vec + 2 * kFusedMaxN;
@@ -831,11 +853,13 @@ __device__ __forceinline__ void epi_pass2_fast(const PlanParams& P, Ctx& c, cons
       for (int i = 0; i < 8; ++i) {
         const float a0 = __uint_as_float(v[2 * i]), a1 = __uint_as_float(v[2 * i + 1]);
         const __half2 h2 = __floats2half2_rn(a0, a1);
-        const float2 hf = __half22float2(h2);
-        const float2 df = __fadd2_rn(f2(a0, a1), f2(-hf.x, -hf.y));
-        const __half2 l2 = __floats2half2_rn(df.x, df.y);
         hw[i] = *reinterpret_cast<const uint32_t*>(&h2);
-        lw[i] = *reinterpret_cast<const uint32_t*>(&l2);
+        if (!FAST) {
+          const float2 hf = __half22float2(h2);
+          const float2 df = __fadd2_rn(f2(a0, a1), f2(-hf.x, -hf.y));
+          const __half2 l2 = __floats2half2_rn(df.x, df.y);
+          lw[i] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
       }
       if (c.wpf && sub == 0 && blk >= 1) {
         // single staging tile: the previous block's store was issued a whole block of math ago, so this wait is short
@@ -846,14 +870,14 @@ __device__ __forceinline__ void epi_pass2_fast(const PlanParams& P, Ctx& c, cons
       for (int i = 0; i < 2; ++i) {
         const uint32_t off = ((static_cast<uint32_t>((sub >> 3) + i) ^ swz) << 4);
         ptx::st_shared_v4(rowaddr + off, hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
-        ptx::st_shared_v4(rowaddr + kStgPlane + off, lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]);
+        if (!FAST) ptx::st_shared_v4(rowaddr + kStgPlane + off, lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]);
       }
     }
     ptx::fence_proxy_async_smem();
     group_bar_sync(et.grp);
     if (leader) {
       ptx::tma_store_2d(tmD, buf, ea.dst_col0 + c0, row_hi);
-      ptx::tma_store_2d(tmD, buf + kStgPlane, ea.dst_col0 + c0, row_lo);
+      if (!FAST) ptx::tma_store_2d(tmD, buf + kStgPlane, ea.dst_col0 + c0, row_lo);
       ptx::bulk_commit();
     }
   }
@@ -965,8 +989,13 @@ __device__ __forceinline__ void epi_ln_fused(const PlanParams& P, Ctx& c, const 
   }
   const float nmr = -mean * rstd;
   if (ea.dstbuf >= 0 && !ea.out_f32 && (N % 32 == 0) && (ea.dst_col0 % 32 == 0)) {
-    if (ea.kind == EPI_LN_MISH) epi_pass2_fast<EPI_LN_MISH>(P, c, et, ea, cb, nvalid, inv_scale, rstd, nmr);
-    else epi_pass2_fast<EPI_LN_SIMNORM>(P, c, et, ea, cb, nvalid, inv_scale, rstd, nmr);
+    if (P.passes == 1) {
+      if (ea.kind == EPI_LN_MISH) epi_pass2_fast<EPI_LN_MISH, true>(P, c, et, ea, cb, nvalid, inv_scale, rstd, nmr);
+      else epi_pass2_fast<EPI_LN_SIMNORM, true>(P, c, et, ea, cb, nvalid, inv_scale, rstd, nmr);
+    } else {
+      if (ea.kind == EPI_LN_MISH) epi_pass2_fast<EPI_LN_MISH>(P, c, et, ea, cb, nvalid, inv_scale, rstd, nmr);
+      else epi_pass2_fast<EPI_LN_SIMNORM>(P, c, et, ea, cb, nvalid, inv_scale, rstd, nmr);
+    }
     return;
   }
   // ---- pass 2 (general path): normalise, activate, emit
@@ -1623,16 +1652,16 @@ __device__ __forceinline__ void epi_wide(const PlanParams& P, Ctx& c, const Laye
 }
 
 // GEMM roles + epilogue of a wide layer; returns the number of accumulator hand-offs (= facc phases consumed).
-__device__ __forceinline__ int wide_layer_tc(const PlanParams& P, Ctx& c, const LayerRec& ly, int srcbuf, const EpiArgs& ea) {
+__device__ __forceinline__ int wide_layer_tc(const PlanParams& P, Ctx& c, const LayerRec& ly, int srcbuf, const EpiArgs& ea, int kc_begin) {
   const int nnc_all = (ly.Npad + kNch - 1) / kNch;
   const int nsc = (nnc_all + 1) / 2;
-  const int nkc = ly.Kpad / kKch;
+  const int nkc = ly.Kpad / kKch - kc_begin;          // K-chunks [kc_begin, Kpad / 64): see PlanParams::zbias
   const int kseg = (P.kseg > 0 && P.kseg < nkc) ? P.kseg : nkc;
   const int nseg = (nkc + kseg - 1) / kseg;
   if (c.warp == 0) {
     if (c.lane == 0)
       for (int sc = 0; sc < nsc; ++sc)
-        for (int seg = 0; seg < nseg; ++seg) tc_producer(P, c, ly, srcbuf, nullptr, 2 * sc, 2, seg * kseg, kseg);
+        for (int seg = 0; seg < nseg; ++seg) tc_producer(P, c, ly, srcbuf, nullptr, 2 * sc, 2, kc_begin + seg * kseg, kseg);
   } else if (c.warp == 1) {
     if (c.lane == 0 && (!c.cg2 || c.rank == 0))
       for (int sc = 0; sc < nsc; ++sc)
@@ -1644,7 +1673,7 @@ __device__ __forceinline__ int wide_layer_tc(const PlanParams& P, Ctx& c, const 
             ++c.a_it;
             ptx::tc_fence_after();
           }
-          tc_mma(P, c, ly, 2 * sc, 2, seg * kseg, kseg);
+          tc_mma(P, c, ly, 2 * sc, 2, kc_begin + seg * kseg, kseg);
         }
   } else if (c.warp >= kEpiWarp0) {
     epi_wide(P, c, ly, ea, nsc, nseg);
@@ -1665,8 +1694,9 @@ __device__ __forceinline__ void publish_planes() {
 // GEMM + epilogue; on return the epilogue's outputs are published (CTA-synchronised, TMA-visible).
 template <int ENGINE, bool EPISODIC, bool WIDE>
 __device__ __forceinline__ void run_layer(const PlanParams& P, Ctx& c, const LayerDev& ly_global, int srcbuf, const EpiArgs& ea,
-                                          const LayerDev* next) {
-  const LayerRec ly = layer_rec(ly_global);          // registers: see LayerRec
+                                          const LayerDev* next, int kc0 = 0, const float* bias_override = nullptr, int next_kc0 = 0) {
+  LayerRec ly = layer_rec(ly_global);                // registers: see LayerRec
+  if (bias_override) ly.bias = bias_override;        // shared-latent fold: see PlanParams::zbias
   const bool is_ln = (ea.kind == EPI_LN_MISH || ea.kind == EPI_LN_SIMNORM);
   const bool fused = (ENGINE == ENGINE_TC) && (ly.Npad <= kFusedMaxN) && (is_ln || ly.Npad <= kNch) &&
                      (ea.kind != EPI_RAW || ly.Npad <= kNch);
@@ -1675,11 +1705,11 @@ __device__ __forceinline__ void run_layer(const PlanParams& P, Ctx& c, const Lay
     if (threadIdx.x == 0) TDMPC2_TRACE(P, c, 0);
     const int hseg = (WIDE && !is_ln && head_seg_ok(P, ea.kind)) ? head_segments(P, ly) : 1;   // K <= 512 unless the model is wide
     if (c.warp == 0) {
-      if (c.lane == 0) tc_producer(P, c, ly, srcbuf, next);
+      if (c.lane == 0) tc_producer(P, c, ly, srcbuf, next, 0, 1 << 30, kc0, 1 << 30, next_kc0);
     } else if (c.warp == 1) {
       if (c.lane == 0 && (!c.cg2 || c.rank == 0)) {
         if (hseg > 1) tc_mma_head_seg(P, c, ly, hseg);
-        else tc_mma(P, c, ly);
+        else tc_mma(P, c, ly, 0, 1 << 30, kc0);
       }
     } else if (c.warp >= kEpiWarp0) {
       if (is_ln) epi_ln_fused(P, c, ly, ea);
@@ -1694,11 +1724,11 @@ __device__ __forceinline__ void run_layer(const PlanParams& P, Ctx& c, const Lay
     // LayerNorm layers (and the diagnostic raw mode) wider than TMEM; heads are never wider than one N-chunk
     const long long tl = prof_clock();
     if (threadIdx.x == 0) TDMPC2_TRACE(P, c, 0);
-    const int nph = wide_layer_tc(P, c, ly, srcbuf, ea);
+    const int nph = wide_layer_tc(P, c, ly, srcbuf, ea, kc0);
     c.pf1 += prof_clock() - tl;
     c.fph0 ^= static_cast<uint32_t>(nph & 1);         // one facc phase per (super-chunk, K-segment)
   } else if (ENGINE == ENGINE_SIMT) {
-    gemm_simt(P, c, ly, srcbuf);
+    gemm_simt(P, c, ly, srcbuf, kc0);
     if (is_ln) rows_ln_act(P, c, ly, ea);
     else rows_head<EPISODIC>(P, c, ly, ea);
   }                                                   // (a tcgen05 kernel without WIDE is never launched on a model with wide layers)
@@ -1983,6 +2013,20 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
         split_store(xhi + static_cast<size_t>(r) * P.KpadX + col, xlo + static_cast<size_t>(r) * P.KpadX + col, x);
       }
     }
+    if (P.mode == MODE_ITER && !P.actions_explicit && threadIdx.x <= P.H) {
+      // This tile's slabs of the (HBM-resident, read-once) noise tensors are contiguous: ask for them now, so that the
+      // per-step action pass and the terminal policy sample find them in L2 instead of paying DRAM latency.
+      const int n0 = (tile % P.tiles_per_env) * kTileM, n1 = min(n0 + kTileM, P.N);
+      const int t = threadIdx.x;
+      if (t < P.H) {
+        const int r0 = max(n0, P.P) - P.P, r1 = n1 - P.P;
+        if (r1 > r0)
+          ptx::bulk_prefetch_l2(P.noise_r + ((static_cast<size_t>(env_tile) * P.H + t) * (P.N - P.P) + r0) * P.A,
+                                static_cast<size_t>(r1 - r0) * P.A * sizeof(float));
+      } else {
+        ptx::bulk_prefetch_l2(P.noise_pi + (static_cast<size_t>(env_tile) * P.N + n0) * P.A, static_cast<size_t>(n1 - n0) * P.A * sizeof(float));
+      }
+    }
     publish_planes();
     c.pf4 += prof_clock() - t_setup;
 
@@ -2003,6 +2047,8 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
       ea.kind = EPI_LN_MISH; ea.dstbuf = -1; ea.dst_col0 = 0; ea.out_f32 = nullptr; ea.out_pitch = 0; ea.rowmap = nullptr;
       ea.head = 0; ea.disc = 0.f; ea.tile = tile; ea.eps_base = nullptr; ea.eps_rows = 0; ea.act_out = nullptr; ea.t_out = 0;
       int li, src;
+      int kc0 = 0;                       // first K-chunk of the GEMM and bias vector: the shared-latent fold (PlanParams::zbias)
+      const float* bias_ov = nullptr;
       if (P.mode == MODE_LAYER) {
         li = P.dbg_layer; src = BUF_X;
         ea.kind = P.dbg_mode == 0 ? EPI_RAW : (P.dbg_mode == 1 ? EPI_LN_MISH : EPI_LN_SIMNORM);
@@ -2044,19 +2090,52 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
               const int n0 = (tile % P.tiles_per_env) * kTileM;
               const float* nz = P.noise_r + (static_cast<size_t>(env_tile) * P.H + t) * (P.N - P.P) * P.A;
               const float* pa = P.pi_actions + (static_cast<size_t>(env_tile) * P.H + t) * P.P * P.A;
-#pragma unroll 4
-              for (int i = threadIdx.x; i < kTileM * P.A; i += kThreads) {
-                const int r = i / P.A, a = i % P.A;
-                const int n = min(n0 + r, P.N - 1);
-                float v;
-                if (n < P.P) v = pa[static_cast<size_t>(n) * P.A + a];
-                else {
-                  v = __fadd_rn(sm_mean[a], __fmul_rn(sm_std[a], __ldcs(&nz[static_cast<size_t>(n - P.P) * P.A + a])));   // one-shot: evict-first
-                  v = fminf(fmaxf(v, -1.f), 1.f);
+              const int ng = (P.A + 7) >> 3;
+              if ((((P.L + P.T) & 7) == 0) && (P.L + P.T + 8 * ng <= P.KpadX)) {
+                // one (row, 8 action columns) item per thread: every load of the pass is in flight at once, two 16-byte
+                // stores per item (columns past A are zero-weight padding of X: zeros there are harmless)
+                for (int i = threadIdx.x; i < kTileM * ng; i += kThreads) {
+                  const int r = i / ng, g8 = (i % ng) * 8;
+                  const int n = min(n0 + r, P.N - 1);
+                  const float* src = (n < P.P) ? pa + static_cast<size_t>(n) * P.A : nz + static_cast<size_t>(n - P.P) * P.A;
+                  float x[8];
+#pragma unroll
+                  for (int u = 0; u < 8; ++u)                                  // noise is one-shot: evict-first
+                    x[u] = (g8 + u < P.A) ? (n < P.P ? src[g8 + u] : __ldcs(src + g8 + u)) : 0.f;
+                  uint32_t hw[4], lw[4];
+#pragma unroll
+                  for (int u = 0; u < 8; u += 2) {
+                    __half h[2], l[2];
+#pragma unroll
+                    for (int w = 0; w < 2; ++w) {
+                      const int a = min(g8 + u + w, P.A - 1);
+                      float v = x[u + w];
+                      if (n >= P.P) v = fminf(fmaxf(__fadd_rn(sm_mean[a], __fmul_rn(sm_std[a], v)), -1.f), 1.f);
+                      v = (g8 + u + w < P.A) ? v * sm_mask[a] : 0.f;
+                      split_f(v, h[w], l[w]);
+                    }
+                    hw[u >> 1] = static_cast<uint32_t>(__half_as_ushort(h[0])) | (static_cast<uint32_t>(__half_as_ushort(h[1])) << 16);
+                    lw[u >> 1] = static_cast<uint32_t>(__half_as_ushort(l[0])) | (static_cast<uint32_t>(__half_as_ushort(l[1])) << 16);
+                  }
+                  const size_t o = static_cast<size_t>(r) * P.KpadX + P.L + P.T + g8;
+                  __stcg(reinterpret_cast<uint4*>(xhi + o), make_uint4(hw[0], hw[1], hw[2], hw[3]));
+                  __stcg(reinterpret_cast<uint4*>(xlo + o), make_uint4(lw[0], lw[1], lw[2], lw[3]));
                 }
-                v *= sm_mask[a];
-                const size_t o = static_cast<size_t>(r) * P.KpadX + P.L + P.T + a;
-                split_store(xhi + o, xlo + o, v);
+              } else {
+#pragma unroll 4
+                for (int i = threadIdx.x; i < kTileM * P.A; i += kThreads) {
+                  const int r = i / P.A, a = i % P.A;
+                  const int n = min(n0 + r, P.N - 1);
+                  float v;
+                  if (n < P.P) v = pa[static_cast<size_t>(n) * P.A + a];
+                  else {
+                    v = __fadd_rn(sm_mean[a], __fmul_rn(sm_std[a], __ldcs(&nz[static_cast<size_t>(n - P.P) * P.A + a])));   // one-shot: evict-first
+                    v = fminf(fmaxf(v, -1.f), 1.f);
+                  }
+                  v *= sm_mask[a];
+                  const size_t o = static_cast<size_t>(r) * P.KpadX + P.L + P.T + a;
+                  split_store(xhi + o, xlo + o, v);
+                }
               }
             }
             publish_planes();
@@ -2070,6 +2149,12 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
         const int base = (EPISODIC && mlp == 5) ? P.li_term
                          : mlp == 0 ? P.li_rew : mlp == 1 ? P.li_dyn : mlp == 2 ? P.li_pi : P.li_q + 3 * qi[mlp - 3];
         li = base + l;
+        if (P.mode == MODE_ITER && P.zb_kc0 > 0 && sidx < SPT * P.H && t == 0 && l == 0 && mlp <= 1) {
+          // t = 0: the rows of the tile share [z | emb]; its product with reward.0 / dynamics.0 was folded into a
+          // per-environment bias by the prologue, the GEMM only covers the action columns
+          kc0 = P.zb_kc0;
+          bias_ov = P.zbias + (static_cast<size_t>(mlp) * P.E + env_tile) * P.zb_pitch;
+        }
         if (l < 2) {
           ea.kind = EPI_LN_MISH; ea.dstbuf = BUF_H1;
         } else if (mlp == 0) {                 // reward (world_model.py:123-130) + two_hot_inv
@@ -2092,6 +2177,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
       }
       c.trace_step = (tile == static_cast<int>(blockIdx.x)) ? sidx : (1 << 30);
       const LayerDev* next = nullptr;
+      int next_kc0 = 0;
       if (WPF && P.mode == MODE_ITER && sidx + 1 < nsteps) {
         // layer of the step after this one (same mapping as above, without its side effects); none after the
         // tile's last step: the refit and the next tile's set-up use the operand smem as scratch
@@ -2102,8 +2188,9 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
         const int base1 = (EPISODIC && mlp1 == 5) ? P.li_term
                           : mlp1 == 0 ? P.li_rew : mlp1 == 1 ? P.li_dyn : mlp1 == 2 ? P.li_pi : P.li_q + 3 * qi[mlp1 - 3];
         next = &LY[base1 + l1];
+        if (P.zb_kc0 > 0 && s1 < SPT && l1 == 0 && mlp1 <= 1) next_kc0 = P.zb_kc0;   // the step after this one is a folded t = 0 layer
       }
-      run_layer<ENGINE, EPISODIC, WIDE>(P, c, LY[li], src, ea, next);
+      run_layer<ENGINE, EPISODIC, WIDE>(P, c, LY[li], src, ea, next, kc0, bias_ov, next_kc0);
     }
 
     const long long t_refit = prof_clock();
@@ -2157,6 +2244,58 @@ __global__ void init_state_kernel(float* mean, float* std, unsigned* env_counter
   if (!t0[e] && t < H - 1) m = prev_mean[(static_cast<size_t>(e) * H + t + 1) * A + a];
   mean[i] = m;
   std[i] = max_std;
+}
+
+// Shared-latent fold (PlanParams::zbias): zbias[mlp][e][n] = bias[n] + 2^-k * sum_{k < Kz} x_e[k] * (W_hi + W_lo)[n][k], x_e = [z_e | emb_task(e)],
+// for mlp 0 = reward.0, 1 = dynamics.0 (world_model.py:114-130: both take [z | emb | a]).  fp32 FFMA over the packed
+// planes (whose sum is W * 2^k to ~22 bits, the operand the tensor-core path multiplies with).  Block = 4 environments
+// x 64 output columns; a warp owns 8 columns, its lanes stride over k (coalesced half2 loads of the K-major rows).
+constexpr int kZbEnvs = 4, kZbCols = 64, kZbKc = 1024;
+__global__ void __launch_bounds__(256) zbias_kernel(const LayerDev* __restrict__ layers, int li_rew, int li_dyn, const float* __restrict__ z,
+                                                    const float* __restrict__ emb, const int* __restrict__ task, int E, int L, int T,
+                                                    int Kz, float* __restrict__ out, int pitch) {
+  __shared__ float xs[kZbEnvs][kZbKc];
+  const int mlp = blockIdx.z;
+  const LayerDev& ly = layers[mlp == 0 ? li_rew : li_dyn];
+  const int e0 = blockIdx.y * kZbEnvs, n0 = blockIdx.x * kZbCols;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[8][kZbEnvs];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int i = 0; i < kZbEnvs; ++i) acc[j][i] = 0.f;
+  for (int kb = 0; kb < Kz; kb += kZbKc) {
+    const int kn = min(kZbKc, Kz - kb);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kZbEnvs * kn; i += blockDim.x) {
+      const int ei = i / kn, k = kb + i % kn, e = min(e0 + ei, E - 1);
+      xs[ei][i % kn] = k < L ? z[static_cast<size_t>(e) * L + k] : emb[static_cast<size_t>(task ? task[e] : 0) * T + (k - L)];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + warp * 8 + j;
+      if (n >= ly.Npad) continue;
+      const __half2* wh = reinterpret_cast<const __half2*>(ly.w_hi + static_cast<size_t>(n) * ly.Kpad + kb);
+      const __half2* wl = reinterpret_cast<const __half2*>(ly.w_lo + static_cast<size_t>(n) * ly.Kpad + kb);
+      for (int k2 = lane; k2 < kn / 2; k2 += 32) {          // Kz and kZbKc are multiples of 64
+        const float2 h = __half22float2(wh[k2]), l = __half22float2(wl[k2]);
+        const float w0 = h.x + l.x, w1 = h.y + l.y;
+#pragma unroll
+        for (int i = 0; i < kZbEnvs; ++i) acc[j][i] = fmaf(xs[i][2 * k2 + 1], w1, fmaf(xs[i][2 * k2], w0, acc[j][i]));
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int n = n0 + warp * 8 + j;
+#pragma unroll
+    for (int i = 0; i < kZbEnvs; ++i) {
+      const float v = warp_sum(acc[j][i]);
+      if (lane == 0 && n < ly.Npad && e0 + i < E)
+        out[(static_cast<size_t>(mlp) * E + e0 + i) * pitch + n] = fmaf(v, ly.inv_scale, ly.bias[n]);
+    }
+  }
 }
 
 // final action (tdmpc2.py:199-206, math.py:86-94); one warp per environment

@@ -124,6 +124,13 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, 
                : "memory");
 }
 
+// Bulk prefetch of a contiguous global range into L2 (no completion tracking): the 16-byte-aligned part of [p, p + bytes).
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, size_t bytes) {
+  const uint64_t a = reinterpret_cast<uint64_t>(p), a0 = (a + 15ull) & ~15ull, a1 = (a + bytes) & ~15ull;
+  if (a1 > a0)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(a0), "r"(static_cast<uint32_t>(a1 - a0)) : "memory");
+}
+
 // 2D tile store shared -> global (bulk async group).
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(

@@ -181,6 +181,9 @@ class Planner:
         if "TDMPC2_B200_HEAD_KSEG" in os.environ or cfg.get("head_kseg", None) is not None:
             _cabi.check(self.lib.tdmpc2_planner_set_head_kseg(
                 self.h, int(os.environ.get("TDMPC2_B200_HEAD_KSEG", cfg.get("head_kseg", 512) or 0))))
+        # arithmetic: 3 = fp32-parity (default); 1 = the declared NON-PARITY fast mode (see include/tdmpc2_b200.h)
+        self.passes = int(os.environ.get("TDMPC2_B200_PASSES", cfg.get("passes", 3) or 3))
+        _cabi.check(self.lib.tdmpc2_planner_set_passes(self.h, self.passes))
         self._keep = []       # tensors referenced by in-flight async calls
         self.weights_version = None
         self._graphs = {}     # eval_mode -> captured launch chain + its static buffers

@@ -142,3 +142,31 @@ def test_non_mpc_act_runs_the_policy_through_the_kernels():
     assert torch.allclose(got_eps, want_eps, atol=1e-5, rtol=0), (got_eps - want_eps).abs().max()
     for e in range(E):                                     # masked action dims are exactly 0 (world_model.py:158-162)
         assert torch.all(got_eps[e, cfg.action_dims[task[e]]:] == 0)
+
+
+@pytest.mark.parametrize("wl,engine", [("c1", "tcgen05x2"), ("c1", "tcgen05"), ("tiny-mt", "tcgen05x2"), ("tiny-mt", "simt")])
+def test_shared_latent_fold_only_reorders_the_sum(wl, engine, monkeypatch):
+    """At rollout step 0 every sample row of an environment carries the same [z | emb] (z.repeat(N), tdmpc2.py:163): the
+    prologue folds its product with reward.0 / dynamics.0 into a per-environment bias (zbias_kernel) and the t = 0
+    GEMMs cover the action columns only.  Same sum, different association: trajectory values with the fold on and off
+    agree to fp32 round-off (2e-5), far inside the 5e-5 the oracle comparison allows."""
+    from tdmpc2_b200.planner import Planner, draw_noise
+    E = 3
+    cfg = workload(wl, num_envs=E)
+    sd = synth_state_dict(cfg, seed=11, perturb=True)
+    g = torch.Generator().manual_seed(5)
+    obs = torch.randn(E, cfg.obs_shape["state"][0], generator=g).cuda()
+    prev = (0.3 * torch.randn(E, cfg.horizon, cfg.action_dim, generator=g)).cuda()
+    t0 = torch.tensor([1, 0, 0], dtype=torch.uint8).cuda()
+    task = torch.tensor([2, 0, 1], dtype=torch.int32).cuda() if cfg.multitask else None
+    noise = draw_noise(cfg, E, "cuda", generator=torch.Generator(device="cuda").manual_seed(9), reference_order=False)
+    vals = {}
+    for fold in ("1", "0"):
+        monkeypatch.setenv("TDMPC2_B200_ZFOLD", fold)
+        pl = Planner(cfg, E, "cuda:0", engine=engine)
+        pl.pack(sd)
+        _, _, tr = pl.plan(obs, task, t0, prev, noise, trace=True)
+        torch.cuda.synchronize()
+        vals[fold] = tr["values"][:, 0].cpu()          # first iteration: identical inputs on both sides
+    d = (vals["1"] - vals["0"]).abs().max().item()
+    assert 0.0 < d < 2e-5, d                           # > 0: the fold really ran
