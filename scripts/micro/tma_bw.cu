@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cuda.h>
+#include <vector>
 #include <cuda_runtime.h>
 #include "../../tdmpc2_b200/csrc/ptx.cuh"
 
@@ -130,12 +131,22 @@ int main() {
   const Case cases[] = {{0, 1, "unicast shared"}, {2, 1, "unicast private"}, {0, 2, "unicast shared, cluster 2"},
                         {3, 4, "unicast shared, 4 KiB slices"}, {1, 2, "multicast 2"}, {1, 4, "multicast 4"},
                         {1, 8, "multicast 8"}};
-  for (int nslots : {12})
+  // partial grids (unicast shared): does the per-SM delivery rate rise when fewer SMs stream at once (chip-level L2 bound)
+  // or stay put (per-SM ingest port bound)?  Decides whether de-phasing the CTAs' GEMM phases can help.
+  struct Run { Case c; int grid; };
+  std::vector<Run> runs;
   for (const Case& c : cases) {
-    P.mode = c.mode; P.csize = c.csize; P.nslots = nslots;
     const int cl = c.mode == 3 ? 1 : c.csize;
     // whole clusters that are co-resident (see the occupancy lines above): 148 / 132 / 120 CTAs
-    const int grid = cl == 4 ? 132 : cl == 8 ? 120 : 148;
+    runs.push_back({c, cl == 4 ? 132 : cl == 8 ? 120 : 148});
+  }
+  for (int g : {111, 74, 37, 16, 4}) { runs.push_back({cases[0], g}); runs.push_back({cases[2], g & ~1}); }
+  for (int nslots : {12})
+  for (const Run& r : runs) {
+    const Case& c = r.c;
+    P.mode = c.mode; P.csize = c.csize; P.nslots = nslots;
+    const int cl = c.mode == 3 ? 1 : c.csize;
+    const int grid = r.grid;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(544); cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim = {unsigned(cl), 1, 1};

@@ -142,6 +142,7 @@ struct tdmpc2_planner {
   size_t l2_window_bytes = 0;       // > 0: launches carry a persisting-L2 access-policy window over the activation scratch
   float l2_hit_ratio = 1.f;
   bool pair_ok = true;              // every layer of the CEM iteration can run as cta_group::2
+  unsigned stagger = 0;             // PlanParams::stagger (TDMPC2_B200_STAGGER, clock cycles; experiment knob)
   int passes = 3;                   // 3 = fp32-parity arithmetic, 1 = declared non-parity fast mode (PlanParams::passes)
   int zb_kc0 = 0, zb_pitch = 0;     // shared-latent fold (PlanParams::zbias): K-chunks of [z | emb] folded into a per-env bias
   const int32_t* cur_task = nullptr;
@@ -250,6 +251,7 @@ extern "C" int tdmpc2_planner_create(const tdmpc2_dims* dims, tdmpc2_planner** o
   while (p->Ppad < d.num_pi_trajs) p->Ppad <<= 1;
   p->tiles_per_env = (d.num_samples + kTileM - 1) / kTileM;
   p->wide_sleep_ns = env_uint("TDMPC2_B200_WIDE_SLEEP_NS", 0);   // experiment knob
+  p->stagger = env_uint("TDMPC2_B200_STAGGER", 0);
   p->pair_ok = true;   // fused layers and the super-chunked wide layers both run as cta_group::2
 
   // ---- packed blob layout
@@ -570,6 +572,7 @@ static int launch_plan(tdmpc2_planner* p, const PlanParams& prm, int ntiles, cud
   prm2.head_kseg = p->head_kseg;
   prm2.wide_sleep_ns = p->wide_sleep_ns;
   prm2.passes = p->passes;
+  prm2.stagger = p->stagger;
   static_assert(sizeof(p->attr_done) / sizeof(bool) >= 16, "attr_done slots");
   // CTA-pair (cta_group::2) launch: CEM iterations only, whole pairs of tiles of one environment
   const bool pair_engine = (p->engine == TDMPC2_ENGINE_TCGEN05_2SM || p->engine == TDMPC2_ENGINE_TCGEN05_PP ||
@@ -588,7 +591,10 @@ static int launch_plan(tdmpc2_planner* p, const PlanParams& prm, int ntiles, cud
     if (epi) return launch_big(p, plan_kernel<ENGINE_SIMT, false, true>, &ad[0], grid, st, false, prm2);
     return launch_big(p, plan_kernel<ENGINE_SIMT>, &ad[1], grid, st, false, prm2);
   }
-  const bool pair = pair_engine && prm.mode == MODE_ITER && (p->tiles_per_env % 2 == 0) && (ntiles % 2 == 0) && p->pair_ok;
+  // CTA pairs take tiles (2p, 2p + 1): CEM iterations with an even number of tiles per environment (so that a pair never
+  // straddles the refit hand-off asymmetrically), and the policy-prior rollouts whenever the tile count is even
+  const bool pair = pair_engine && p->pair_ok && (ntiles % 2 == 0) &&
+                    ((prm.mode == MODE_ITER && p->tiles_per_env % 2 == 0) || prm.mode == MODE_PRIOR);
   if (pair) {
     grid &= ~1;
     if (wide) {

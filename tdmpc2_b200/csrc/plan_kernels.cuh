@@ -143,6 +143,9 @@ struct PlanParams {
   // 3 = fp32-parity arithmetic (A_lo W_hi + A_hi W_lo + A_hi W_hi); 1 = the DECLARED NON-PARITY fast mode: hi planes only
   // (one fp16 MMA per product, fp32 accumulate), half the operand bytes, no lo planes written.  tdmpc2_planner_set_passes.
   int passes;
+  // MODE_ITER: every second CTA (pair) starts this many clock cycles late, so that neighbouring SMs are not all in their
+  // GEMM phase (L2 -> SM ingest, tensor-pipe power) and all in their epilogue at the same instants.  0 = off.
+  unsigned stagger;
 };
 
 // The layer table lives in global memory; role loops are full of asm volatile(... "memory") (TMA issue, mbarrier waits,
@@ -1932,6 +1935,11 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
   }
 
   const LayerDev* LY = P.layers;
+
+  if (P.stagger != 0u && P.mode == MODE_ITER && ((static_cast<unsigned>(blockIdx.x) >> (CG2 ? 1 : 0)) & 1u)) {
+    const long long t_start = clock64();
+    while (clock64() - t_start < static_cast<long long>(P.stagger)) __nanosleep(500);
+  }
 
   // pair mode: the two CTAs of a pair take tiles (2p, 2p+1) and run the same number of loop trips
   for (int tile = CG2 ? 2 * (static_cast<int>(blockIdx.x) >> 1) + c.rank : static_cast<int>(blockIdx.x); tile < P.ntiles;
