@@ -552,7 +552,7 @@ def main():
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if args.passes == 3 else "f16", "data": "synthetic",
         "config": {"workload": describe(wl, cfg, E_local),
-                   "global_envs": E_total, "parallelism": f"env-shard x{world}", "engine": agent.planner.engine_name,
+                   "global_envs": E_total, "parallelism": f"env-shard x{world}", "engine": agent.planner.iter_engine,
                    "arithmetic": "3-pass fp16-split operands on tcgen05 kind::f16, fp32 accumulate (fp32-parity mode)" if args.passes == 3
                                  else "DECLARED NON-PARITY fast mode: single-pass fp16 operands on tcgen05 kind::f16, fp32 accumulate",
                    "launch": "CUDA-graph replay of prologue -> I x iter -> epilogue" if agent._use_graph and not args.no_graph
@@ -567,7 +567,7 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src,
-                     "kernel": "plan_kernel<tcgen05> MODE_ITER (one CEM iteration)",
+                     "kernel": ("plan_pp_kernel" if agent.planner.iter_engine == "tcgen05pp" else "plan_kernel<tcgen05, pair>") + " (one CEM iteration)",
                      "ms_per_launch": ms_iter, "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({peak_src}, burst)",
                      "flop_per_launch": flops_iter,
                      "note": ("achieved counts ALGORITHMIC flops (2 Q heads, 1x); the fp32-parity path issues 3 fp16 MMAs "

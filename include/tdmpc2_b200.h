@@ -135,6 +135,9 @@ int tdmpc2_planner_workspace_bytes(const tdmpc2_planner* p, size_t* out);
  * workspace and encode the TMA descriptors.  Synchronous. */
 int tdmpc2_planner_bind(tdmpc2_planner* p, void* packed, void* workspace);
 int tdmpc2_planner_set_engine(tdmpc2_planner* p, int engine);
+/* The engine the CEM-iteration launches actually run: the requested one falls back (3 -> 2 -> 0) when the model or the
+ * batch shape does not fit it.  -1 on a null planner. */
+int tdmpc2_planner_iter_engine(const tdmpc2_planner* p);
 /* enable != 0: every planning launch carries an access-policy window that keeps the per-CTA activation scratch in the
  * persisting part of L2 (sets the DEVICE-wide cudaLimitPersistingL2CacheSize, hence opt-in); 0 switches it off.
  * No reference counterpart (the reference's activations are ordinary torch tensors). */

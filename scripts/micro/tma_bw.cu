@@ -12,7 +12,10 @@
 #include <cuda_runtime.h>
 #include "../../tdmpc2_b200/csrc/ptx.cuh"
 
-constexpr int kSlots = 12;   // ring capacity; P.nslots of them are used
+#ifndef TB_SLOTS
+#define TB_SLOTS 12
+#endif
+constexpr int kSlots = TB_SLOTS;   // ring capacity; P.nslots of them are used
 constexpr int kBox = 64 * 128 * 2;   // 16 KiB: 64 fp16 columns x 128 rows
 
 struct Params {
@@ -73,7 +76,11 @@ __global__ void __launch_bounds__(640, 1) bw_kernel(const __grid_constant__ Para
   } else if ((threadIdx.x & 31) == 0) {
     // consumers: warp (r, k) frees, in CTA r, the slots s = k (mod K).  One warp owns a slot for the whole run (a
     // parity wait must never lag a barrier by two phases); remote arrives are slow, so K of them are in flight per target.
+#ifdef TB_CONS3
+    const int w = (threadIdx.x >> 5) - 1, K = 3, r = w / K, k = w % K;
+#else
     const int w = (threadIdx.x >> 5) - 1, K = C == 8 ? 2 : 12 / C, r = w / K, k = w % K;
+#endif
     if (r < C) {
       for (int i = 0; i < P.nbox; ++i) {
         const int s = i % P.nslots, ph = (i / P.nslots) & 1;
@@ -141,7 +148,7 @@ int main() {
     runs.push_back({c, cl == 4 ? 132 : cl == 8 ? 120 : 148});
   }
   for (int g : {111, 74, 37, 16, 4}) { runs.push_back({cases[0], g}); runs.push_back({cases[2], g & ~1}); }
-  for (int nslots : {12})
+  for (int nslots : {kSlots})
   for (const Run& r : runs) {
     const Case& c = r.c;
     P.mode = c.mode; P.csize = c.csize; P.nslots = nslots;
@@ -150,7 +157,11 @@ int main() {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(544); cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim = {unsigned(cl), 1, 1};
+#ifdef TB_NOCLUSTER
+    cfg.attrs = at; cfg.numAttrs = (cl > 1) ? 1 : 0;
+#else
     cfg.attrs = at; cfg.numAttrs = 1;
+#endif
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e30f; long long cyc = 0;
     for (int rep = 0; rep < 3; ++rep) {

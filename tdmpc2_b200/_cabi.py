@@ -17,7 +17,7 @@ ABI_VERSION = 4            # TDMPC2_B200_ABI_VERSION of include/tdmpc2_b200.h th
 SYMBOLS = [
     "tdmpc2_abi_version", "tdmpc2_last_error", "tdmpc2_planner_create", "tdmpc2_planner_destroy",
     "tdmpc2_planner_packed_bytes", "tdmpc2_planner_workspace_bytes", "tdmpc2_planner_bind",
-    "tdmpc2_planner_set_engine", "tdmpc2_planner_set_l2_persist", "tdmpc2_planner_set_kseg", "tdmpc2_planner_set_head_kseg", "tdmpc2_planner_set_passes", "tdmpc2_pack_weights", "tdmpc2_plan_prologue", "tdmpc2_plan_iter",
+    "tdmpc2_planner_set_engine", "tdmpc2_planner_iter_engine", "tdmpc2_planner_set_l2_persist", "tdmpc2_planner_set_kseg", "tdmpc2_planner_set_head_kseg", "tdmpc2_planner_set_passes", "tdmpc2_pack_weights", "tdmpc2_plan_prologue", "tdmpc2_plan_iter",
     "tdmpc2_plan_epilogue", "tdmpc2_plan_get_state", "tdmpc2_estimate_value", "tdmpc2_debug_layer",
     "tdmpc2_planner_layer_count", "tdmpc2_planner_launch_count", "tdmpc2_planner_set_profile",
 ]
@@ -74,6 +74,7 @@ def load():
     lib.tdmpc2_planner_workspace_bytes.argtypes = [vp, C.POINTER(C.c_size_t)]
     lib.tdmpc2_planner_bind.argtypes = [vp, vp, vp]
     lib.tdmpc2_planner_set_engine.argtypes = [vp, C.c_int]
+    lib.tdmpc2_planner_iter_engine.argtypes = [vp]
     lib.tdmpc2_planner_set_l2_persist.argtypes = [vp, C.c_int]
     lib.tdmpc2_planner_set_kseg.argtypes = [vp, C.c_int]
     lib.tdmpc2_planner_set_head_kseg.argtypes = [vp, C.c_int]

@@ -359,9 +359,10 @@ static int make_map(EncodeTiledFn enc, CUtensorMap* m, void* base, uint64_t kpad
   cuuint64_t strides[1] = {kpad * 2};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  // 64-column boxes (operand loads): 128-byte rows, 128B swizzle; 32-column boxes (epilogue stores): 64B swizzle
+  // 64-column boxes (operand loads): 128-byte rows, 128B swizzle; 32-column boxes (epilogue stores): 64B swizzle;
+  // 16-column boxes (ping-pong epilogue stores): 32-byte rows, no swizzle
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   box_cols == kKch ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   box_cols == kKch ? CU_TENSOR_MAP_SWIZZLE_128B : box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(TDMPC2_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) kpad=%llu rows=%llu", (int)r,
                                      (unsigned long long)kpad, (unsigned long long)rows);
@@ -393,8 +394,8 @@ extern "C" int tdmpc2_planner_bind(tdmpc2_planner* p, void* packed, void* worksp
     const uint64_t rows = static_cast<uint64_t>(p->nslots) * 2 * kTileM;
     if ((rc = make_map(enc, &B.tmX64, p->ws + p->off_X, p->KpadX, rows, kKch, kPPHalf))) return rc;
     if ((rc = make_map(enc, &B.tmH64, p->ws + p->off_H, p->KpadH, rows, kKch, kPPHalf))) return rc;
-    if ((rc = make_map(enc, &B.tmXs64, p->ws + p->off_X, p->KpadX, rows, 32, kPPHalf))) return rc;
-    if ((rc = make_map(enc, &B.tmHs64, p->ws + p->off_H, p->KpadH, rows, 32, kPPHalf))) return rc;
+    if ((rc = make_map(enc, &B.tmXs64, p->ws + p->off_X, p->KpadX, rows, kPPStgCols, kPPHalf))) return rc;
+    if ((rc = make_map(enc, &B.tmHs64, p->ws + p->off_H, p->KpadH, rows, kPPStgCols, kPPHalf))) return rc;
   }
   for (int m = 0; m < p->nmaps; ++m)
     if ((rc = make_map(enc, &B.tmW[m], p->packed + p->map_off[m], p->map_kpad[m], p->map_rows[m]))) return rc;
@@ -519,6 +520,17 @@ static bool pp_eligible(const tdmpc2_planner* p) {
   return true;
 }
 
+// The engine the CEM-iteration launches of this planner actually run (the requested one falls back when a model or
+// shape does not fit it: ping-pong -> CTA pairs -> single CTAs).
+extern "C" int tdmpc2_planner_iter_engine(const tdmpc2_planner* p) {
+  if (!p) return -1;
+  if (p->engine == TDMPC2_ENGINE_SIMT || p->engine == TDMPC2_ENGINE_TCGEN05) return p->engine;
+  const bool pairs = (p->tiles_per_env % 2 == 0) && p->pair_ok;
+  if (!pairs) return TDMPC2_ENGINE_TCGEN05;
+  if (p->engine == TDMPC2_ENGINE_TCGEN05_PP) return (p->passes == 3 && pp_eligible(p)) ? TDMPC2_ENGINE_TCGEN05_PP : TDMPC2_ENGINE_TCGEN05_2SM;
+  return p->engine;
+}
+
 // W prefetch (plan_kernel<..., WPF>): every LayerNorm layer of the CEM iteration must take the epilogue's fast path
 // (whole 32-column blocks out through TMA stores), which is the only one that stages in the A ring
 static bool wpf_eligible(const tdmpc2_planner* p) {
@@ -578,7 +590,7 @@ static int launch_plan(tdmpc2_planner* p, const PlanParams& prm, int ntiles, cud
   const bool pair_engine = (p->engine == TDMPC2_ENGINE_TCGEN05_2SM || p->engine == TDMPC2_ENGINE_TCGEN05_PP ||
                             p->engine == TDMPC2_ENGINE_TCGEN05_2SM_PF);
   if (p->engine == TDMPC2_ENGINE_TCGEN05_PP && prm.mode == MODE_ITER && (p->tiles_per_env % 2 == 0) && (ntiles % 2 == 0) &&
-      pp_eligible(p)) {
+      p->passes == 3 && pp_eligible(p)) {
     // ping-pong kernel (plan_pp.cuh): GEMM of one 64-row half overlaps the epilogue of the other
     if (!p->smem_attr_pp) {
       CUDA_TRY(cudaFuncSetAttribute(plan_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPPSmemBytes));

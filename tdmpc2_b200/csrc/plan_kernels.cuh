@@ -106,7 +106,7 @@ struct PlanParams {
   CUtensorMap tmH;                 // [slots*2*128, KpadH]
   CUtensorMap tmXs, tmHs;          // same tensors, box 32 x 128, 64-byte swizzle: the epilogue's TMA stores
   CUtensorMap tmX64, tmH64;        // 64-row boxes (ping-pong engine, plan_pp.cuh): loads 64 x 64, 128-byte swizzle
-  CUtensorMap tmXs64, tmHs64;      //                                             : stores 32 x 64, 64-byte swizzle
+  CUtensorMap tmXs64, tmHs64;      //                                             : stores 16 x 64, 32-byte rows, no swizzle
   CUtensorMap tmW[kMaxWMaps];      // weights, one map per Kpad class, box 64 x 128
   const LayerDev* layers;
   int E, N, P, Ppad, K, H, obs_dim, A, Apad, L, M, T, B, num_q, simnorm, num_enc;   // Apad = pad32(A): the pi head's
@@ -383,15 +383,17 @@ __device__ __forceinline__ void prod_load_a(const PlanParams& P, Ctx& c, const C
   c.pf0 += prof_clock() - tw;
   uint8_t* st = c.stage_base + s * kASlotBytes;
   const bool lo = P.passes != 1;                 // fast mode streams the hi planes only
-  if (c.cg2) {
-    // both CTAs of the pair stream their own 128 rows; the bytes of both land on the leader's barrier
-    if (c.rank == 0) ptx::mbar_expect_tx(&c.a_full[s], lo ? 2 * kASlotBytes : 2 * kAPlane);
-    ptx::tma_load_2d_2sm(tmA, &c.a_full[s], st, kc * kKch, arow_hi);
-    if (lo) ptx::tma_load_2d_2sm(tmA, &c.a_full[s], st + kAPlane, kc * kKch, arow_lo);
-  } else {
-    ptx::mbar_expect_tx(&c.a_full[s], lo ? kASlotBytes : kAPlane);
-    ptx::tma_load_2d(tmA, &c.a_full[s], st, kc * kKch, arow_hi);
-    if (lo) ptx::tma_load_2d(tmA, &c.a_full[s], st + kAPlane, kc * kKch, arow_lo);
+  if (ptx::elect_one()) {                        // the whole warp runs the role loop, one lane issues (see tc_producer)
+    if (c.cg2) {
+      // both CTAs of the pair stream their own 128 rows; the bytes of both land on the leader's barrier
+      if (c.rank == 0) ptx::mbar_expect_tx(&c.a_full[s], lo ? 2 * kASlotBytes : 2 * kAPlane);
+      ptx::tma_load_2d_2sm(tmA, &c.a_full[s], st, kc * kKch, arow_hi);
+      if (lo) ptx::tma_load_2d_2sm(tmA, &c.a_full[s], st + kAPlane, kc * kKch, arow_lo);
+    } else {
+      ptx::mbar_expect_tx(&c.a_full[s], lo ? kASlotBytes : kAPlane);
+      ptx::tma_load_2d(tmA, &c.a_full[s], st, kc * kKch, arow_hi);
+      if (lo) ptx::tma_load_2d(tmA, &c.a_full[s], st + kAPlane, kc * kKch, arow_lo);
+    }
   }
   ++c.pa_it;
 }
@@ -402,6 +404,7 @@ __device__ __forceinline__ void prod_load_w(Ctx& c, const CUtensorMap* tmW, int 
   ptx::mbar_wait(&c.w_empty[s], ph ^ 1);
   c.pf0 += prof_clock() - tw;
   uint8_t* st = c.stage_base + kWRingOff + s * c.w_stride;
+  if (!ptx::elect_one()) { ++c.pw_it; return; }
   if (c.cg2) {
     // each CTA streams HALF of the N-chunk's weight rows (one 128-row box per plane; for a 128-column chunk only
     // its first 64 rows are consumed): the pair MMA reads B rows [0, N/2) from the leader and [N/2, N) from the peer
@@ -422,6 +425,10 @@ __device__ __forceinline__ void prod_load_w(Ctx& c, const CUtensorMap* tmW, int 
 
 // N-chunks [nc0, nc0 + nnc_lim) of the layer (default: all of them): K-chunks outermost, each A chunk is loaded once
 // and multiplied with every N-chunk of the range; layers wider than TMEM call this once per 512-column super-chunk.
+// Role loops (TMA producer, MMA issuer) are run by the WHOLE warp, with one elected lane issuing the asynchronous
+// instructions: in warp-convergent code the compiler keeps ring counters, coordinates and operand descriptors in uniform
+// registers (12 UTCHMMA back to back), whereas inside an `if (lane == 0)` branch every cp.async.bulk.tensor / tcgen05.mma
+// gets a ~13-instruction "elect + R2UR + retry" waterfall (~120 cycles per MMA: more than an N = 128 MMA takes).
 __device__ __forceinline__ void tc_producer(const PlanParams& P, Ctx& c, const LayerRec& ly, int srcbuf, const LayerDev* next,
                                             int nc0 = 0, int nnc_lim = 1 << 30, int kc0 = 0, int kc_lim = 1 << 30, int next_kc0 = 0) {
   const int nkc = min(ly.Kpad / kKch, kc0 + kc_lim);
@@ -455,6 +462,11 @@ __device__ __forceinline__ void tc_producer(const PlanParams& P, Ctx& c, const L
 // 12 MMAs of one (A K-chunk, W K-chunk x N-chunk) pair: A_lo*W_hi + A_hi*W_lo + A_hi*W_hi, 4 K-steps of 16.
 __device__ __forceinline__ void mma_stage(uint32_t d, uint32_t sa, uint32_t sw, uint32_t w_lo_off, uint32_t idesc, bool first, bool cg2,
                                           bool one_pass = false) {
+#ifdef TDMPC2_EXP_NOMMA   // measurement build: no MMAs are issued, the commits release the operand slots at once -> the GEMM
+  return;                 // phases last exactly as long as the operand ingest (results are garbage; scripts/gpu_r2l.sh)
+#endif
+  if (!ptx::elect_one()) return;   // whole-warp role loop, one lane issues (tcgen05.commit must come from the same lane:
+                                   // elect.sync with a full mask always picks the same one)
   if (one_pass) {                                   // declared non-parity fast mode: A_hi * W_hi only
 #pragma unroll
     for (int ks = 0; ks < kKch / 16; ++ks) {
@@ -513,16 +525,22 @@ __device__ __forceinline__ void tc_mma(const PlanParams& P, Ctx& c, const LayerR
       const int ncols = min(kNch, ly.Npad - nc * kNch);
       mma_stage(c.tmem_base + (nc - nc0) * kNch, sbase + as * kASlotBytes, sbase + kWRingOff + ws * c.w_stride, c.w_lo_off,
                 ptx::make_idesc_f16(c.cg2 ? 2 * kTileM : kTileM, ncols), kc == kc0, c.cg2 != 0, P.passes == 1);
-      if (c.cg2) ptx::umma_commit_2sm(&c.w_empty[ws]);
-      else ptx::umma_commit(&c.w_empty[ws]);     // frees the W slot when these MMAs retire
+      if (ptx::elect_one()) {
+        if (c.cg2) ptx::umma_commit_2sm(&c.w_empty[ws]);
+        else ptx::umma_commit(&c.w_empty[ws]);     // frees the W slot when these MMAs retire
+      }
       ++c.mw_it;
     }
-    if (c.cg2) ptx::umma_commit_2sm(&c.a_empty[as]);
-    else ptx::umma_commit(&c.a_empty[as]);
+    if (ptx::elect_one()) {
+      if (c.cg2) ptx::umma_commit_2sm(&c.a_empty[as]);
+      else ptx::umma_commit(&c.a_empty[as]);
+    }
     ++c.ma_it;
   }
-  if (c.cg2) ptx::umma_commit_2sm(&c.facc[0]);
-  else ptx::umma_commit(&c.facc[0]);
+  if (ptx::elect_one()) {
+    if (c.cg2) ptx::umma_commit_2sm(&c.facc[0]);
+    else ptx::umma_commit(&c.facc[0]);
+  }
   TDMPC2_TRACE(P, c, 3);
 }
 
@@ -554,12 +572,16 @@ __device__ __forceinline__ void tc_mma_head_seg(const PlanParams& P, Ctx& c, con
       ptx::tc_fence_after();
       mma_stage(c.tmem_base + b * kNch, sbase + as * kASlotBytes, sbase + kWRingOff + ws * c.w_stride, c.w_lo_off, idesc,
                 kc == kc0, c.cg2 != 0, P.passes == 1);
-      if (c.cg2) { ptx::umma_commit_2sm(&c.w_empty[ws]); ptx::umma_commit_2sm(&c.a_empty[as]); }
-      else { ptx::umma_commit(&c.w_empty[ws]); ptx::umma_commit(&c.a_empty[as]); }
+      if (ptx::elect_one()) {
+        if (c.cg2) { ptx::umma_commit_2sm(&c.w_empty[ws]); ptx::umma_commit_2sm(&c.a_empty[as]); }
+        else { ptx::umma_commit(&c.w_empty[ws]); ptx::umma_commit(&c.a_empty[as]); }
+      }
       ++c.mw_it; ++c.ma_it;
     }
-    if (c.cg2) ptx::umma_commit_2sm(&c.facc[b]);
-    else ptx::umma_commit(&c.facc[b]);
+    if (ptx::elect_one()) {
+      if (c.cg2) ptx::umma_commit_2sm(&c.facc[b]);
+      else ptx::umma_commit(&c.facc[b]);
+    }
   }
 }
 
@@ -1662,11 +1684,10 @@ __device__ __forceinline__ int wide_layer_tc(const PlanParams& P, Ctx& c, const 
   const int kseg = (P.kseg > 0 && P.kseg < nkc) ? P.kseg : nkc;
   const int nseg = (nkc + kseg - 1) / kseg;
   if (c.warp == 0) {
-    if (c.lane == 0)
-      for (int sc = 0; sc < nsc; ++sc)
-        for (int seg = 0; seg < nseg; ++seg) tc_producer(P, c, ly, srcbuf, nullptr, 2 * sc, 2, kc_begin + seg * kseg, kseg);
+    for (int sc = 0; sc < nsc; ++sc)
+      for (int seg = 0; seg < nseg; ++seg) tc_producer(P, c, ly, srcbuf, nullptr, 2 * sc, 2, kc_begin + seg * kseg, kseg);
   } else if (c.warp == 1) {
-    if (c.lane == 0 && (!c.cg2 || c.rank == 0))
+    if (!c.cg2 || c.rank == 0)
       for (int sc = 0; sc < nsc; ++sc)
         for (int seg = 0; seg < nseg; ++seg) {
           if (sc + seg > 0) {                           // the previous accumulator has been drained
@@ -1708,9 +1729,9 @@ __device__ __forceinline__ void run_layer(const PlanParams& P, Ctx& c, const Lay
     if (threadIdx.x == 0) TDMPC2_TRACE(P, c, 0);
     const int hseg = (WIDE && !is_ln && head_seg_ok(P, ea.kind)) ? head_segments(P, ly) : 1;   // K <= 512 unless the model is wide
     if (c.warp == 0) {
-      if (c.lane == 0) tc_producer(P, c, ly, srcbuf, next, 0, 1 << 30, kc0, 1 << 30, next_kc0);
+      tc_producer(P, c, ly, srcbuf, next, 0, 1 << 30, kc0, 1 << 30, next_kc0);
     } else if (c.warp == 1) {
-      if (c.lane == 0 && (!c.cg2 || c.rank == 0)) {
+      if (!c.cg2 || c.rank == 0) {
         if (hseg > 1) tc_mma_head_seg(P, c, ly, hseg);
         else tc_mma(P, c, ly, 0, 1 << 30, kc0);
       }

@@ -34,10 +34,15 @@ constexpr int kPPASlot = 2 * kPPAPlane;                // hi | lo
 constexpr int kPPARing = 3;
 constexpr int kPPWPlane = 128 * 128;                   // 16 KiB: this CTA's 128 weight rows of a 256-column chunk
 constexpr int kPPWSlot = 2 * kPPWPlane;
-constexpr int kPPWRing = 3;
+// Operand rings: what bounds a half's GEMM is the number of operand bytes in flight (a TMA request takes ~2.8 k cycles
+// from issue to a released slot; the hardware delivers > 65 B/clk/SM when enough requests are outstanding:
+// profiles/r02_nomma_*.txt, r02_micro_ingest_paths.txt), and a half needs 640 KB per 12.3 k cycles of MMA.  Four weight
+// slots instead of three; the 32 KiB come out of the epilogue's staging tiles, which shrink to 64 rows x 16 columns.
+constexpr int kPPWRing = 4;
 constexpr int kPPWOff = kPPARing * kPPASlot;           // 48 KiB
-constexpr int kPPStgOff = kPPWOff + kPPWRing * kPPWSlot;   // 144 KiB
-constexpr int kPPStgPlane = kPPHalf * 64;              // 4 KiB: 64 rows x 32 fp16, 64-byte swizzle
+constexpr int kPPStgOff = kPPWOff + kPPWRing * kPPWSlot;   // 176 KiB
+constexpr int kPPStgCols = 16;                         // columns per staged block
+constexpr int kPPStgPlane = kPPHalf * kPPStgCols * 2;  // 2 KiB: 64 rows x 16 fp16, row-major (32-byte rows, no swizzle)
 constexpr int kPPStgBuf = 2 * kPPStgPlane;             // hi | lo
 constexpr int kPPGroups = 8;                           // block groups: 2 column halves x 4 column groups, 2 warps each
 constexpr int kPPOperandBytes = kPPStgOff + kPPGroups * kPPStgBuf;   // 208 KiB
@@ -49,6 +54,7 @@ constexpr int kPPMaxSteps = 48;
 constexpr int kPPProg = 2 * kPPMaxSteps * 32;          // double-buffered layer program
 constexpr int kPPSmemBytes = kPPOperandBytes + kPPCtrl + kPPVec + kPPPart + kPPAct + kPPProg + 1024;
 static_assert(kPPSmemBytes <= 232448, "ping-pong kernel shared memory");
+static_assert(kPPGroups * kPPStgBuf >= kPPHalf * 128 * 4, "the pi head's exchange buffer aliases the staging area");
 
 // Diagnostics: clock stamps of CTA 0's first tile, [step][event] after the per-CTA counters (see TDMPC2_TRACE).
 #define PP_TRACE(P_, on_, s_, ev_)                                                           \
@@ -117,6 +123,37 @@ __device__ __forceinline__ void pp_write_actions(const PlanParams& P, PPCtx& c, 
   const int n0 = (tile % P.tiles_per_env) * kTileM;
   const float* nz = P.noise_r + (static_cast<size_t>(env) * P.H + t) * (P.N - P.P) * P.A;
   const float* pa = P.pi_actions + (static_cast<size_t>(env) * P.H + t) * P.P * P.A;
+  const int ng = (P.A + 7) >> 3;
+  if (P.L + P.T + 8 * ng <= P.KpadX) {            // ((L + T) % 8 == 0 is a condition of this kernel: pp_eligible)
+    // one (row, 8 action columns) item per thread, two 16-byte stores per item (same pass as plan_kernel's)
+    for (int i = tid; i < nrows * ng; i += kEpiThreads) {
+      const int r = r0 + i / ng, g8 = (i % ng) * 8;
+      const int n = n0 + r;
+      const float* src = (n < P.P) ? pa + static_cast<size_t>(n) * P.A : nz + static_cast<size_t>(n - P.P) * P.A;
+      float x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) x[u] = (g8 + u < P.A) ? (n < P.P ? src[g8 + u] : __ldcs(src + g8 + u)) : 0.f;
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int u = 0; u < 8; u += 2) {
+        __half h[2], l[2];
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          const int a = min(g8 + u + w, P.A - 1);
+          float v = x[u + w];
+          if (n >= P.P) v = fminf(fmaxf(__fadd_rn(sm_mean[a], __fmul_rn(sm_std[a], v)), -1.f), 1.f);
+          v = (g8 + u + w < P.A) ? v * sm_mask[a] : 0.f;
+          split_f(v, h[w], l[w]);
+        }
+        hw[u >> 1] = static_cast<uint32_t>(__half_as_ushort(h[0])) | (static_cast<uint32_t>(__half_as_ushort(h[1])) << 16);
+        lw[u >> 1] = static_cast<uint32_t>(__half_as_ushort(l[0])) | (static_cast<uint32_t>(__half_as_ushort(l[1])) << 16);
+      }
+      const size_t o = static_cast<size_t>(r) * P.KpadX + P.L + P.T + g8;
+      __stcg(reinterpret_cast<uint4*>(xhi + o), make_uint4(hw[0], hw[1], hw[2], hw[3]));
+      __stcg(reinterpret_cast<uint4*>(xlo + o), make_uint4(lw[0], lw[1], lw[2], lw[3]));
+    }
+    return;
+  }
 #pragma unroll 4
   for (int i = tid; i < nrows * P.A; i += kEpiThreads) {
     const int r = r0 + i / P.A, a = i % P.A;
@@ -189,19 +226,14 @@ __device__ __forceinline__ void pp_epi_ln(const PlanParams& P, PPCtx& c, const P
     rstd = rsqrtf(m2 / static_cast<float>(ly.N) + 1e-5f);       // nn.LayerNorm eps, biased variance
   }
   const float2 rstd2 = f2s(rstd), nmr2 = f2s(-mean * rstd);
-  // ---- pass 2: normalise, activate, split, stage, TMA-store one 64 x 32 block per chunk
+  // ---- pass 2: normalise, activate, split, stage, TMA-store one 64 x 16 block per 16 columns
   uint8_t* buf = c.base + kPPStgOff + et.bg * kPPStgBuf;
-  const uint32_t rowaddr = ptx::smem_u32(buf) + static_cast<uint32_t>(et.row) * 64u;
-  const uint32_t swz = static_cast<uint32_t>((et.row >> 1) & 3);
+  const uint32_t rowaddr = ptx::smem_u32(buf) + static_cast<uint32_t>(et.row) * (kPPStgCols * 2u);
   const bool leader = ((et.q & 1) == 0) && (c.lane == 0);
   const CUtensorMap* tmD = (st.dstbuf == BUF_X) ? &P.tmXs64 : &P.tmHs64;
   const int row_hi = plane_row0(P, c.slot, st.dstbuf, 0) + h * kPPHalf, row_lo = plane_row0(P, c.slot, st.dstbuf, 1) + h * kPPHalf;
   for (int nc = 0; nc < nnc; ++nc) {
     const int c0 = nc * kNch + et.colhalf * 128 + et.grp * 32;
-    if (nc > 0) {                                                  // single staging buffer: previous store must have read it
-      if (leader) ptx::bulk_wait_read<0>();
-      pp_group_sync(et.bg);
-    }
 #pragma unroll
     for (int sub = 0; sub < 32; sub += 16) {
       uint32_t v[16];
@@ -248,19 +280,23 @@ __device__ __forceinline__ void pp_epi_ln(const PlanParams& P, PPCtx& c, const P
         hw[i] = *reinterpret_cast<const uint32_t*>(&h2);
         lw[i] = *reinterpret_cast<const uint32_t*>(&l2);
       }
+      if (nc > 0 || sub > 0) {
+        // single staging block per group: its previous store (issued a whole block of math ago) must have read it
+        if (leader) ptx::bulk_wait_read<0>();
+        pp_group_sync(et.bg);
+      }
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const uint32_t off = ((static_cast<uint32_t>((sub >> 3) + i) ^ swz) << 4);
-        ptx::st_shared_v4(rowaddr + off, hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
-        ptx::st_shared_v4(rowaddr + kPPStgPlane + off, lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]);
+        ptx::st_shared_v4(rowaddr + 16u * i, hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
+        ptx::st_shared_v4(rowaddr + kPPStgPlane + 16u * i, lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]);
       }
-    }
-    ptx::fence_proxy_async_smem();
-    pp_group_sync(et.bg);
-    if (leader) {
-      ptx::tma_store_2d(tmD, buf, c0, row_hi);            // LN outputs always start at column 0 of their buffer
-      ptx::tma_store_2d(tmD, buf + kPPStgPlane, c0, row_lo);
-      ptx::bulk_commit();
+      ptx::fence_proxy_async_smem();
+      pp_group_sync(et.bg);
+      if (leader) {
+        ptx::tma_store_2d(tmD, buf, c0 + sub, row_hi);      // LN outputs always start at column 0 of their buffer
+        ptx::tma_store_2d(tmD, buf + kPPStgPlane, c0 + sub, row_lo);
+        ptx::bulk_commit();
+      }
     }
   }
 }
@@ -308,17 +344,20 @@ __device__ __forceinline__ void pp_epi_twohot(const PlanParams& P, PPCtx& c, con
 // pi head (world_model.py:144-174): Npad = 128, so lanes < 64 hold logical columns [0, 64) and lanes >= 64 columns
 // [64, 128).  Mean logits are columns [0, A), log-std logits columns [Apad, Apad + A): every thread drops its 16
 // biased logits into an smem row, then the threads owning mean columns finish the action.
-constexpr int kPPPiPitch = 129;
+// exchange buffer of the pi head: [64 rows][128] fp32 = the 32 KiB of the staging area; element (row, col) lives at
+// column col ^ (row & 31) of its row, so that the 32 rows of a warp touching one column hit 32 different banks
+constexpr int kPPPiPitch = 128;
+__device__ __forceinline__ int pp_pi_idx(int row, int col) { return row * kPPPiPitch + (col ^ (row & 31)); }
 __device__ __forceinline__ void pp_epi_pi(const PlanParams& P, PPCtx& c, const PPThread& et, const LayerDev& ly, int h, int tile,
                                           int env, int task) {
   const float* sb = c.vec;
-  float* xch = reinterpret_cast<float*>(c.base + kPPStgOff);           // [64 rows][129] fp32, 33 KiB of the staging area
+  float* xch = reinterpret_cast<float*>(c.base + kPPStgOff);           // [64 rows][128] fp32: see pp_pi_idx
   const int c0 = et.colhalf * 64 + et.grp * 16;
   uint32_t v[16];
   ptx::tmem_ld_32x16(et.taddr + c.tmem_base + static_cast<uint32_t>(h * 256 + et.grp * 16), v);
   ptx::tmem_ld_wait();
 #pragma unroll
-  for (int i = 0; i < 16; ++i) xch[et.row * kPPPiPitch + c0 + i] = fmaf(__uint_as_float(v[i]), ly.inv_scale, sb[c0 + i]);
+  for (int i = 0; i < 16; ++i) xch[pp_pi_idx(et.row, c0 + i)] = fmaf(__uint_as_float(v[i]), ly.inv_scale, sb[c0 + i]);
   epi_bar_sync();
   const int a0 = c0;
   if (a0 < P.A) {
@@ -327,7 +366,7 @@ __device__ __forceinline__ void pp_epi_pi(const PlanParams& P, PPCtx& c, const P
     __half* xhi = plane_ptr(P, c.slot, BUF_X, 0) + static_cast<size_t>(r) * P.KpadX + P.L + P.T;
     __half* xlo = plane_ptr(P, c.slot, BUF_X, 1) + static_cast<size_t>(r) * P.KpadX + P.L + P.T;
     const float* eps = P.noise_pi + (static_cast<size_t>(env) * P.N + n) * P.A;
-    const float* xr = xch + et.row * kPPPiPitch;
+    const float* xr = xch;
     const bool vec = (((P.L + P.T) & 7) == 0) && (P.L + P.T + a0 + 16 <= P.KpadX);
     uint32_t hw[8], lw[8];
 #pragma unroll
@@ -338,7 +377,7 @@ __device__ __forceinline__ void pp_epi_pi(const PlanParams& P, PPCtx& c, const P
         const int a = a0 + i + u;
         act2[u] = 0.f;
         if (a < P.A) {
-          act2[u] = pi_action(P, xr[a], xr[P.Apad + a], eps[a], task, a);
+          act2[u] = pi_action(P, xr[pp_pi_idx(et.row, a)], xr[pp_pi_idx(et.row, P.Apad + a)], eps[a], task, a);
           if (!vec) split_store(xhi + a, xlo + a, act2[u]);
         }
       }
@@ -405,8 +444,12 @@ __global__ void __launch_bounds__(kPPThreads, 1) plan_pp_kernel(const __grid_con
   const int tile0 = 2 * (static_cast<int>(blockIdx.x) >> 1) + c.rank;
 
   if (c.warp == 0) {
-    // =================================================================== TMA producer (one lane, both CTAs)
-    if (c.lane == 0) {
+    // =================================================================== TMA producer (both CTAs)
+    // The WHOLE warp runs the loops and one elected lane issues: in warp-convergent code the compiler keeps counters,
+    // coordinates and descriptors in uniform registers, whereas inside a single-lane branch every cp.async.bulk.tensor /
+    // tcgen05.mma is wrapped in a ~13-instruction "elect + R2UR + retry" waterfall (the MMA issuer then needs ~125 cycles
+    // per MMA, twice what the M = 128 pair MMA takes: profiles/r02_timeline_pp.txt before / after).
+    {
       uint32_t pa_it = 0, pw_it = 0, rdy_it[2] = {0, 0};
       int tcount = 0;
       for (int tile = tile0; tile < P.ntiles; tile += gridDim.x, ++tcount) {
@@ -426,9 +469,11 @@ __global__ void __launch_bounds__(kPPThreads, 1) plan_pp_kernel(const __grid_con
                 const uint32_t sl = pa_it % kPPARing, ph = (pa_it / kPPARing) & 1;
                 ptx::mbar_wait(&c.a_empty[sl], ph ^ 1);
                 uint8_t* dst = c.base + sl * kPPASlot;
-                if (c.rank == 0) ptx::mbar_expect_tx(&c.a_full[sl], 2 * kPPASlot);
-                ptx::tma_load_2d_2sm(tmA, &c.a_full[sl], dst, kc * kKch, arow_hi);
-                ptx::tma_load_2d_2sm(tmA, &c.a_full[sl], dst + kPPAPlane, kc * kKch, arow_lo);
+                if (ptx::elect_one()) {
+                  if (c.rank == 0) ptx::mbar_expect_tx(&c.a_full[sl], 2 * kPPASlot);
+                  ptx::tma_load_2d_2sm(tmA, &c.a_full[sl], dst, kc * kKch, arow_hi);
+                  ptx::tma_load_2d_2sm(tmA, &c.a_full[sl], dst + kPPAPlane, kc * kKch, arow_lo);
+                }
                 ++pa_it;
               }
               for (int nc = 0; nc < nnc; ++nc) {
@@ -436,10 +481,12 @@ __global__ void __launch_bounds__(kPPThreads, 1) plan_pp_kernel(const __grid_con
                 const uint32_t sl = pw_it % kPPWRing, ph = (pw_it / kPPWRing) & 1;
                 ptx::mbar_wait(&c.w_empty[sl], ph ^ 1);
                 uint8_t* dst = c.base + kPPWOff + sl * kPPWSlot;
-                if (c.rank == 0) ptx::mbar_expect_tx(&c.w_full[sl], 2 * kPPWSlot);
                 const int wr = ly.wrow + nc * kNch + c.rank * (ncols / 2);
-                ptx::tma_load_2d_2sm(tmW, &c.w_full[sl], dst, kc * kKch, wr);
-                ptx::tma_load_2d_2sm(tmW, &c.w_full[sl], dst + kPPWPlane, kc * kKch, wr + ly.Npad);
+                if (ptx::elect_one()) {
+                  if (c.rank == 0) ptx::mbar_expect_tx(&c.w_full[sl], 2 * kPPWSlot);
+                  ptx::tma_load_2d_2sm(tmW, &c.w_full[sl], dst, kc * kKch, wr);
+                  ptx::tma_load_2d_2sm(tmW, &c.w_full[sl], dst + kPPWPlane, kc * kKch, wr + ly.Npad);
+                }
                 ++pw_it;
               }
             }
@@ -448,8 +495,8 @@ __global__ void __launch_bounds__(kPPThreads, 1) plan_pp_kernel(const __grid_con
       }
     }
   } else if (c.warp == 1) {
-    // =================================================================== MMA issuer (leader CTA only)
-    if (c.lane == 0 && c.rank == 0) {
+    // =================================================================== MMA issuer (leader CTA only; whole warp, elected issue)
+    if (c.rank == 0) {
       uint32_t ma_it = 0, mw_it = 0, rdy_it[2] = {0, 0}, free_it[2] = {0, 0};
       const uint32_t sbase = ptx::smem_u32(c.base);
       int tcount = 0;
@@ -477,23 +524,29 @@ __global__ void __launch_bounds__(kPPThreads, 1) plan_pp_kernel(const __grid_con
                 const uint32_t d = c.tmem_base + static_cast<uint32_t>(h * 256 + nc * 128);
                 const uint32_t sa = sbase + as * kPPASlot, sw = sbase + kPPWOff + ws * kPPWSlot;
                 const uint32_t idesc = ptx::make_idesc_f16(2 * kPPHalf, ncols);
+                if (ptx::elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < kKch / 16; ++ks) {
-                  const uint64_t a_hi = ptx::make_sw128_kmajor_desc(sa + ks * 32);
-                  const uint64_t a_lo = ptx::make_sw128_kmajor_desc(sa + kPPAPlane + ks * 32);
-                  const uint64_t w_hi = ptx::make_sw128_kmajor_desc(sw + ks * 32);
-                  const uint64_t w_lo = ptx::make_sw128_kmajor_desc(sw + kPPWPlane + ks * 32);
-                  ptx::umma_f16_2sm(d, a_lo, w_hi, idesc, !(kc == 0 && ks == 0));
-                  ptx::umma_f16_2sm(d, a_hi, w_lo, idesc, 1);
-                  ptx::umma_f16_2sm(d, a_hi, w_hi, idesc, 1);
+                  for (int ks = 0; ks < kKch / 16; ++ks) {
+                    const uint64_t a_hi = ptx::make_sw128_kmajor_desc(sa + ks * 32);
+                    const uint64_t a_lo = ptx::make_sw128_kmajor_desc(sa + kPPAPlane + ks * 32);
+                    const uint64_t w_hi = ptx::make_sw128_kmajor_desc(sw + ks * 32);
+                    const uint64_t w_lo = ptx::make_sw128_kmajor_desc(sw + kPPWPlane + ks * 32);
+#ifndef TDMPC2_EXP_NOMMA   // (measurement build: see mma_stage in plan_kernels.cuh)
+                    ptx::umma_f16_2sm(d, a_lo, w_hi, idesc, !(kc == 0 && ks == 0));
+                    ptx::umma_f16_2sm(d, a_hi, w_lo, idesc, 1);
+                    ptx::umma_f16_2sm(d, a_hi, w_hi, idesc, 1);
+#else
+                    (void)a_hi; (void)a_lo; (void)w_hi; (void)w_lo; (void)d; (void)idesc;
+#endif
+                  }
+                  ptx::umma_commit_2sm(&c.w_empty[ws]);
                 }
-                ptx::umma_commit_2sm(&c.w_empty[ws]);
                 ++mw_it;
               }
-              ptx::umma_commit_2sm(&c.a_empty[as]);
+              if (ptx::elect_one()) ptx::umma_commit_2sm(&c.a_empty[as]);
               ++ma_it;
             }
-            ptx::umma_commit_2sm(&c.facc[h]);
+            if (ptx::elect_one()) ptx::umma_commit_2sm(&c.facc[h]);
             PP_TRACE(P, blockIdx.x == 0 && tcount == 0, s, 2 + 2 * h);
           }
         }
@@ -536,6 +589,18 @@ __global__ void __launch_bounds__(kPPThreads, 1) plan_pp_kernel(const __grid_con
         prog[tid] = st;
       }
       for (int r = tid; r < kTileM; r += kEpiThreads) { c.G[r] = 0.f; c.q1[r] = 0.f; }
+      if (tid <= P.H) {
+        // this tile's slabs of the read-once noise tensors: ask for them now (L2) instead of paying DRAM latency per step
+        const int n0 = (tile % P.tiles_per_env) * kTileM, n1 = n0 + kTileM;
+        if (tid < P.H) {
+          const int r0 = max(n0, P.P) - P.P, r1 = n1 - P.P;
+          if (r1 > r0)
+            ptx::bulk_prefetch_l2(P.noise_r + ((static_cast<size_t>(env) * P.H + tid) * (P.N - P.P) + r0) * P.A,
+                                  static_cast<size_t>(r1 - r0) * P.A * sizeof(float));
+        } else {
+          ptx::bulk_prefetch_l2(P.noise_pi + (static_cast<size_t>(env) * P.N + n0) * P.A, static_cast<size_t>(kTileM) * P.A * sizeof(float));
+        }
+      }
       {
         __half* xhi = plane_ptr(P, c.slot, BUF_X, 0);
         __half* xlo = plane_ptr(P, c.slot, BUF_X, 1);
@@ -599,8 +664,12 @@ __global__ void __launch_bounds__(kPPThreads, 1) plan_pp_kernel(const __grid_con
           PP_TRACE(P, tr_on, s, 6 + 3 * h);
           if (t_next >= 0) pp_write_actions(P, c, tile, env, task, t_next, h * kPPHalf, kPPHalf, h == 0);
           if (is_ln && ((et.q & 1) == 0) && c.lane == 0) ptx::bulk_wait<0>();      // this block group's stores are performed
-          __threadfence();
-          ptx::fence_proxy_async_all();
+          if (!is_ln || t_next >= 0) {
+            // heads and the action pass wrote global memory through the generic proxy; LayerNorm outputs left through
+            // TMA stores only (the leaders have waited for them), for which the barrier below is all the next loads need
+            __threadfence();
+            ptx::fence_proxy_async_all();
+          }
           epi_bar_sync();
           if (tid == 0) {
             pp_arrive_leader(&c.acc_free[h], c.rank);                 // TMEM of half h may be overwritten

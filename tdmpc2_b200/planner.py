@@ -23,7 +23,7 @@ from .config import Config, get_discount
 
 # GEMM engine of the CEM-iteration kernel (include/tdmpc2_b200.h, tdmpc2_engine).  "tcgen05pp" falls back to
 # "tcgen05x2" and that to "tcgen05" inside the library when a model / shape does not fit; TDMPC2_B200_ENGINE overrides.
-DEFAULT_ENGINE = os.environ.get("TDMPC2_B200_ENGINE", "tcgen05x2")
+DEFAULT_ENGINE = os.environ.get("TDMPC2_B200_ENGINE", "tcgen05pp")
 # Wide layers (48M / 317M presets): elements of the reduction dimension accumulated in TMEM before the partial sum is
 # flushed and added in fp32 round-to-nearest.  2048 keeps the 317M preset (K = 4096) inside the parity tolerance
 # (5e-5 + 1e-5 |v|) at +6 % time; 1024 halves the error again at +20 %; 0 = one accumulation (fastest, 2.8e-4 on |v| ~ 16).
@@ -204,6 +204,14 @@ class Planner:
                 "tcgen05pp": _cabi.ENGINE_TCGEN05_PP, "tcgen05x2pf": _cabi.ENGINE_TCGEN05_2SM_PF}[engine]
         _cabi.check(self.lib.tdmpc2_planner_set_engine(self.h, code))
         self.engine = engine
+
+    @property
+    def iter_engine(self) -> str:
+        """The engine the CEM-iteration launches actually run (the requested one falls back when the model / batch
+        shape does not fit it)."""
+        code = int(self.lib.tdmpc2_planner_iter_engine(self.h))
+        return {_cabi.ENGINE_TCGEN05: "tcgen05", _cabi.ENGINE_SIMT: "simt", _cabi.ENGINE_TCGEN05_2SM: "tcgen05x2",
+                _cabi.ENGINE_TCGEN05_PP: "tcgen05pp", _cabi.ENGINE_TCGEN05_2SM_PF: "tcgen05x2pf"}.get(code, "?")
 
     @property
     def launches(self) -> int:

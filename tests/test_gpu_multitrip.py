@@ -49,10 +49,11 @@ def _two_plans(pl, obs, task, t0, prev, nz_a, nz_b):
     return (a1, m1, tr1), (a2, m2, tr2)
 
 
+@pytest.mark.parametrize("engine", ["tcgen05x2", "tcgen05pp"])
 @pytest.mark.parametrize("E", [64, 256])
-def test_many_trip_batch_is_bit_identical_to_small_runs_and_matches_oracle(E):
-    """c1 model (the bench's 5M dog-run net) on the default CTA-pair engine: E=64 -> 256 tiles (1.7 trips/CTA),
-    E=256 -> 1024 tiles (6.9 trips/CTA; exactly bench.py's c2 schedule)."""
+def test_many_trip_batch_is_bit_identical_to_small_runs_and_matches_oracle(E, engine):
+    """c1 model (the bench's 5M dog-run net) on the CTA-pair engine and on the ping-pong engine (the default for this
+    model): E=64 -> 256 tiles (1.7 trips/CTA), E=256 -> 1024 tiles (6.9 trips/CTA; exactly bench.py's c2 schedule)."""
     from oracle.plan_oracle import plan_oracle
     cfg = workload("c1", num_envs=E)
     assert E * ((cfg.num_samples + 127) // 128) > _num_sms()
@@ -61,7 +62,7 @@ def test_many_trip_batch_is_bit_identical_to_small_runs_and_matches_oracle(E):
     oracle_envs = [0, E // 3, E // 2 + 1, E - 1]
     nz_a, on_a = mixed_noise(cfg, E, oracle_envs, 100)
     nz_b, on_b = mixed_noise(cfg, E, oracle_envs, 200)
-    pl = _planner(cfg, E, "tcgen05x2", sd)
+    pl = _planner(cfg, E, engine, sd)
     big1, big2 = _two_plans(pl, obs, task, t0, prev, nz_a, nz_b)
     del pl
     # ---- bit-identity against single-trip 2-environment runs of the same environments
@@ -69,7 +70,7 @@ def test_many_trip_batch_is_bit_identical_to_small_runs_and_matches_oracle(E):
     for envs in pairs:
         idx = list(envs)
         cfg2 = workload("c1", num_envs=2)
-        pl2 = _planner(cfg2, 2, "tcgen05x2", sd)
+        pl2 = _planner(cfg2, 2, engine, sd)
         small1, small2 = _two_plans(pl2, obs[idx], None, t0[idx], prev[idx], slice_noise(nz_a, idx), slice_noise(nz_b, idx))
         for big, small, which in ((big1, small1, "first"), (big2, small2, "warm-started")):
             (ab, mb, trb), (as_, ms, trs) = big, small
