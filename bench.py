@@ -566,6 +566,7 @@ def main():
                 "h2d_bytes_per_step": int(E_local * obs_dim * 4), "d2h_bytes_per_step": int(E_total * A_ * 4)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "frac_vs_sustained": achieved / float(peaks.get("bf16_tflops_sustained", peak)),
                      "traffic": traffic, "traffic_source": traffic_src,
                      "kernel": ("plan_pp_kernel" if agent.planner.iter_engine == "tcgen05pp" else "plan_kernel<tcgen05, pair>") + " (one CEM iteration)",
                      "ms_per_launch": ms_iter, "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({peak_src}, burst)",

@@ -142,6 +142,7 @@ struct tdmpc2_planner {
   size_t l2_window_bytes = 0;       // > 0: launches carry a persisting-L2 access-policy window over the activation scratch
   float l2_hit_ratio = 1.f;
   bool pair_ok = true;              // every layer of the CEM iteration can run as cta_group::2
+  int l2hint = 0;                   // PlanParams::l2hint (TDMPC2_B200_L2HINT; experiment knob for the wide models)
   unsigned stagger = 0;             // PlanParams::stagger (TDMPC2_B200_STAGGER, clock cycles; experiment knob)
   int passes = 3;                   // 3 = fp32-parity arithmetic, 1 = declared non-parity fast mode (PlanParams::passes)
   int zb_kc0 = 0, zb_pitch = 0;     // shared-latent fold (PlanParams::zbias): K-chunks of [z | emb] folded into a per-env bias
@@ -252,6 +253,7 @@ extern "C" int tdmpc2_planner_create(const tdmpc2_dims* dims, tdmpc2_planner** o
   p->tiles_per_env = (d.num_samples + kTileM - 1) / kTileM;
   p->wide_sleep_ns = env_uint("TDMPC2_B200_WIDE_SLEEP_NS", 0);   // experiment knob
   p->stagger = env_uint("TDMPC2_B200_STAGGER", 0);
+  p->l2hint = static_cast<int>(env_uint("TDMPC2_B200_L2HINT", 0));
   p->pair_ok = true;   // fused layers and the super-chunked wide layers both run as cta_group::2
 
   // ---- packed blob layout
@@ -585,6 +587,7 @@ static int launch_plan(tdmpc2_planner* p, const PlanParams& prm, int ntiles, cud
   prm2.wide_sleep_ns = p->wide_sleep_ns;
   prm2.passes = p->passes;
   prm2.stagger = p->stagger;
+  prm2.l2hint = p->l2hint;
   static_assert(sizeof(p->attr_done) / sizeof(bool) >= 16, "attr_done slots");
   // CTA-pair (cta_group::2) launch: CEM iterations only, whole pairs of tiles of one environment
   const bool pair_engine = (p->engine == TDMPC2_ENGINE_TCGEN05_2SM || p->engine == TDMPC2_ENGINE_TCGEN05_PP ||

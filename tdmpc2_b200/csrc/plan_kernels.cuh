@@ -146,6 +146,10 @@ struct PlanParams {
   // MODE_ITER: every second CTA (pair) starts this many clock cycles late, so that neighbouring SMs are not all in their
   // GEMM phase (L2 -> SM ingest, tensor-pipe power) and all in their epilogue at the same instants.  0 = off.
   unsigned stagger;
+  // Wide models (activation planes + weights exceed L2): 1 = operand loads carry L2 eviction hints -- the per-CTA activation
+  // planes, re-read once per 512-column super-chunk with a reuse distance far beyond L2, are loaded evict-first so that
+  // they stop displacing the weight chunks that all 148 CTAs read within a short window (evict-last).  0 = evict-normal.
+  int l2hint;
 };
 
 // The layer table lives in global memory; role loops are full of asm volatile(... "memory") (TMA issue, mbarrier waits,
@@ -387,8 +391,9 @@ __device__ __forceinline__ void prod_load_a(const PlanParams& P, Ctx& c, const C
     if (c.cg2) {
       // both CTAs of the pair stream their own 128 rows; the bytes of both land on the leader's barrier
       if (c.rank == 0) ptx::mbar_expect_tx(&c.a_full[s], lo ? 2 * kASlotBytes : 2 * kAPlane);
-      ptx::tma_load_2d_2sm(tmA, &c.a_full[s], st, kc * kKch, arow_hi);
-      if (lo) ptx::tma_load_2d_2sm(tmA, &c.a_full[s], st + kAPlane, kc * kKch, arow_lo);
+      const uint64_t pol = P.l2hint ? ptx::kL2EvictFirst : ptx::kL2EvictNormal;
+      ptx::tma_load_2d_2sm(tmA, &c.a_full[s], st, kc * kKch, arow_hi, pol);
+      if (lo) ptx::tma_load_2d_2sm(tmA, &c.a_full[s], st + kAPlane, kc * kKch, arow_lo, pol);
     } else {
       ptx::mbar_expect_tx(&c.a_full[s], lo ? kASlotBytes : kAPlane);
       ptx::tma_load_2d(tmA, &c.a_full[s], st, kc * kKch, arow_hi);
@@ -397,7 +402,8 @@ __device__ __forceinline__ void prod_load_a(const PlanParams& P, Ctx& c, const C
   }
   ++c.pa_it;
 }
-__device__ __forceinline__ void prod_load_w(Ctx& c, const CUtensorMap* tmW, int Npad, int wrow, int kc, int nc, bool lo = true) {
+__device__ __forceinline__ void prod_load_w(Ctx& c, const CUtensorMap* tmW, int Npad, int wrow, int kc, int nc, bool lo = true,
+                                            bool l2hint = false) {
   const int ncols = min(kNch, Npad - nc * kNch);   // 128 or 256
   const uint32_t s = c.pw_it % c.w_ring, ph = (c.pw_it / c.w_ring) & 1;
   const long long tw = prof_clock();
@@ -410,8 +416,9 @@ __device__ __forceinline__ void prod_load_w(Ctx& c, const CUtensorMap* tmW, int 
     // its first 64 rows are consumed): the pair MMA reads B rows [0, N/2) from the leader and [N/2, N) from the peer
     if (c.rank == 0) ptx::mbar_expect_tx(&c.w_full[s], (lo ? 2 : 1) * (2 * 128 * 128));
     const int wr = wrow + nc * kNch + c.rank * (ncols / 2);
-    ptx::tma_load_2d_2sm(tmW, &c.w_full[s], st, kc * kKch, wr);
-    if (lo) ptx::tma_load_2d_2sm(tmW, &c.w_full[s], st + c.w_lo_off, kc * kKch, wr + Npad);
+    const uint64_t pol = l2hint ? ptx::kL2EvictLast : ptx::kL2EvictNormal;
+    ptx::tma_load_2d_2sm(tmW, &c.w_full[s], st, kc * kKch, wr, pol);
+    if (lo) ptx::tma_load_2d_2sm(tmW, &c.w_full[s], st + c.w_lo_off, kc * kKch, wr + Npad, pol);
   } else {
     ptx::mbar_expect_tx(&c.w_full[s], (lo ? 2 : 1) * ncols * 128);
     for (int b = 0; b < ncols / 128; ++b) {
@@ -442,7 +449,7 @@ __device__ __forceinline__ void tc_producer(const PlanParams& P, Ctx& c, const L
     prod_load_a(P, c, tmA, kc, arow_hi, arow_lo);
     for (int nc = nc0; nc < nc0 + nnc; ++nc) {
       if (skip) --skip;
-      else prod_load_w(c, tmW, ly.Npad, ly.wrow, kc, nc, P.passes != 1);
+      else prod_load_w(c, tmW, ly.Npad, ly.wrow, kc, nc, P.passes != 1, P.l2hint != 0);
     }
   }
   if (c.wpf) {

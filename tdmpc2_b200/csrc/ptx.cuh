@@ -164,9 +164,10 @@ __device__ __forceinline__ void cluster_sync() {
 // Clearing this bit of a shared::cluster address selects the even (leader) CTA of the pair.
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
 // 2D tile load into THIS CTA's smem whose transaction bytes are counted on the LEADER CTA's mbarrier.
+// L2 cache-hint operands of cp.async.bulk.tensor (the encodings createpolicy.fractional.L2::evict_* returns for fraction 1.0)
+constexpr uint64_t kL2EvictNormal = 0x1000000000000000ull, kL2EvictFirst = 0x12F0000000000000ull, kL2EvictLast = 0x14F0000000000000ull;
 __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* m, uint64_t* bar, void* smem_dst, int32_t c0,
-                                                int32_t c1) {
-  const uint64_t policy = 0x1000000000000000ull;   // L2 evict-normal
+                                                int32_t c1, uint64_t policy = kL2EvictNormal) {
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
       " [%0], [%1, {%3, %4}], [%2], %5;\n" ::"r"(smem_u32(smem_dst)),
