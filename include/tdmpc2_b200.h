@@ -35,8 +35,9 @@
 extern "C" {
 #endif
 
-#define TDMPC2_B200_ABI_VERSION 4   /* 2: tdmpc2_weights.termination, dims.episodic = 1 accepted; 3: tdmpc2_planner_set_l2_persist;
-                                       4: tdmpc2_planner_set_passes (declared non-parity fast mode) */
+#define TDMPC2_B200_ABI_VERSION 5   /* 2: tdmpc2_weights.termination, dims.episodic = 1 accepted; 3: tdmpc2_planner_set_l2_persist;
+                                       4: tdmpc2_planner_set_passes (declared non-parity fast mode), set_kseg, iter_engine;
+                                       5: pixel encoder (tdmpc2_pixel_*), tdmpc2_plan_prologue_latent, dims.num_enc_layers = 0 */
 #define TDMPC2_MAX_ENC_LAYERS 8
 
 typedef enum tdmpc2_status {
@@ -170,6 +171,35 @@ int tdmpc2_pack_weights(tdmpc2_planner* p, const tdmpc2_weights* w, void* stream
 int tdmpc2_plan_prologue(tdmpc2_planner* p, const float* obs, const int32_t* task,
                          const uint8_t* t0, const float* prev_mean,
                          const float* noise_prior, void* stream);
+/* The same with the latent given: z [E, L] replaces encode(obs, task).  For models without a state encoder
+ * (dims.num_enc_layers = 0; cfg.obs == 'rgb': z comes from tdmpc2_pixel_encode). */
+int tdmpc2_plan_prologue_latent(tdmpc2_planner* p, const float* z, const int32_t* task,
+                                const uint8_t* t0, const float* prev_mean,
+                                const float* noise_prior, void* stream);
+
+/* ---- pixel observations (cfg.obs == 'rgb') ------------------------------- */
+/* Replaces WorldModel.encode for obs type 'rgb' (world_model.py:103-112 -> layers.conv, layers.py:136-150): ShiftAug
+ * (layers.py:36-59; part of the nn.Sequential, hence applied at inference too), PixelPreprocess (:62-71), four
+ * Conv2d (7/2, 5/2, 3/2, 3/1) with ReLU between them, Flatten, SimNorm.  64 x 64 frames; latent_dim = 16 * num_channels. */
+typedef struct tdmpc2_pixel_dims {
+  int32_t num_envs;        /* E                                                          */
+  int32_t in_channels;     /* cfg.obs_shape['rgb'][0] (3 x frame stack)                  */
+  int32_t num_channels;    /* cfg.num_channels (config.yaml:58), a multiple of 8         */
+  int32_t simnorm_dim;     /* cfg.simnorm_dim                                            */
+} tdmpc2_pixel_dims;
+typedef struct tdmpc2_conv_weights {   /* device pointers into the state dict: _encoder.rgb.{2,4,6,8}.{weight,bias} */
+  const float* weight[4];              /* [out, in, k, k] as nn.Conv2d stores them       */
+  const float* bias[4];
+} tdmpc2_conv_weights;
+typedef struct tdmpc2_pixel_encoder tdmpc2_pixel_encoder;
+int tdmpc2_pixel_encoder_create(const tdmpc2_pixel_dims* dims, tdmpc2_pixel_encoder** out);
+void tdmpc2_pixel_encoder_destroy(tdmpc2_pixel_encoder* e);
+int tdmpc2_pixel_encoder_workspace_bytes(const tdmpc2_pixel_encoder* e, size_t* out);
+/*   frames [E, C, 64, 64] fp32 in 0..255; shift [E, 2] = the (x, y) values torch.randint(0, 7) draws in ShiftAug
+ *   (layers.py:55), as floats; grid_base [64] = torch.linspace(-1 + 1/70, 1 - 1/70, 70)[:64] (layers.py:51);
+ *   z_out [E, 16 * num_channels]; workspace: caller-owned, tdmpc2_pixel_encoder_workspace_bytes. */
+int tdmpc2_pixel_encode(tdmpc2_pixel_encoder* e, void* workspace, const tdmpc2_conv_weights* w, const float* frames,
+                        const float* shift, const float* grid_base, float* z_out, void* stream);
 
 /* Replaces ONE pass of the loop tdmpc2.py:173-197 (sample, _estimate_value
  * :122-136, topk, MPPI weights, refit) for all E environments.

@@ -45,6 +45,9 @@ CASES = {
                       [(True, False, None, 300), (False, False, None, 301), (False, True, None, 302)]),
     "c1_dog5m_episodic": ("c1", {"episodic": True}, 2, True, 1.0,
                           [(True, False, None, 6), (False, False, None, 7)]),
+    # cfg.obs == 'rgb': layers.conv encoder with ShiftAug inside encode() (layers.py:36-71,136-150)
+    "tiny_rgb": ("tiny-rgb", {}, 14, True, 1.0,
+                 [(True, False, None, 400), (False, False, None, 401), (False, True, None, 402)]),
 }
 
 
@@ -63,7 +66,8 @@ def main(only=None):
             term_bias = balance_termination(cfg, sd)
         agent = rh.build_agent(cfg, sd)
         g = torch.Generator().manual_seed(1000 + wseed)
-        obs_dim = cfg.obs_shape["state"][0]
+        rgb = cfg.get("obs", "state") == "rgb"
+        obs_dim = None if rgb else cfg.obs_shape["state"][0]
         rec = dict(workload=wl, overrides=repr(over), weight_seed=wseed, perturb=perturb, emb_scale=emb_scale,
                    weight_checksum=state_dict_checksum(sd), n_calls=len(calls),
                    torch_version=torch.__version__)
@@ -71,7 +75,8 @@ def main(only=None):
             rec["term_bias"] = term_bias
         prev_mean = torch.zeros(cfg.horizon, cfg.action_dim)
         for i, (t0, ev, task, seed) in enumerate(calls):
-            obs = torch.randn(obs_dim, generator=g)
+            obs = (torch.randint(0, 256, tuple(cfg.obs_shape["rgb"]), generator=g).float() if rgb
+                   else torch.randn(obs_dim, generator=g))
             out = rh.run_plan(agent, obs, seed=seed, t0=t0, eval_mode=ev, task=task, prev_mean=prev_mean)
             rec.update({f"c{i}_obs": obs.numpy(), f"c{i}_t0": t0, f"c{i}_eval_mode": ev,
                         f"c{i}_task": -1 if task is None else task, f"c{i}_seed": seed,

@@ -9,7 +9,8 @@ It restates, in plain fp32 PyTorch-on-CPU, the algorithm of the reference
 
   plan_oracle        <- TDMPC2._plan              tdmpc2/tdmpc2.py:138-206
   estimate_value     <- TDMPC2._estimate_value    tdmpc2/tdmpc2.py:122-136
-  OracleModel.encode <- WorldModel.encode         common/world_model.py:103-112
+  OracleModel.encode <- WorldModel.encode         common/world_model.py:103-112  (obs 'rgb': layers.conv / ShiftAug /
+                                                  PixelPreprocess, common/layers.py:36-71,136-150)
   OracleModel.task_emb <- WorldModel.task_emb     common/world_model.py:88-101  (nn.Embedding max_norm=1, :21)
   OracleModel.next   <- WorldModel.next           common/world_model.py:114-121
   OracleModel.reward <- WorldModel.reward         common/world_model.py:123-130
@@ -61,12 +62,15 @@ class PlanNoise:
     qidx: torch.Tensor
     expo: torch.Tensor
     final: torch.Tensor
+    shift: Optional[torch.Tensor] = None   # [E, 2] pixel models only: ShiftAug's randint(0, 7) (x, y), layers.py:55 -- the FIRST draw
 
     def to(self, device) -> "PlanNoise":
-        return PlanNoise(*(getattr(self, f).to(device) for f in ("prior", "r", "pi", "qidx", "expo", "final")))
+        return PlanNoise(*(getattr(self, f).to(device) for f in ("prior", "r", "pi", "qidx", "expo", "final")),
+                         None if self.shift is None else self.shift.to(device))
 
     def env(self, e: int) -> "PlanNoise":
-        return PlanNoise(*(getattr(self, f)[e:e + 1] for f in ("prior", "r", "pi", "qidx", "expo", "final")))
+        return PlanNoise(*(getattr(self, f)[e:e + 1] for f in ("prior", "r", "pi", "qidx", "expo", "final")),
+                         None if self.shift is None else self.shift[e:e + 1])
 
 
 def draw_noise(cfg, seed: int, num_envs: int, eval_mode: bool = False) -> PlanNoise:
@@ -76,8 +80,12 @@ def draw_noise(cfg, seed: int, num_envs: int, eval_mode: bool = False) -> PlanNo
     H, N, P, A, I, K = (cfg.horizon, cfg.num_samples, cfg.num_pi_trajs, cfg.action_dim,
                         cfg.iterations, cfg.num_elites)
     out: Dict[str, List[torch.Tensor]] = {k: [] for k in ("prior", "r", "pi", "qidx", "expo", "final")}
+    rgb = cfg.get("obs", "state") == "rgb"
+    shifts = []
     for e in range(num_envs):
         g = torch.Generator(device="cpu").manual_seed(seed + e)
+        if rgb:      # ShiftAug.forward inside encode() (layers.py:55): same call, same dtype, n = 1
+            shifts.append(torch.randint(0, 2 * 3 + 1, size=(1, 1, 1, 2), dtype=torch.float32, generator=g).view(2))
         prior = torch.zeros(H, P, A)
         if P > 0:
             for t in range(H):                       # H-1 loop draws + the final pi() (tdmpc2.py:157-160)
@@ -92,7 +100,7 @@ def draw_noise(cfg, seed: int, num_envs: int, eval_mode: bool = False) -> PlanNo
         for k, v in (("prior", prior), ("r", torch.stack(r)), ("pi", torch.stack(pi)),
                      ("qidx", torch.stack(qidx)), ("expo", expo), ("final", final)):
             out[k].append(v)
-    return PlanNoise(**{k: torch.stack(v) for k, v in out.items()})
+    return PlanNoise(**{k: torch.stack(v) for k, v in out.items()}, shift=torch.stack(shifts) if rgb else None)
 
 
 # --------------------------------------------------------------------------- model
@@ -152,10 +160,37 @@ class OracleModel:
             w = w * (1.0 / (n + 1e-7))
         return torch.cat([x, w.unsqueeze(0).repeat(x.shape[0], 1)], dim=-1)
 
-    def encode(self, obs: torch.Tensor, task: Optional[int]) -> torch.Tensor:
+    def encode(self, obs: torch.Tensor, task: Optional[int], shift: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if self.cfg.get("obs", "state") == "rgb":
+            return self.encode_rgb(obs, shift)
         if self.cfg.multitask:
             obs = self.task_emb(obs, task)
         return self._mlp("_encoder.state", obs, "simnorm")
+
+    def encode_rgb(self, obs: torch.Tensor, shift: torch.Tensor) -> torch.Tensor:
+        """layers.conv (layers.py:136-150) on obs [n, C, 64, 64]: ShiftAug (:36-59) with its randint made explicit
+        (`shift` [n, 2], values 0..6), PixelPreprocess (:62-71), 4 x Conv2d (+ ReLU between), Flatten, SimNorm."""
+        pad = 3
+        x = obs.float()
+        n, _, h, w = x.size()
+        assert h == w == 64                                                          # layers.py:141
+        x = F.pad(x, (pad,) * 4, "replicate")
+        eps = 1.0 / (h + 2 * pad)
+        arange = torch.linspace(-1.0 + eps, 1.0 - eps, h + 2 * pad, dtype=x.dtype)[:h]
+        arange = arange.unsqueeze(0).repeat(h, 1).unsqueeze(2)
+        base_grid = torch.cat([arange, arange.transpose(1, 0)], dim=2)
+        base_grid = base_grid.unsqueeze(0).repeat(n, 1, 1, 1)
+        sh = shift.to(x.dtype).view(n, 1, 1, 2).clone()
+        sh *= 2.0 / (h + 2 * pad)
+        x = F.grid_sample(x, base_grid + sh, padding_mode="zeros", align_corners=False)
+        x = x.div(255.).sub(0.5)
+        for i, (idx, stride) in enumerate(((2, 2), (4, 2), (6, 2), (8, 1))):
+            x = F.conv2d(x, self.sd[f"_encoder.rgb.{idx}.weight"], self.sd[f"_encoder.rgb.{idx}.bias"], stride=stride)
+            if i < 3:
+                x = F.relu(x)
+        x = x.flatten(1)
+        shp = x.shape                                                                # SimNorm, layers.py:84-88
+        return F.softmax(x.view(*shp[:-1], -1, self.cfg.simnorm_dim), dim=-1).view(*shp)
 
     def next(self, z, a, task):
         if self.cfg.multitask:
@@ -267,7 +302,10 @@ def plan_one(model: OracleModel, obs, task, t0: bool, prev_mean, noise: PlanNois
     """One reference `_plan` call (tdmpc2.py:138-206) with explicit noise; E == 1."""
     cfg = model.cfg
     H, N, P, A, K = cfg.horizon, cfg.num_samples, cfg.num_pi_trajs, cfg.action_dim, cfg.num_elites
-    z = model.encode(obs.view(1, -1), task)
+    if cfg.get("obs", "state") == "rgb":
+        z = model.encode(obs.unsqueeze(0), task, noise.shift[0:1])                   # tdmpc2.py:111 unsqueezes; :153 encodes
+    else:
+        z = model.encode(obs.view(1, -1), task)
     z0 = z
     pi_actions = torch.zeros(H, P, A)
     if P > 0:

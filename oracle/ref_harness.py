@@ -171,7 +171,9 @@ def run_plan(agent, obs: torch.Tensor, *, seed: int, t0: bool, eval_mode: bool,
     torch.topk = spy
     try:
         tk = None if task is None else torch.tensor([task])
-        a = agent._plan(obs.view(1, -1), t0=t0, eval_mode=eval_mode, task=tk)
+        # tdmpc2.py:111: act() unsqueezes the observation -- [1, obs_dim] for states, [1, C, 64, 64] for pixels
+        o = obs.unsqueeze(0) if agent.cfg.get("obs", "state") == "rgb" else obs.view(1, -1)
+        a = agent._plan(o, t0=t0, eval_mode=eval_mode, task=tk)
     finally:
         torch.topk = real_topk
     return dict(action=a.clone(), mean=agent._prev_mean.detach().clone(),

@@ -87,7 +87,7 @@ def get_discount(cfg: Config, episode_length: int) -> float:
     return min(max((frac - 1) / frac, cfg.discount_min), cfg.discount_max)
 
 
-def make_cfg(*, obs_dim: int, action_dim: int, model_size: Optional[int] = 5,
+def make_cfg(*, obs_dim: int = 0, action_dim: int, model_size: Optional[int] = 5,
              episode_length: int = 500, tasks: Optional[List[str]] = None,
              action_dims: Optional[List[int]] = None,
              episode_lengths: Optional[List[int]] = None,
@@ -115,7 +115,10 @@ def make_cfg(*, obs_dim: int, action_dim: int, model_size: Optional[int] = 5,
     else:
         kw["tasks"] = [overrides.get("task", "dog-run")]
         kw["task_dim"] = 0
-    kw["obs_shape"] = {"state": (obs_dim,)}
+    if overrides.get("obs", "state") == "rgb":       # envs/dmcontrol.py:108: 64 x 64 frames, 3 channels x frame stack
+        kw["obs_shape"] = {"rgb": (int(overrides.pop("obs_channels", 9)), 64, 64)}
+    else:
+        kw["obs_shape"] = {"state": (obs_dim,)}
     kw["action_dim"] = action_dim
     kw["episode_length"] = episode_length
     kw.update(overrides)
@@ -165,6 +168,11 @@ def workload(name: str, **overrides: Any) -> Config:
                   enc_dim=640, mlp_dim=1152, latent_dim=576, num_enc_layers=2, num_q=2,
                   num_envs=2, num_samples=256, num_elites=16, num_pi_trajs=8,
                   horizon=2, iterations=2)
+    elif name == "tiny-rgb":  # test-sized pixel-observation model: layers.conv encoder, latent = 16 * num_channels
+        kw = dict(obs="rgb", obs_channels=6, action_dim=4, model_size=None, task="tiny-rgb",
+                  num_channels=8, enc_dim=64, mlp_dim=128, latent_dim=128, num_enc_layers=2, num_q=3,
+                  num_envs=2, num_samples=128, num_elites=16, num_pi_trajs=8,
+                  horizon=3, iterations=3)
     elif name == "tiny-mt":  # test-sized multi-task model
         kw = dict(obs_dim=11, action_dim=5, model_size=None, task="tiny-mt",
                   tasks=[f"t{i}" for i in range(4)], action_dims=[5, 3, 4, 2],

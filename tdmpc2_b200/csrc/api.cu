@@ -16,6 +16,7 @@
 #include "../../include/tdmpc2_b200.h"
 #include "plan_kernels.cuh"
 #include "plan_pp.cuh"
+#include "pixel_encoder.cuh"
 
 using namespace tdmpc2;
 
@@ -195,7 +196,7 @@ extern "C" int tdmpc2_planner_create(const tdmpc2_dims* dims, tdmpc2_planner** o
   if (d.episodic && d.task_dim > 0)   // WorldModel.termination asserts task is None (world_model.py:136)
     return fail(TDMPC2_ERR_UNSUPPORTED, "episodic (termination head) models are single-task in the reference");
   if (d.num_envs < 1 || d.num_samples < 1 || d.horizon < 1 || d.iterations < 1 || d.obs_dim < 1 || d.action_dim < 1 ||
-      d.latent_dim < 1 || d.mlp_dim < 1 || d.enc_dim < 1 || d.num_enc_layers < 1 || d.num_q < 2 || d.num_bins < 0 ||
+      d.latent_dim < 1 || d.mlp_dim < 1 || d.enc_dim < 1 || d.num_enc_layers < 0 || d.num_q < 2 || d.num_bins < 0 ||
       d.task_dim < 0 || d.num_tasks < 1)
     return fail(TDMPC2_ERR_INVALID, "non-positive dimension");
   if (d.num_bins < 2)   // math.two_hot_inv's num_bins == 0 (raw) / == 1 (symexp only) regression heads (math.py:76-79)
@@ -224,10 +225,11 @@ extern "C" int tdmpc2_planner_create(const tdmpc2_dims* dims, tdmpc2_planner** o
   const int D = L + T + A;
   bool ok = true;
   auto add = [&](int K, int N, bool ln) { int i = add_layer(p, K, N, ln); if (i < 0) ok = false; return i; };
-  // encoder: mlp(obs+T, n_hidden*[enc_dim], L, act=SimNorm)  (layers.py:157-159)
-  p->num_enc = n_hidden + 1;
+  // encoder: mlp(obs+T, n_hidden*[enc_dim], L, act=SimNorm)  (layers.py:157-159); num_enc_layers == 0: the model has no
+  // state encoder (pixel observations: tdmpc2_pixel_encode + tdmpc2_plan_prologue_latent supply the latent)
+  p->num_enc = d.num_enc_layers == 0 ? 0 : n_hidden + 1;
   p->li_enc = static_cast<int>(p->layers.size());
-  { int k = d.obs_dim + T; for (int i = 0; i < n_hidden; ++i) { add(k, d.enc_dim, true); k = d.enc_dim; } add(k, L, true); }
+  if (p->num_enc > 0) { int k = d.obs_dim + T; for (int i = 0; i < n_hidden; ++i) { add(k, d.enc_dim, true); k = d.enc_dim; } add(k, L, true); }
   p->li_dyn = static_cast<int>(p->layers.size()); add(D, M, true); add(M, M, true); add(M, L, true);
   p->li_rew = static_cast<int>(p->layers.size()); add(D, M, true); add(M, M, true); add(M, B, false);
   p->li_pi = static_cast<int>(p->layers.size()); add(L + T, M, true); add(M, M, true);
@@ -674,12 +676,14 @@ static int ready(tdmpc2_planner* p) {
   return 0;
 }
 
-extern "C" int tdmpc2_plan_prologue(tdmpc2_planner* p, const float* obs, const int32_t* task, const uint8_t* t0,
-                                    const float* prev_mean, const float* noise_prior, void* stream_) {
+// obs != nullptr: z = encode(obs, task) through the state encoder; z_in != nullptr: the latent is given (pixel models)
+static int prologue_impl(tdmpc2_planner* p, const float* obs, const float* z_in, const int32_t* task, const uint8_t* t0,
+                         const float* prev_mean, const float* noise_prior, void* stream_) {
   int rc = ready(p);
   if (rc) return rc;
   const tdmpc2_dims& d = p->d;
-  if (!obs || !t0 || !prev_mean) return fail(TDMPC2_ERR_INVALID, "null argument");
+  if ((!obs && !z_in) || !t0 || !prev_mean) return fail(TDMPC2_ERR_INVALID, "null argument");
+  if (obs && p->num_enc == 0) return fail(TDMPC2_ERR_STATE, "this planner was created without a state encoder (num_enc_layers = 0): use tdmpc2_plan_prologue_latent");
   if (d.task_dim > 0 && !task) return fail(TDMPC2_ERR_INVALID, "multi-task model needs task indices");
   if (d.num_pi_trajs > 0 && !noise_prior) return fail(TDMPC2_ERR_INVALID, "noise_prior is required when num_pi_trajs > 0");
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
@@ -691,10 +695,14 @@ extern "C" int tdmpc2_plan_prologue(tdmpc2_planner* p, const float* obs, const i
   p->launches += 1;
   PlanParams prm = p->base;
   prm.task = p->cur_task;
-  prm.obs = obs;
-  prm.mode = MODE_ENCODE;
-  prm.ntiles = (d.num_envs + kTileM - 1) / kTileM;
-  if ((rc = launch_plan(p, prm, prm.ntiles, st))) return rc;
+  if (obs) {
+    prm.obs = obs;
+    prm.mode = MODE_ENCODE;
+    prm.ntiles = (d.num_envs + kTileM - 1) / kTileM;
+    if ((rc = launch_plan(p, prm, prm.ntiles, st))) return rc;
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(p->base.z, z_in, static_cast<size_t>(d.num_envs) * d.latent_dim * 4, cudaMemcpyDeviceToDevice, st));
+  }
   if (p->zb_kc0 > 0) {
     // shared-latent fold: [z | emb] . W of reward.0 / dynamics.0, once per plan() (z is the same in every CEM iteration)
     const dim3 grid((p->zb_pitch + kZbCols - 1) / kZbCols, (d.num_envs + kZbEnvs - 1) / kZbEnvs, 2);
@@ -711,6 +719,66 @@ extern "C" int tdmpc2_plan_prologue(tdmpc2_planner* p, const float* obs, const i
     prm.ntiles = (d.num_envs + per - 1) / per;
     if ((rc = launch_plan(p, prm, prm.ntiles, st))) return rc;
   }
+  return 0;
+}
+
+extern "C" int tdmpc2_plan_prologue(tdmpc2_planner* p, const float* obs, const int32_t* task, const uint8_t* t0,
+                                    const float* prev_mean, const float* noise_prior, void* stream_) {
+  if (!obs) return fail(TDMPC2_ERR_INVALID, "null argument");
+  return prologue_impl(p, obs, nullptr, task, t0, prev_mean, noise_prior, stream_);
+}
+extern "C" int tdmpc2_plan_prologue_latent(tdmpc2_planner* p, const float* z, const int32_t* task, const uint8_t* t0,
+                                           const float* prev_mean, const float* noise_prior, void* stream_) {
+  if (!z) return fail(TDMPC2_ERR_INVALID, "null argument");
+  return prologue_impl(p, nullptr, z, task, t0, prev_mean, noise_prior, stream_);
+}
+
+// ------------------------------------------------------------------------------------ pixel encoder (cfg.obs == 'rgb')
+struct tdmpc2_pixel_encoder {
+  tdmpc2_pixel_dims d;
+  size_t ws_bytes = 0, smem = 0;
+  bool attr_done = false;
+};
+
+extern "C" int tdmpc2_pixel_encoder_create(const tdmpc2_pixel_dims* dims, tdmpc2_pixel_encoder** out) {
+  if (!dims || !out) return fail(TDMPC2_ERR_INVALID, "null argument");
+  const tdmpc2_pixel_dims& d = *dims;
+  if (d.num_envs < 1 || d.in_channels < 1 || d.num_channels < 8 || d.num_channels % 8 != 0 || d.simnorm_dim < 1 ||
+      (16 * d.num_channels) % d.simnorm_dim != 0)
+    return fail(TDMPC2_ERR_INVALID, "pixel encoder: num_channels must be a positive multiple of 8 and simnorm_dim must divide 16 * num_channels");
+  int num_sms = 0;
+  int rc = check_device(&num_sms);
+  if (rc) return rc;
+  tdmpc2_pixel_encoder* e = new tdmpc2_pixel_encoder();
+  e->d = d;
+  e->ws_bytes = align_up(static_cast<size_t>(d.num_envs) * d.num_channels * kPixO1 * kPixO1 * 4, 256);
+  const size_t stage = static_cast<size_t>(d.in_channels) * kPixHW * kPixHW;
+  const size_t maps = static_cast<size_t>(d.num_channels) * (kPixO2 * kPixO2 + kPixO3 * kPixO3 + kPixO4 * kPixO4);
+  e->smem = std::max(stage, maps) * 4;
+  if (e->smem > 227 * 1024) { delete e; return fail(TDMPC2_ERR_INVALID, "pixel encoder: %d input channels do not fit shared memory", d.in_channels); }
+  *out = e;
+  return 0;
+}
+extern "C" void tdmpc2_pixel_encoder_destroy(tdmpc2_pixel_encoder* e) { delete e; }
+extern "C" int tdmpc2_pixel_encoder_workspace_bytes(const tdmpc2_pixel_encoder* e, size_t* out) {
+  if (!e || !out) return fail(TDMPC2_ERR_INVALID, "null argument");
+  *out = e->ws_bytes;
+  return 0;
+}
+extern "C" int tdmpc2_pixel_encode(tdmpc2_pixel_encoder* e, void* workspace, const tdmpc2_conv_weights* w, const float* frames,
+                                   const float* shift, const float* grid_base, float* z_out, void* stream_) {
+  if (!e || !workspace || !w || !frames || !shift || !grid_base || !z_out) return fail(TDMPC2_ERR_INVALID, "null argument");
+  for (int i = 0; i < 4; ++i) if (!w->weight[i] || !w->bias[i]) return fail(TDMPC2_ERR_INVALID, "pixel encoder: null conv weight");
+  PixelParams P{};
+  P.frames = frames; P.shift = shift; P.grid = grid_base; P.scratch = static_cast<float*>(workspace); P.z = z_out;
+  for (int i = 0; i < 4; ++i) { P.w[i] = w->weight[i]; P.b[i] = w->bias[i]; }
+  P.E = e->d.num_envs; P.C = e->d.in_channels; P.nc = e->d.num_channels; P.simnorm = e->d.simnorm_dim;
+  if (!e->attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(pixel_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(e->smem)));
+    e->attr_done = true;
+  }
+  pixel_encode_kernel<<<P.E, kPixThreads, e->smem, static_cast<cudaStream_t>(stream_)>>>(P);
+  CUDA_TRY(cudaGetLastError());
   return 0;
 }
 

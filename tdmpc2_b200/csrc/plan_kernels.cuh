@@ -830,7 +830,7 @@ __device__ __forceinline__ void epi_pass2_fast(const PlanParams& P, Ctx& c, cons
   // staging tiles: two per group aliasing the idle W ring -- or, when the W ring is busy prefetching the next layer
   // (c.wpf), ONE per group in the idle A ring, re-used once the previous store has read it
   uint8_t* stg = c.wpf ? c.stage_base + et.grp * kStgBuf : c.stage_base + kWRingOff + et.grp * (2 * kStgBuf);
-  const bool leader = (et.q == 0) && (c.lane == 0);
+  const bool lead_warp = (et.q == 0);   // one elected lane of the group's first warp issues, commits and waits (cheap in SASS: no waterfall)
   const CUtensorMap* tmD = (ea.dstbuf == BUF_X) ? &P.tmXs : &P.tmHs;
   const uint32_t swz = static_cast<uint32_t>((et.row >> 1) & 3);
   const int row_hi = plane_row0(P, c.slot, ea.dstbuf, 0), row_lo = plane_row0(P, c.slot, ea.dstbuf, 1);
@@ -841,7 +841,7 @@ __device__ __forceinline__ void epi_pass2_fast(const PlanParams& P, Ctx& c, cons
     uint8_t* buf = c.wpf ? stg : stg + (blk & 1) * kStgBuf;
     const uint32_t rowaddr = ptx::smem_u32(buf) + static_cast<uint32_t>(et.row) * 64u;
     if (!c.wpf && blk >= 2) {                                     // buffer reuse: its previous store must have read it
-      if (leader) ptx::bulk_wait_read<1>();
+      if (lead_warp && ptx::elect_one()) ptx::bulk_wait_read<1>();
       group_bar_sync(et.grp);
     }
 #pragma unroll
@@ -895,7 +895,7 @@ __device__ __forceinline__ void epi_pass2_fast(const PlanParams& P, Ctx& c, cons
       }
       if (c.wpf && sub == 0 && blk >= 1) {
         // single staging tile: the previous block's store was issued a whole block of math ago, so this wait is short
-        if (leader) ptx::bulk_wait_read<0>();
+        if (lead_warp && ptx::elect_one()) ptx::bulk_wait_read<0>();
         group_bar_sync(et.grp);
       }
 #pragma unroll
@@ -907,13 +907,13 @@ __device__ __forceinline__ void epi_pass2_fast(const PlanParams& P, Ctx& c, cons
     }
     ptx::fence_proxy_async_smem();
     group_bar_sync(et.grp);
-    if (leader) {
+    if (lead_warp && ptx::elect_one()) {
       ptx::tma_store_2d(tmD, buf, ea.dst_col0 + c0, row_hi);
       if (!FAST) ptx::tma_store_2d(tmD, buf + kStgPlane, ea.dst_col0 + c0, row_lo);
       ptx::bulk_commit();
     }
   }
-  if (leader) ptx::bulk_wait<0>();                               // stores performed before the layer is published
+  if (lead_warp && ptx::elect_one()) ptx::bulk_wait<0>();                               // stores performed before the layer is published
 }
 
 // bias + LayerNorm + (Mish | SimNorm); planes and/or fp32 rows out.  16 epilogue warps: 4 lane quarters x 4
@@ -1440,14 +1440,14 @@ __device__ __forceinline__ void wide_pass2_tma(const PlanParams& P, Ctx& c, cons
   uint8_t* inb = c.stage_base + kWRingOff + et.grp * (2 * kStgBuf);  // 2 x 16 KiB raw blocks
   uint8_t* stg = c.stage_base + et.grp * kStgBuf;                    // 16 KiB output tile (hi 8 KiB | lo 8 KiB)
   uint64_t* bars = c.rawb + et.grp * 2;
-  const bool leader = (et.q == 0) && (c.lane == 0);
+  const bool lead_warp = (et.q == 0);   // one elected lane of the group's first warp issues, commits and waits (cheap in SASS: no waterfall)
   const CUtensorMap* tmD = (ea.dstbuf == BUF_X) ? &P.tmXs : &P.tmHs;
   const uint32_t swz = static_cast<uint32_t>((et.row >> 1) & 3);
   const int row_hi = plane_row0(P, c.slot, ea.dstbuf, 0), row_lo = plane_row0(P, c.slot, ea.dstbuf, 1);
   const float2 rstd2 = f2s(rstd), nmr2 = f2s(nmr);
   const uint32_t rowaddr = ptx::smem_u32(stg) + static_cast<uint32_t>(et.row) * 64u;
   uint32_t it = c.rb_it;                              // blocks consumed by this group so far: buffer = it & 1
-  if (leader) {
+  if (lead_warp && ptx::elect_one()) {
     for (int j = 0; j < 2; ++j) {
       const int b = et.grp + 4 * j;
       if (b < nblk) {
@@ -1460,7 +1460,7 @@ __device__ __forceinline__ void wide_pass2_tma(const PlanParams& P, Ctx& c, cons
   for (int b = et.grp; b < nblk; b += kEpiGroups, ++it) {
     const uint32_t ib = it & 1u;
     // the previous block's TMA store has finished reading the output tile
-    if (leader) ptx::bulk_wait_read<0>();
+    if (lead_warp && ptx::elect_one()) ptx::bulk_wait_read<0>();
     group_bar_sync(et.grp);
     ptx::mbar_wait(&bars[ib], (it >> 1) & 1u);
     const float* blk = reinterpret_cast<const float*>(inb + ib * kStgBuf) + et.row;     // element (col, row) at blk[col * 128]
@@ -1490,7 +1490,7 @@ __device__ __forceinline__ void wide_pass2_tma(const PlanParams& P, Ctx& c, cons
     }
     ptx::fence_proxy_async_smem();
     group_bar_sync(et.grp);                            // tile complete; every thread of the group is done with raw buffer ib
-    if (leader) {
+    if (lead_warp && ptx::elect_one()) {
       ptx::tma_store_2d(tmD, stg, ea.dst_col0 + b * 32, row_hi);
       ptx::tma_store_2d(tmD, stg + kStgPlane, ea.dst_col0 + b * 32, row_lo);
       ptx::bulk_commit();
@@ -1502,7 +1502,7 @@ __device__ __forceinline__ void wide_pass2_tma(const PlanParams& P, Ctx& c, cons
     }
   }
   c.rb_it = it;
-  if (leader) ptx::bulk_wait<0>();                                 // stores performed before the layer is published
+  if (lead_warp && ptx::elect_one()) ptx::bulk_wait<0>();                                 // stores performed before the layer is published
 }
 
 // General fallback of the normalise pass (fp32 row output, ragged N, unaligned destination): plain loads of the raw

@@ -229,7 +229,7 @@ __device__ __forceinline__ void pp_epi_ln(const PlanParams& P, PPCtx& c, const P
   // ---- pass 2: normalise, activate, split, stage, TMA-store one 64 x 16 block per 16 columns
   uint8_t* buf = c.base + kPPStgOff + et.bg * kPPStgBuf;
   const uint32_t rowaddr = ptx::smem_u32(buf) + static_cast<uint32_t>(et.row) * (kPPStgCols * 2u);
-  const bool leader = ((et.q & 1) == 0) && (c.lane == 0);
+  const bool lead_warp = (et.q & 1) == 0;              // of the two warps that share a block; one elected lane of it issues
   const CUtensorMap* tmD = (st.dstbuf == BUF_X) ? &P.tmXs64 : &P.tmHs64;
   const int row_hi = plane_row0(P, c.slot, st.dstbuf, 0) + h * kPPHalf, row_lo = plane_row0(P, c.slot, st.dstbuf, 1) + h * kPPHalf;
   for (int nc = 0; nc < nnc; ++nc) {
@@ -282,7 +282,7 @@ __device__ __forceinline__ void pp_epi_ln(const PlanParams& P, PPCtx& c, const P
       }
       if (nc > 0 || sub > 0) {
         // single staging block per group: its previous store (issued a whole block of math ago) must have read it
-        if (leader) ptx::bulk_wait_read<0>();
+        if (lead_warp && ptx::elect_one()) ptx::bulk_wait_read<0>();   // (the same lane issues, commits and waits)
         pp_group_sync(et.bg);
       }
 #pragma unroll
@@ -292,7 +292,7 @@ __device__ __forceinline__ void pp_epi_ln(const PlanParams& P, PPCtx& c, const P
       }
       ptx::fence_proxy_async_smem();
       pp_group_sync(et.bg);
-      if (leader) {
+      if (lead_warp && ptx::elect_one()) {
         ptx::tma_store_2d(tmD, buf, c0 + sub, row_hi);      // LN outputs always start at column 0 of their buffer
         ptx::tma_store_2d(tmD, buf + kPPStgPlane, c0 + sub, row_lo);
         ptx::bulk_commit();
@@ -456,6 +456,38 @@ __global__ void __launch_bounds__(kPPThreads, 1) plan_pp_kernel(const __grid_con
         const PPStep* prog = c.prog + (tcount & 1) * kPPMaxSteps;
         for (int s = 0; s < nsteps; ++s) {
           for (int h = 0; h < 2; ++h) {
+            int npre = 0;
+#ifdef TDMPC2_PP_PREFETCH
+            // Experiment (off by default: measured slower, profiles/README.md): the weights of (h, s) do not depend on the
+            // epilogue that is still producing its activation planes, so while waiting for act_ready refill every weight
+            // slot the MMAs release with the head of this half's weight stream (not for the first half-step of a tile,
+            // whose layer program is published by that very barrier).  Non-blocking probes: try_wait may suspend.
+            if (s > 0 || h > 0) {
+              const PPStep st0 = prog[s];
+              const LayerDev& ly0 = LY[st0.li];
+              const CUtensorMap* tmW0 = &P.tmW[ly0.wmap];
+              const int nnc0 = (ly0.Npad + kNch - 1) / kNch, maxpre = min(kPPWRing, (ly0.Kpad / kKch) * nnc0);
+              while (true) {
+                if (npre < maxpre) {
+                  const uint32_t sl = pw_it % kPPWRing, ph = (pw_it / kPPWRing) & 1;
+                  if (__any_sync(0xffffffffu, ptx::mbar_test_wait(&c.w_empty[sl], ph ^ 1))) {
+                    const int kc = npre / nnc0, nc = npre % nnc0;
+                    const int ncols = min(kNch, ly0.Npad - nc * kNch);
+                    uint8_t* dst = c.base + kPPWOff + sl * kPPWSlot;
+                    const int wr = ly0.wrow + nc * kNch + c.rank * (ncols / 2);
+                    if (ptx::elect_one()) {
+                      if (c.rank == 0) ptx::mbar_expect_tx(&c.w_full[sl], 2 * kPPWSlot);
+                      ptx::tma_load_2d_2sm(tmW0, &c.w_full[sl], dst, kc * kKch, wr);
+                      ptx::tma_load_2d_2sm(tmW0, &c.w_full[sl], dst + kPPWPlane, kc * kKch, wr + ly0.Npad);
+                    }
+                    ++pw_it; ++npre;
+                    continue;
+                  }
+                }
+                if (__any_sync(0xffffffffu, ptx::mbar_test_wait(&c.act_ready[h], rdy_it[h] & 1))) break;
+              }
+            } else
+#endif
             ptx::mbar_wait(&c.act_ready[h], rdy_it[h] & 1);          // planes of (h, s) are published
             ++rdy_it[h];
             const PPStep st = prog[s];
@@ -477,6 +509,7 @@ __global__ void __launch_bounds__(kPPThreads, 1) plan_pp_kernel(const __grid_con
                 ++pa_it;
               }
               for (int nc = 0; nc < nnc; ++nc) {
+                if (kc * nnc + nc < npre) continue;                  // already requested while waiting for act_ready
                 const int ncols = min(kNch, ly.Npad - nc * kNch);
                 const uint32_t sl = pw_it % kPPWRing, ph = (pw_it / kPPWRing) & 1;
                 ptx::mbar_wait(&c.w_empty[sl], ph ^ 1);
@@ -663,7 +696,10 @@ __global__ void __launch_bounds__(kPPThreads, 1) plan_pp_kernel(const __grid_con
           ptx::tc_fence_before();
           PP_TRACE(P, tr_on, s, 6 + 3 * h);
           if (t_next >= 0) pp_write_actions(P, c, tile, env, task, t_next, h * kPPHalf, kPPHalf, h == 0);
-          if (is_ln && ((et.q & 1) == 0) && c.lane == 0) ptx::bulk_wait<0>();      // this block group's stores are performed
+          if (is_ln && ((et.q & 1) == 0)) {
+            __syncwarp();
+            if (ptx::elect_one()) ptx::bulk_wait<0>();                 // this block group's stores are performed
+          }
           if (!is_ln || t_next >= 0) {
             // heads and the action pass wrote global memory through the generic proxy; LayerNorm outputs left through
             // TMA stores only (the leaders have waited for them), for which the barrier below is all the next loads need

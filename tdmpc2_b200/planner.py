@@ -43,17 +43,19 @@ class Noise:
     qidx: torch.Tensor
     expo: torch.Tensor
     final: Optional[torch.Tensor]
+    shift: Optional[torch.Tensor] = None     # [E, 2] (x, y): ShiftAug's randint(0, 7) of pixel models, layers.py:55 (drawn first)
 
     @classmethod
-    def from_env_major(cls, prior, r, pi, qidx, expo, final, device=None) -> "Noise":
+    def from_env_major(cls, prior, r, pi, qidx, expo, final, device=None, shift=None) -> "Noise":
         """From the oracle's environment-major layout (r [E,I,...], pi [E,I,...], qidx [E,I,2])."""
         mv = lambda t: t if device is None else t.to(device)
         return cls(mv(prior).contiguous(), mv(r).transpose(0, 1).contiguous(), mv(pi).transpose(0, 1).contiguous(),
                    mv(qidx).to(torch.int32).transpose(0, 1).contiguous(), mv(expo).contiguous(),
-                   None if final is None else mv(final).contiguous())
+                   None if final is None else mv(final).contiguous(),
+                   None if shift is None else mv(shift).to(torch.float32).contiguous())
 
     def tensors(self):
-        return [t for t in (self.prior, self.r, self.pi, self.qidx, self.expo, self.final) if t is not None]
+        return [t for t in (self.prior, self.r, self.pi, self.qidx, self.expo, self.final, self.shift) if t is not None]
 
 
 def alloc_noise(cfg: Config, num_envs: int, device, eval_mode: bool = False) -> Noise:
@@ -73,6 +75,8 @@ def alloc_noise(cfg: Config, num_envs: int, device, eval_mode: bool = False) -> 
     nz = Noise(views[0], views[1], views[2], torch.empty(I, E, 2, device=device, dtype=torch.int32),
                torch.empty(E, K, device=device, dtype=torch.float32), None if eval_mode else views[3])
     nz._flat = flat
+    if cfg.get("obs", "state") == "rgb":
+        nz.shift = torch.empty(E, 2, device=device, dtype=torch.float32)
     return nz
 
 
@@ -94,6 +98,8 @@ def draw_noise(cfg: Config, num_envs: int, device, eval_mode: bool = False,
     if reference_order is None:
         reference_order = (E == 1)
     nz = out if out is not None else alloc_noise(cfg, E, device, eval_mode)
+    if nz.shift is not None:      # ShiftAug inside encode(): the first draw of a reference _plan on pixels (layers.py:55)
+        nz.shift.copy_(torch.randint(0, 7, (E, 2), device=device, dtype=torch.float32, generator=g))
     if reference_order and E == 1:
         for t in range(H if P > 0 else 0):
             nz.prior[0, t] = torch.randn(P, A, **kw)
@@ -149,11 +155,12 @@ class Planner:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _cabi.CabiError("the B200 planner needs a CUDA device; there is no CPU fallback")
+        self.rgb = cfg.get("obs", "state") == "rgb"
         d = _cabi.Dims(
             num_envs=self.E, num_samples=cfg.num_samples, num_pi_trajs=cfg.num_pi_trajs, num_elites=cfg.num_elites,
-            horizon=cfg.horizon, iterations=cfg.iterations, obs_dim=cfg.obs_shape["state"][0],
+            horizon=cfg.horizon, iterations=cfg.iterations, obs_dim=1 if self.rgb else cfg.obs_shape["state"][0],
             action_dim=cfg.action_dim, latent_dim=cfg.latent_dim, mlp_dim=cfg.mlp_dim, enc_dim=cfg.enc_dim,
-            num_enc_layers=cfg.num_enc_layers, task_dim=cfg.task_dim if cfg.multitask else 0,
+            num_enc_layers=0 if self.rgb else cfg.num_enc_layers, task_dim=cfg.task_dim if cfg.multitask else 0,
             num_tasks=len(cfg.tasks) if cfg.multitask else 1, num_q=cfg.num_q, num_bins=cfg.num_bins,
             simnorm_dim=cfg.simnorm_dim, episodic=int(bool(cfg.episodic)), temperature=cfg.temperature,
             min_std=cfg.min_std, max_std=cfg.max_std, log_std_min=float(cfg.log_std_min),
@@ -169,6 +176,22 @@ class Planner:
             _cabi.check(self.lib.tdmpc2_planner_workspace_bytes(h, C.byref(nb)))
             self.workspace = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
             _cabi.check(self.lib.tdmpc2_planner_bind(h, self.packed.data_ptr(), self.workspace.data_ptr()))
+        self.pix = None
+        if self.rgb:           # pixel observations: the conv encoder is its own small object (include/tdmpc2_b200.h)
+            C_in = cfg.obs_shape["rgb"][0]
+            pd = _cabi.PixelDims(num_envs=self.E, in_channels=C_in, num_channels=cfg.num_channels, simnorm_dim=cfg.simnorm_dim)
+            ph = C.c_void_p()
+            with torch.cuda.device(self.device):
+                _cabi.check(self.lib.tdmpc2_pixel_encoder_create(C.byref(pd), C.byref(ph)))
+                nb = C.c_size_t()
+                _cabi.check(self.lib.tdmpc2_pixel_encoder_workspace_bytes(ph, C.byref(nb)))
+            self.pix = ph
+            self.pix_ws = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
+            self.pix_z = torch.empty(self.E, cfg.latent_dim, dtype=torch.float32, device=self.device)
+            # ShiftAug's base grid, computed by torch.linspace exactly as the reference does (layers.py:50-51)
+            eps = 1.0 / (64 + 2 * 3)
+            self.pix_grid = torch.linspace(-1.0 + eps, 1.0 - eps, 64 + 2 * 3, device=self.device, dtype=torch.float32)[:64].contiguous()
+            self._conv = None
         self.set_engine(engine)
         # TDMPC2_B200_L2_PERSIST=1: keep the activation scratch in the persisting part of L2 (device-wide carve-out)
         self.l2_persist = os.environ.get("TDMPC2_B200_L2_PERSIST", "0") not in ("", "0")
@@ -194,6 +217,9 @@ class Planner:
             if getattr(self, "h", None):
                 self.lib.tdmpc2_planner_destroy(self.h)
                 self.h = None
+            if getattr(self, "pix", None):
+                self.lib.tdmpc2_pixel_encoder_destroy(self.pix)
+                self.pix = None
         except Exception:
             pass
 
@@ -239,9 +265,18 @@ class Planner:
 
         W = _cabi.Weights()
         n = 0
-        while f"_encoder.state.{n}.weight" in sd:
-            W.enc[n] = lin(f"_encoder.state.{n}")
-            n += 1
+        if self.rgb:       # layers.conv: Conv2d modules at Sequential indices 2, 4, 6, 8 (layers.py:136-150); used as they are
+            cw = _cabi.ConvWeights()
+            conv_keep = []
+            for i, idx in enumerate((2, 4, 6, 8)):
+                w_, b_ = f(f"_encoder.rgb.{idx}.weight"), f(f"_encoder.rgb.{idx}.bias")
+                conv_keep.extend([w_, b_])
+                cw.weight[i], cw.bias[i] = w_.data_ptr(), b_.data_ptr()
+            self._conv, self._conv_keep = cw, conv_keep
+        else:
+            while f"_encoder.state.{n}.weight" in sd:
+                W.enc[n] = lin(f"_encoder.state.{n}")
+                n += 1
         W.num_enc = n
         for i in range(3):
             W.dynamics[i] = lin(f"_dynamics.{i}")
@@ -269,6 +304,24 @@ class Planner:
             _cabi.check(self.lib.tdmpc2_plan_prologue(self.h, _ptr(obs), _ptr(task), _ptr(t0), _ptr(prev_mean),
                                                       _ptr(noise_prior), self._stream()))
 
+    def encode_pixels(self, frames, shift) -> torch.Tensor:
+        """z = encode(obs) for pixel observations: frames [E, C, 64, 64] (any dtype, values 0..255), shift [E, 2] -> the
+        planner's static latent buffer [E, L]."""
+        if self.pix is None or self._conv is None:
+            raise _cabi.CabiError("encode_pixels needs a cfg.obs == 'rgb' planner with packed weights")
+        frames = frames.to(self.device, torch.float32).contiguous()
+        self._keep_pix = [frames, shift]
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.tdmpc2_pixel_encode(self.pix, self.pix_ws.data_ptr(), C.byref(self._conv), _ptr(frames),
+                                                     _ptr(shift), _ptr(self.pix_grid), _ptr(self.pix_z), self._stream()))
+        return self.pix_z
+
+    def prologue_latent(self, z, task, t0, prev_mean, noise_prior) -> None:
+        self._keep = [z, task, t0, prev_mean, noise_prior]
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.tdmpc2_plan_prologue_latent(self.h, _ptr(z), _ptr(task), _ptr(t0), _ptr(prev_mean),
+                                                             _ptr(noise_prior), self._stream()))
+
     def iterate(self, noise_r, noise_pi, qidx, values_out=None, elite_idx_out=None) -> None:
         with torch.cuda.device(self.device):
             _cabi.check(self.lib.tdmpc2_plan_iter(self.h, _ptr(noise_r), _ptr(noise_pi), _ptr(qidx),
@@ -295,7 +348,10 @@ class Planner:
     def _launch_chain(self, obs, task, t0, prev_mean, noise: Noise, action, new_mean, tr=None) -> None:
         """prologue -> I x iter -> epilogue on the current stream (10 launches for I = 6)."""
         cfg, E, dev = self.cfg, self.E, self.device
-        self.prologue(obs, task, t0, prev_mean, noise.prior)
+        if self.rgb:
+            self.prologue_latent(self.encode_pixels(obs, noise.shift), task, t0, prev_mean, noise.prior)
+        else:
+            self.prologue(obs, task, t0, prev_mean, noise.prior)
         if tr is not None:
             st = self.get_state()
             tr["z"], tr["pi_actions"] = st["z"], st["pi_actions"]
@@ -359,7 +415,8 @@ class Planner:
     def _capture(self, eval_mode: bool):
         cfg, E, dev = self.cfg, self.E, self.device
         f32 = dict(device=dev, dtype=torch.float32)
-        st = dict(obs=torch.zeros(E, cfg.obs_shape["state"][0], **f32), t0=torch.ones(E, device=dev, dtype=torch.uint8),
+        obs_shape = tuple(cfg.obs_shape["rgb"]) if self.rgb else (cfg.obs_shape["state"][0],)
+        st = dict(obs=torch.zeros(E, *obs_shape, **f32), t0=torch.ones(E, device=dev, dtype=torch.uint8),
                   prev=torch.zeros(E, cfg.horizon, cfg.action_dim, **f32),
                   task=torch.zeros(E, device=dev, dtype=torch.int32) if cfg.multitask else None,
                   noise=alloc_noise(cfg, E, dev, eval_mode), action=torch.empty(E, cfg.action_dim, **f32),

@@ -32,7 +32,7 @@ def head_layout(cfg: Config) -> Dict[str, Dict]:
     """Per-head (in, out) layer dims and which layers carry a LayerNorm."""
     L, M, A, T, B = cfg.latent_dim, cfg.mlp_dim, cfg.action_dim, cfg.task_dim, max(cfg.num_bins, 1)
     D = L + A + T
-    obs_dim = cfg.obs_shape["state"][0]
+    obs_dim = cfg.obs_shape["state"][0] if "state" in cfg.obs_shape else 1
     n_hidden = max(cfg.num_enc_layers - 1, 1)
     return {
         # layers.enc: every layer is a NormedLinear, last activation SimNorm (layers.py:157-159)
@@ -82,7 +82,17 @@ def synth_state_dict(cfg: Config, seed: int = 1, perturb: bool = False,
             masks[i, :a] = 1.0
         sd["_action_masks"] = masks  # world_model.py:22-24
     lay = head_layout(cfg)
-    for name in ("_encoder.state", "_dynamics", "_reward", "_pi"):
+    if cfg.get("obs", "state") == "rgb":
+        # layers.conv (layers.py:136-150): Conv2d at Sequential indices 2, 4, 6, 8.  The reference leaves them at
+        # nn.Conv2d's default init (init.weight_init does not touch Conv2d); synthetic values of that scale.
+        C, nc = cfg.obs_shape["rgb"][0], cfg.num_channels
+        for idx, (cin, k) in zip((2, 4, 6, 8), ((C, 7), (nc, 5), (nc, 3), (nc, 3))):
+            bound = 1.0 / (cin * k * k) ** 0.5
+            sd[f"_encoder.rgb.{idx}.weight"] = (torch.rand(nc, cin, k, k, generator=gen) * 2 - 1) * bound
+            sd[f"_encoder.rgb.{idx}.bias"] = (torch.rand(nc, generator=gen) * 2 - 1) * bound
+    else:
+        fill("_encoder.state", lay["_encoder.state"]["dims"], lay["_encoder.state"]["ln_last"])
+    for name in ("_dynamics", "_reward", "_pi"):
         fill(name, lay[name]["dims"], lay[name]["ln_last"])
     q: Dict[str, torch.Tensor] = {}
     _sd, sd = sd, q

@@ -84,7 +84,7 @@ class TDMPC2(torch.nn.Module):
         """tdmpc2.py:97-120.  obs [obs_dim] (CPU) -> action [A] (CPU); or batched
         obs [E, obs_dim], t0 bool | [E], task int | [E] -> [E, A]."""
         obs = obs.to(self.device, non_blocking=True)
-        batched = obs.ndim == 2
+        batched = obs.ndim == (4 if self.cfg.get("obs", "state") == "rgb" else 2)   # rgb: [C, 64, 64] per environment
         if not batched:
             obs = obs.unsqueeze(0)
         if task is not None and not torch.is_tensor(task):
@@ -103,19 +103,27 @@ class TDMPC2(torch.nn.Module):
         cfg, E, dev = self.cfg, self.num_envs, self.device
         if cfg.num_pi_trajs < 1:
             raise NotImplementedError("the kernel policy path needs cfg.num_pi_trajs >= 1")
-        obs = obs.to(dev, torch.float32).reshape(E, -1).contiguous()
+        rgb = cfg.get("obs", "state") == "rgb"
+        obs = obs.to(dev, torch.float32)
+        obs = (obs.reshape(E, *cfg.obs_shape["rgb"]) if rgb else obs.reshape(E, -1)).contiguous()
         taskv = None
         if cfg.multitask:
             if task is None:
                 raise ValueError("multi-task model needs `task`")
             taskv = torch.as_tensor(task, device=dev).reshape(-1).to(torch.int32)
             taskv = taskv.expand(E).contiguous() if taskv.numel() == 1 else taskv.contiguous()
+        pl = self.planner
+        shift = None
+        if rgb:                                                                     # ShiftAug's draw comes first (layers.py:55)
+            shift = torch.randint(0, 7, (E, 2), device=dev, dtype=torch.float32, generator=self.generator)
         noise = torch.zeros(E, cfg.horizon, cfg.num_pi_trajs, cfg.action_dim, device=dev)
         if not eval_mode:
             noise[:, 0, 0] = torch.randn(E, cfg.action_dim, device=dev, generator=self.generator) if eps is None else eps.to(dev)
-        pl = self.planner
-        pl.prologue(obs, taskv, torch.ones(E, dtype=torch.uint8, device=dev),
-                    torch.zeros(E, cfg.horizon, cfg.action_dim, device=dev), noise)
+        ones, zeros = torch.ones(E, dtype=torch.uint8, device=dev), torch.zeros(E, cfg.horizon, cfg.action_dim, device=dev)
+        if rgb:
+            pl.prologue_latent(pl.encode_pixels(obs, shift), taskv, ones, zeros, noise)
+        else:
+            pl.prologue(obs, taskv, ones, zeros, noise)
         return pl.get_state()["pi_actions"][:, 0, 0].clone()
 
     @torch.no_grad()
@@ -125,7 +133,7 @@ class TDMPC2(torch.nn.Module):
         else [E, A]."""
         cfg, E, dev = self.cfg, self.num_envs, self.device
         obs = obs.to(dev, torch.float32)
-        if obs.ndim == 1:
+        if obs.ndim == (3 if cfg.get("obs", "state") == "rgb" else 1):
             obs = obs.unsqueeze(0)
         if obs.shape[0] != E:
             raise ValueError(f"obs has {obs.shape[0]} environments, agent was built for cfg.num_envs={E}")
@@ -159,7 +167,7 @@ class TDMPC2(torch.nn.Module):
             if noise is None:
                 noise = draw_noise(cfg, E, dev, eval_mode=eval_mode, generator=self.generator)
             elif eval_mode:
-                noise = Noise(noise.prior, noise.r, noise.pi, noise.qidx, noise.expo, None)
+                noise = Noise(noise.prior, noise.r, noise.pi, noise.qidx, noise.expo, None, noise.shift)
             action, new_mean, trace = self.planner.plan(obs, taskv, t0v, prev, noise, trace=return_trace)
         self._prev_mean.copy_(new_mean.reshape(self._prev_mean.shape))           # tdmpc2.py:205
         out = action[0] if E == 1 else action

@@ -7,7 +7,8 @@ runs in the fused sm_100a kernels, including the non-MPC `act()` branch (TDMPC2.
 
 What is kept, because reference checkpoints and `evaluate.py` depend on it:
 
-  * `state_dict()` / `load_state_dict()` with exactly the reference's keys: `_encoder.state.{i}.*`, `_dynamics.{i}.*`,
+  * `state_dict()` / `load_state_dict()` with exactly the reference's keys: `_encoder.state.{i}.*` (or, for pixel
+    observations, `_encoder.rgb.{2,4,6,8}.{weight,bias}`: layers.conv, layers.py:136-150), `_dynamics.{i}.*`,
     `_reward.{i}.*`, `_pi.{i}.*`, `_termination.{i}.*` (episodic), the stacked `_Qs.params.{i}.*` with their
     `_detach_Qs_params.*` aliases (same storage) and `_target_Qs_params.*` copies, tensordict's `__batch_size` /
     `__device` metadata entries, `_task_emb.weight`, `_action_masks`, `log_std_min`, `log_std_dif`;
@@ -39,8 +40,13 @@ class WorldModel(nn.Module):
     def __init__(self, cfg):
         super().__init__()
         self.cfg = cfg
-        if cfg.get("obs", "state") != "state":
-            raise NotImplementedError("pixel encoder is out of scope for the planning path (SURVEY.md section 8(f))")
+        if cfg.get("obs", "state") not in ("state", "rgb"):
+            raise NotImplementedError(f"Encoder for observation type {cfg.get('obs')} not implemented.")   # layers.py:163
+        if cfg.get("obs", "state") == "rgb":
+            if cfg.multitask:
+                raise NotImplementedError("pixel observations are single-task in this build")
+            if 16 * cfg.num_channels != cfg.latent_dim:
+                raise ValueError("layers.conv flattens [num_channels, 4, 4]: latent_dim must be 16 * num_channels")
         seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())          # consumes torch's global RNG like nn.init does
         init = synth_state_dict(cfg, seed=seed)
         init["_reward.2.weight"].zero_()                                 # world_model.py:32

@@ -8,7 +8,7 @@ from helpers import load_golden, stable_positions, boundary_separated
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["tiny", "tiny_mt", "c1_dog5m", "c3_humanoid48m_e1", "c4_mt80_317m_e1", "tiny_episodic", "c1_dog5m_episodic"]
+CASES = ["tiny", "tiny_mt", "c1_dog5m", "c3_humanoid48m_e1", "c4_mt80_317m_e1", "tiny_episodic", "c1_dog5m_episodic", "tiny_rgb"]
 # A termination decision flips a trajectory value by O(1): samples whose termination logit lies within this margin
 # of the 0.5 boundary (by the oracle, which is bit-identical to the reference) are not compared.
 TERM_MARGIN = 2e-5
@@ -32,7 +32,8 @@ def test_agent_matches_reference_golden(name):
     checked_actions = 0
     for c in calls:
         n = oracle_noise(cfg, c["seed"], 1, eval_mode=c["eval_mode"])
-        noise = Noise.from_env_major(n.prior, n.r, n.pi, n.qidx, n.expo, None if c["eval_mode"] else n.final, device="cuda")
+        noise = Noise.from_env_major(n.prior, n.r, n.pi, n.qidx, n.expo, None if c["eval_mode"] else n.final, device="cuda",
+                                     shift=n.shift)
         agent._prev_mean.copy_(c["prev_mean"].cuda())
         action, tr = agent._plan(c["obs"].cuda().unsqueeze(0), t0=c["t0"], eval_mode=c["eval_mode"],
                                  task=None if c["task"] is None else torch.tensor([c["task"]]).cuda(),
