@@ -63,7 +63,7 @@ def test_world_model_state_dict_layout():
     from tdmpc2_b200.config import workload
     from tdmpc2_b200.synth import synth_state_dict
     from tdmpc2_b200.world_model import WorldModel, convert_legacy_checkpoint
-    for wl, over in (("tiny", {}), ("tiny-mt", {}), ("tiny", {"episodic": True})):
+    for wl, over in (("tiny", {}), ("tiny-mt", {}), ("tiny", {"episodic": True}), ("tiny-rgb", {})):
         cfg = workload(wl, **over)
         m = WorldModel(cfg)
         sd = m.state_dict()
@@ -97,6 +97,25 @@ def test_world_model_state_dict_layout():
         m2.load_state_dict(conv)
         for k in want:
             assert torch.equal(m2.state_dict()[k], want[k]), k
+
+
+def test_pixel_model_keys_are_the_references():
+    """cfg.obs == 'rgb': the container's encoder keys are what the reference's own layers.conv registers
+    (_encoder.rgb.{2,4,6,8}.{weight,bias}, layers.py:136-150).  Needs the reference checkout (build container only)."""
+    from oracle import ref_harness
+    if not ref_harness.available():
+        pytest.skip("reference checkout not present")
+    from tdmpc2_b200.config import workload
+    from tdmpc2_b200.synth import synth_state_dict
+    cfg = workload("tiny-rgb")
+    sd = synth_state_dict(cfg, seed=2)
+    agent = ref_harness.build_agent(cfg, sd)                 # asserts key-for-key equality with the reference model
+    ref_keys = {k for k in agent.model.state_dict() if k.startswith("_encoder.")}
+    assert ref_keys == {k for k in sd if k.startswith("_encoder.")} == {
+        f"_encoder.rgb.{i}.{n}" for i in (2, 4, 6, 8) for n in ("weight", "bias")}
+    with pytest.raises(ValueError):                          # layers.conv flattens [num_channels, 4, 4]
+        from tdmpc2_b200.world_model import WorldModel
+        WorldModel(workload("tiny-rgb", latent_dim=64))
 
 
 def test_graft_entry_build():
