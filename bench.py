@@ -528,12 +528,13 @@ def main():
     peaks, peak_src = load_peaks()
     traffic, traffic_src = None, None
     try:   # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture of this workload
-        with open(os.path.join(ROOT, "profiles", f"r02_traffic_{wl}.json")) as f:
+        sfx = "_pp" if agent.planner.iter_engine == "tcgen05pp" else ""       # one capture per engine
+        with open(os.path.join(ROOT, "profiles", f"r02_traffic_{wl}{sfx}.json")) as f:
             tj = json.load(f)
         if int(tj.get("envs", -1)) == E_local and args.passes == 3:
             from tdmpc2_b200 import build as _b
             traffic = tj["dram_bytes_per_launch"]
-            traffic_src = {"file": f"profiles/r02_traffic_{wl}.json", "kernel_sources_unchanged_since_capture":
+            traffic_src = {"file": f"profiles/r02_traffic_{wl}{sfx}.json", "kernel_sources_unchanged_since_capture":
                            tj.get("lib_digest") == _b._digest()}
     except Exception:
         traffic = None

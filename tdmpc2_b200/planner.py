@@ -23,7 +23,11 @@ from .config import Config, get_discount
 
 # GEMM engine of the CEM-iteration kernel (include/tdmpc2_b200.h, tdmpc2_engine).  "tcgen05pp" falls back to
 # "tcgen05x2" and that to "tcgen05" inside the library when a model / shape does not fit; TDMPC2_B200_ENGINE overrides.
-DEFAULT_ENGINE = os.environ.get("TDMPC2_B200_ENGINE", "tcgen05pp")
+# "auto": batches that fit one trip of the persistent grid (tiles <= SMs: latency-bound, e.g. the reference's one environment per
+# act()) take the ping-pong engine, which needs 23 % fewer cycles per iteration; larger batches run at the board's power cap, where
+# the busier kernel is simply clocked lower and the CTA-pair engine's smaller operand traffic makes it the faster one by a few
+# per cent (profiles/README.md, "The c2 kernel is power-bound now").
+DEFAULT_ENGINE = os.environ.get("TDMPC2_B200_ENGINE", "auto")
 # Wide layers (48M / 317M presets): elements of the reduction dimension accumulated in TMEM before the partial sum is
 # flushed and added in fp32 round-to-nearest.  2048 keeps the 317M preset (K = 4096) inside the parity tolerance
 # (5e-5 + 1e-5 |v|) at +6 % time; 1024 halves the error again at +20 %; 0 = one accumulation (fastest, 2.8e-4 on |v| ~ 16).
@@ -225,6 +229,10 @@ class Planner:
 
     def set_engine(self, engine: str) -> None:
         engine = engine or DEFAULT_ENGINE
+        if engine == "auto":
+            tiles = self.E * ((self.cfg.num_samples + 127) // 128)
+            sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+            engine = "tcgen05pp" if tiles <= sms else "tcgen05x2"
         self.engine_name = engine
         code = {"tcgen05": _cabi.ENGINE_TCGEN05, "simt": _cabi.ENGINE_SIMT, "tcgen05x2": _cabi.ENGINE_TCGEN05_2SM,
                 "tcgen05pp": _cabi.ENGINE_TCGEN05_PP, "tcgen05x2pf": _cabi.ENGINE_TCGEN05_2SM_PF}[engine]
