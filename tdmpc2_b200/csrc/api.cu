@@ -143,7 +143,7 @@ struct tdmpc2_planner {
   size_t l2_window_bytes = 0;       // > 0: launches carry a persisting-L2 access-policy window over the activation scratch
   float l2_hit_ratio = 1.f;
   bool pair_ok = true;              // every layer of the CEM iteration can run as cta_group::2
-  int l2hint = 0;                   // PlanParams::l2hint (TDMPC2_B200_L2HINT; experiment knob for the wide models)
+  int l2hint = 2;                   // PlanParams::l2hint (TDMPC2_B200_L2HINT): 2 = evict-last on fused activation stores (default), 1 = operand-load hints (experiment)
   unsigned stagger = 0;             // PlanParams::stagger (TDMPC2_B200_STAGGER, clock cycles; experiment knob)
   int passes = 3;                   // 3 = fp32-parity arithmetic, 1 = declared non-parity fast mode (PlanParams::passes)
   int zb_kc0 = 0, zb_pitch = 0;     // shared-latent fold (PlanParams::zbias): K-chunks of [z | emb] folded into a per-env bias
@@ -255,7 +255,7 @@ extern "C" int tdmpc2_planner_create(const tdmpc2_dims* dims, tdmpc2_planner** o
   p->tiles_per_env = (d.num_samples + kTileM - 1) / kTileM;
   p->wide_sleep_ns = env_uint("TDMPC2_B200_WIDE_SLEEP_NS", 0);   // experiment knob
   p->stagger = env_uint("TDMPC2_B200_STAGGER", 0);
-  p->l2hint = static_cast<int>(env_uint("TDMPC2_B200_L2HINT", 0));
+  p->l2hint = static_cast<int>(env_uint("TDMPC2_B200_L2HINT", 2));   // bit 1 (value 2) on by default: see PlanParams::l2hint
   p->pair_ok = true;   // fused layers and the super-chunked wide layers both run as cta_group::2
 
   // ---- packed blob layout

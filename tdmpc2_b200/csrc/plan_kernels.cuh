@@ -148,7 +148,8 @@ struct PlanParams {
   unsigned stagger;
   // Wide models (activation planes + weights exceed L2): 1 = operand loads carry L2 eviction hints -- the per-CTA activation
   // planes, re-read once per 512-column super-chunk with a reuse distance far beyond L2, are loaded evict-first so that
-  // they stop displacing the weight chunks that all 148 CTAs read within a short window (evict-last).  0 = evict-normal.
+  // they stop displacing the weight chunks that all 148 CTAs read within a short window (evict-last).  Bit 1 (value 2):
+  // evict-last on the fused epilogues' activation-plane stores (default on).  0 = evict-normal everywhere.
   int l2hint;
 };
 
@@ -391,7 +392,7 @@ __device__ __forceinline__ void prod_load_a(const PlanParams& P, Ctx& c, const C
     if (c.cg2) {
       // both CTAs of the pair stream their own 128 rows; the bytes of both land on the leader's barrier
       if (c.rank == 0) ptx::mbar_expect_tx(&c.a_full[s], lo ? 2 * kASlotBytes : 2 * kAPlane);
-      const uint64_t pol = P.l2hint ? ptx::kL2EvictFirst : ptx::kL2EvictNormal;
+      const uint64_t pol = (P.l2hint & 1) ? ptx::kL2EvictFirst : ptx::kL2EvictNormal;
       ptx::tma_load_2d_2sm(tmA, &c.a_full[s], st, kc * kKch, arow_hi, pol);
       if (lo) ptx::tma_load_2d_2sm(tmA, &c.a_full[s], st + kAPlane, kc * kKch, arow_lo, pol);
     } else {
@@ -449,7 +450,7 @@ __device__ __forceinline__ void tc_producer(const PlanParams& P, Ctx& c, const L
     prod_load_a(P, c, tmA, kc, arow_hi, arow_lo);
     for (int nc = nc0; nc < nc0 + nnc; ++nc) {
       if (skip) --skip;
-      else prod_load_w(c, tmW, ly.Npad, ly.wrow, kc, nc, P.passes != 1, P.l2hint != 0);
+      else prod_load_w(c, tmW, ly.Npad, ly.wrow, kc, nc, P.passes != 1, (P.l2hint & 1) != 0);
     }
   }
   if (c.wpf) {
@@ -908,8 +909,14 @@ __device__ __forceinline__ void epi_pass2_fast(const PlanParams& P, Ctx& c, cons
     ptx::fence_proxy_async_smem();
     group_bar_sync(et.grp);
     if (lead_warp && ptx::elect_one()) {
-      ptx::tma_store_2d(tmD, buf, ea.dst_col0 + c0, row_hi);
-      if (!FAST) ptx::tma_store_2d(tmD, buf + kStgPlane, ea.dst_col0 + c0, row_lo);
+      if (P.l2hint & 2) {     // evict-last on the activation-plane stores (re-read by the next layer, then overwritten):
+                              // DRAM write-back of the scratch 2.11 -> 1.43 GB per c2 iteration, -0.9 % per plan under the power cap
+        ptx::tma_store_2d_hint(tmD, buf, ea.dst_col0 + c0, row_hi, ptx::kL2EvictLast);
+        if (!FAST) ptx::tma_store_2d_hint(tmD, buf + kStgPlane, ea.dst_col0 + c0, row_lo, ptx::kL2EvictLast);
+      } else {
+        ptx::tma_store_2d(tmD, buf, ea.dst_col0 + c0, row_hi);
+        if (!FAST) ptx::tma_store_2d(tmD, buf + kStgPlane, ea.dst_col0 + c0, row_lo);
+      }
       ptx::bulk_commit();
     }
   }

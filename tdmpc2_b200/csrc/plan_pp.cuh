@@ -293,8 +293,13 @@ __device__ __forceinline__ void pp_epi_ln(const PlanParams& P, PPCtx& c, const P
       ptx::fence_proxy_async_smem();
       pp_group_sync(et.bg);
       if (lead_warp && ptx::elect_one()) {
-        ptx::tma_store_2d(tmD, buf, c0 + sub, row_hi);      // LN outputs always start at column 0 of their buffer
-        ptx::tma_store_2d(tmD, buf + kPPStgPlane, c0 + sub, row_lo);
+        if (P.l2hint & 2) {                                   // evict-last: re-read by the next layer (see plan_kernels.cuh)
+          ptx::tma_store_2d_hint(tmD, buf, c0 + sub, row_hi, ptx::kL2EvictLast);   // LN outputs start at column 0 of their buffer
+          ptx::tma_store_2d_hint(tmD, buf + kPPStgPlane, c0 + sub, row_lo, ptx::kL2EvictLast);
+        } else {
+          ptx::tma_store_2d(tmD, buf, c0 + sub, row_hi);
+          ptx::tma_store_2d(tmD, buf + kPPStgPlane, c0 + sub, row_lo);
+        }
         ptx::bulk_commit();
       }
     }

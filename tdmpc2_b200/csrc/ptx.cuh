@@ -116,6 +116,8 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
 
 // ------------------------------------------------------------------ TMA
+// L2 cache-hint operands of cp.async.bulk.tensor (the encodings createpolicy.fractional.L2::evict_* returns for fraction 1.0)
+constexpr uint64_t kL2EvictNormal = 0x1000000000000000ull, kL2EvictFirst = 0x12F0000000000000ull, kL2EvictLast = 0x14F0000000000000ull;
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
@@ -151,6 +153,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+// The same with an L2 cache-hint operand (kL2Evict*, below): the activation planes are re-read by the very next layer.
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;\n" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(policy)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {   // at most N groups still reading their smem source
@@ -177,8 +186,6 @@ __device__ __forceinline__ void cluster_sync() {
 // Clearing this bit of a shared::cluster address selects the even (leader) CTA of the pair.
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
 // 2D tile load into THIS CTA's smem whose transaction bytes are counted on the LEADER CTA's mbarrier.
-// L2 cache-hint operands of cp.async.bulk.tensor (the encodings createpolicy.fractional.L2::evict_* returns for fraction 1.0)
-constexpr uint64_t kL2EvictNormal = 0x1000000000000000ull, kL2EvictFirst = 0x12F0000000000000ull, kL2EvictLast = 0x14F0000000000000ull;
 __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* m, uint64_t* bar, void* smem_dst, int32_t c0,
                                                 int32_t c1, uint64_t policy = kL2EvictNormal) {
   asm volatile(
