@@ -406,6 +406,9 @@ def main():
     ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the plan chain eagerly instead of replaying the CUDA graph")
+    ap.add_argument("--rng", default="torch", choices=["torch", "philox"],
+                    help="torch = the reference's noise draws (parity; the headline); philox = the DECLARED NON-PARITY throughput "
+                         "mode: the two large noise tensors are generated inside the kernels (its own line; no oracle comparison)")
     ap.add_argument("--passes", type=int, default=3, choices=[1, 3],
                     help="3 = fp32-parity arithmetic (the headline); 1 = the DECLARED NON-PARITY fast mode (one fp16 MMA per "
                          "product): its own line, dtype f16, parity_check reports the elite-flip rate instead of gating")
@@ -433,6 +436,7 @@ def main():
     cfg = bench_cfg(wl, args.envs)
     cfg.cuda_graph = not args.no_graph
     cfg.passes = args.passes
+    cfg.rng = args.rng
     E_local = cfg.num_envs                       # weak scaling: per-GPU work is fixed
     E_total = E_local * world
     sd = synth_state_dict(cfg, seed=1)
@@ -507,7 +511,11 @@ def main():
     t0v = torch.zeros(E_local, dtype=torch.uint8, device=dev)
     prev = agent._prev_mean.reshape(E_local, cfg.horizon, A).contiguous()
     pl.prologue(obs_dev, task_dev, t0v, prev, noise.prior)
-    its = [(noise.r[i], noise.pi[i], noise.qidx[i]) for i in range(cfg.iterations)]
+    if pl.philox:
+        its = [(i, noise.qidx[i]) for i in range(cfg.iterations)]
+        pl.iterate = pl.iterate_rng                       # same timing loop, in-kernel noise
+    else:
+        its = [(noise.r[i], noise.pi[i], noise.qidx[i]) for i in range(cfg.iterations)]
     for a_ in its[:2]:
         pl.iterate(*a_)
     torch.cuda.synchronize()
@@ -547,7 +555,7 @@ def main():
     steps_per_plan = E_total * cfg.num_samples * cfg.horizon
     value = steps_per_plan / (ms_step * 1e-3)
     e2e_value = steps_per_plan / (ms_e2e * 1e-3)
-    noise_mb = 4 * E_local * cfg.iterations * (cfg.horizon * (cfg.num_samples - cfg.num_pi_trajs) + cfg.num_samples) * A_ / 1e6
+    noise_mb = 0.0 if args.rng != "torch" else 4 * E_local * cfg.iterations * (cfg.horizon * (cfg.num_samples - cfg.num_pi_trajs) + cfg.num_samples) * A_ / 1e6
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -556,6 +564,8 @@ def main():
                    "global_envs": E_total, "parallelism": f"env-shard x{world}", "engine": agent.planner.iter_engine,
                    "arithmetic": "3-pass fp16-split operands on tcgen05 kind::f16, fp32 accumulate (fp32-parity mode)" if args.passes == 3
                                  else "DECLARED NON-PARITY fast mode: single-pass fp16 operands on tcgen05 kind::f16, fp32 accumulate",
+                   "rng": "torch CUDA generator (reference draw semantics)" if args.rng == "torch"
+                          else "DECLARED NON-PARITY: in-kernel Philox4x32-10 + Box-Muller for noise_r / noise_pi",
                    "launch": "CUDA-graph replay of prologue -> I x iter -> epilogue" if agent._use_graph and not args.no_graph
                              else "eager launch chain",
                    "l2": f"no flush: per-step inputs exceed L2 (fresh noise tensors, {noise_mb:.0f} MB/step/GPU)"
@@ -584,7 +594,9 @@ def main():
         except Exception as e:
             line["e2e"]["act_latency_e1"] = {"error": repr(e)[:200]}
         torch.cuda.empty_cache()
-        if not args.no_parity:
+        if args.rng != "torch":
+            line["parity_check"] = {"skipped": "in-kernel noise stream: the oracle consumes torch's draws (declared non-parity mode)"}
+        elif not args.no_parity:
             try:
                 line["parity_check"] = parity_check(cfg, sd, obs_host.clone(), task_host, E_local, dev, args.engine,
                                                     envs=[0, E_local - 1, E_local // 2 + 1])

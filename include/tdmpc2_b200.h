@@ -35,9 +35,10 @@
 extern "C" {
 #endif
 
-#define TDMPC2_B200_ABI_VERSION 5   /* 2: tdmpc2_weights.termination, dims.episodic = 1 accepted; 3: tdmpc2_planner_set_l2_persist;
+#define TDMPC2_B200_ABI_VERSION 6   /* 2: tdmpc2_weights.termination, dims.episodic = 1 accepted; 3: tdmpc2_planner_set_l2_persist;
                                        4: tdmpc2_planner_set_passes (declared non-parity fast mode), set_kseg, iter_engine;
-                                       5: pixel encoder (tdmpc2_pixel_*), tdmpc2_plan_prologue_latent, dims.num_enc_layers = 0 */
+                                       5: pixel encoder (tdmpc2_pixel_*), tdmpc2_plan_prologue_latent, dims.num_enc_layers = 0;
+                                       6: tdmpc2_plan_iter_rng (declared non-parity in-kernel noise), tdmpc2_debug_rng */
 #define TDMPC2_MAX_ENC_LAYERS 8
 
 typedef enum tdmpc2_status {
@@ -176,6 +177,15 @@ int tdmpc2_plan_prologue(tdmpc2_planner* p, const float* obs, const int32_t* tas
 int tdmpc2_plan_prologue_latent(tdmpc2_planner* p, const float* z, const int32_t* task,
                                 const uint8_t* t0, const float* prev_mean,
                                 const float* noise_prior, void* stream);
+
+/* DECLARED NON-PARITY throughput mode of tdmpc2_plan_iter: the two large noise tensors (tdmpc2.py:176, world_model.py:156) are
+ * generated inside the kernel -- Philox4x32-10 + Box-Muller under rng_state = {seed, plan counter} (device memory, uint64[2];
+ * the caller bumps the counter once per plan()), stream 2 * iteration (+1 for the policy sample) -- instead of being drawn by
+ * torch into HBM.  Not torch's stream: actions differ from the reference's for the same torch seed; never the headline number. */
+int tdmpc2_plan_iter_rng(tdmpc2_planner* p, const uint64_t* rng_state, int iteration, const int32_t* qidx,
+                         float* values_out, int64_t* elite_idx_out, void* stream);
+/* Diagnostics: out[4 g + i] = normal i of group group0 + g of `stream` (what the kernels consume). */
+int tdmpc2_debug_rng(const uint64_t* rng_state, uint32_t stream, uint64_t group0, int ngroups, float* out, void* stream_);
 
 /* ---- pixel observations (cfg.obs == 'rgb') ------------------------------- */
 /* Replaces WorldModel.encode for obs type 'rgb' (world_model.py:103-112 -> layers.conv, layers.py:136-150): ShiftAug

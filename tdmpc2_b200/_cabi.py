@@ -11,14 +11,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TDMPC2_B200_LIB") or os.path.join(HERE, "libtdmpc2_b200.so")
 MAX_ENC_LAYERS = 8
 ENGINE_TCGEN05, ENGINE_SIMT, ENGINE_TCGEN05_2SM, ENGINE_TCGEN05_PP, ENGINE_TCGEN05_2SM_PF = 0, 1, 2, 3, 4
-ABI_VERSION = 5            # TDMPC2_B200_ABI_VERSION of include/tdmpc2_b200.h this binding was written against
+ABI_VERSION = 6            # TDMPC2_B200_ABI_VERSION of include/tdmpc2_b200.h this binding was written against
 
 # every symbol include/tdmpc2_b200.h declares
 SYMBOLS = [
     "tdmpc2_abi_version", "tdmpc2_last_error", "tdmpc2_planner_create", "tdmpc2_planner_destroy",
     "tdmpc2_planner_packed_bytes", "tdmpc2_planner_workspace_bytes", "tdmpc2_planner_bind",
     "tdmpc2_planner_set_engine", "tdmpc2_planner_iter_engine", "tdmpc2_planner_set_l2_persist", "tdmpc2_planner_set_kseg", "tdmpc2_planner_set_head_kseg", "tdmpc2_planner_set_passes", "tdmpc2_pack_weights", "tdmpc2_plan_prologue", "tdmpc2_plan_prologue_latent",
-    "tdmpc2_pixel_encoder_create", "tdmpc2_pixel_encoder_destroy", "tdmpc2_pixel_encoder_workspace_bytes", "tdmpc2_pixel_encode", "tdmpc2_plan_iter",
+    "tdmpc2_pixel_encoder_create", "tdmpc2_pixel_encoder_destroy", "tdmpc2_pixel_encoder_workspace_bytes", "tdmpc2_pixel_encode", "tdmpc2_plan_iter", "tdmpc2_plan_iter_rng", "tdmpc2_debug_rng",
     "tdmpc2_plan_epilogue", "tdmpc2_plan_get_state", "tdmpc2_estimate_value", "tdmpc2_debug_layer",
     "tdmpc2_planner_layer_count", "tdmpc2_planner_launch_count", "tdmpc2_planner_set_profile",
 ]
@@ -97,6 +97,8 @@ def load():
     lib.tdmpc2_pixel_encoder_workspace_bytes.argtypes = [vp, C.POINTER(C.c_size_t)]
     lib.tdmpc2_pixel_encode.argtypes = [vp, vp, C.POINTER(ConvWeights), vp, vp, vp, vp, vp]
     lib.tdmpc2_plan_iter.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.tdmpc2_plan_iter_rng.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp]
+    lib.tdmpc2_debug_rng.argtypes = [vp, C.c_uint32, C.c_uint64, C.c_int, vp, vp]
     lib.tdmpc2_plan_epilogue.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.tdmpc2_plan_get_state.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.tdmpc2_estimate_value.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]

@@ -799,6 +799,35 @@ extern "C" int tdmpc2_plan_iter(tdmpc2_planner* p, const float* noise_r, const f
   return launch_plan(p, prm, prm.ntiles, static_cast<cudaStream_t>(stream_));
 }
 
+// Declared non-parity throughput mode: the iteration generates its two large noise tensors itself (rng.cuh).
+extern "C" int tdmpc2_plan_iter_rng(tdmpc2_planner* p, const uint64_t* rng_state, int iteration, const int32_t* qidx,
+                                    float* values_out, int64_t* elite_idx_out, void* stream_) {
+  int rc = ready(p);
+  if (rc) return rc;
+  const tdmpc2_dims& d = p->d;
+  if (!rng_state || !qidx || iteration < 0) return fail(TDMPC2_ERR_INVALID, "null argument");
+  if (p->engine == TDMPC2_ENGINE_SIMT) return fail(TDMPC2_ERR_UNSUPPORTED, "in-kernel noise needs a tcgen05 engine");
+  PlanParams prm = p->base;
+  prm.task = p->cur_task;
+  prm.mode = MODE_ITER;
+  prm.noise_r = nullptr; prm.noise_pi = nullptr; prm.qidx = qidx;
+  prm.rng_state = reinterpret_cast<const unsigned long long*>(rng_state);
+  prm.rng_iter = iteration;
+  prm.values_out = values_out;
+  prm.elite_idx_out = reinterpret_cast<long long*>(elite_idx_out);
+  prm.ntiles = d.num_envs * p->tiles_per_env;
+  prm.zb_kc0 = p->zb_kc0;
+  return launch_plan(p, prm, prm.ntiles, static_cast<cudaStream_t>(stream_));
+}
+// Diagnostics / tests: the normals of `ngroups` consecutive groups of one stream (4 per group).
+extern "C" int tdmpc2_debug_rng(const uint64_t* rng_state, uint32_t stream, uint64_t group0, int ngroups, float* out, void* stream_) {
+  if (!rng_state || !out || ngroups < 1) return fail(TDMPC2_ERR_INVALID, "bad debug_rng arguments");
+  rng_debug_kernel<<<(ngroups + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      reinterpret_cast<const unsigned long long*>(rng_state), stream, group0, ngroups, out);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int tdmpc2_plan_epilogue(tdmpc2_planner* p, const float* expo, const float* noise_final, float* action_out,
                                     float* prev_mean_out, int32_t* pick_out, void* stream_) {
   int rc = ready(p);

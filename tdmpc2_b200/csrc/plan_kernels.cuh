@@ -42,6 +42,7 @@
 #include <stdint.h>
 
 #include "ptx.cuh"
+#include "rng.cuh"
 
 namespace tdmpc2 {
 
@@ -151,6 +152,10 @@ struct PlanParams {
   // they stop displacing the weight chunks that all 148 CTAs read within a short window (evict-last).  Bit 1 (value 2):
   // evict-last on the fused epilogues' activation-plane stores (default on).  0 = evict-normal everywhere.
   int l2hint;
+  // Declared non-parity throughput mode (rng.cuh): non-null = the CEM iteration generates noise_r / noise_pi itself
+  // (noise_r / noise_pi are null then); rng_iter = index of this iteration within the plan (selects the Philox stream)
+  const unsigned long long* rng_state;
+  int rng_iter;
 };
 
 // The layer table lives in global memory; role loops are full of asm volatile(... "memory") (TMA issue, mbarrier waits,
@@ -324,6 +329,23 @@ __device__ __forceinline__ RowMap map_row(const PlanParams& P, int tile, int r) 
   return m;
 }
 
+// In-kernel noise (rng.cuh): group indices.  noise_r element (e, t, n, a), n >= P: group ((e H + t) N + n) A4 + a / 4 of
+// stream 2 iter; noise_pi element (e, n, a): group (e N + n) A4 + a / 4 of stream 2 iter + 1; A4 = ceil(A / 4).
+__device__ __forceinline__ unsigned long long rng_group_r(const PlanParams& P, int e, int t, int n, int a4) {
+  return ((static_cast<unsigned long long>(e) * P.H + t) * P.N + n) * static_cast<unsigned>((P.A + 3) >> 2) + a4;
+}
+__device__ __forceinline__ unsigned long long rng_group_pi(const PlanParams& P, int e, int n, int a4) {
+  return (static_cast<unsigned long long>(e) * P.N + n) * static_cast<unsigned>((P.A + 3) >> 2) + a4;
+}
+__device__ __forceinline__ float noise_r_at(const PlanParams& P, int e, int t, int n, int a) {
+  if (P.rng_state) return rng_pick(rng_normal4(P.rng_state, 2u * P.rng_iter, rng_group_r(P, e, t, n, a >> 2)), a & 3);
+  return __ldcs(&P.noise_r[((static_cast<size_t>(e) * P.H + t) * (P.N - P.P) + (n - P.P)) * P.A + a]);
+}
+__device__ __forceinline__ float noise_pi_at(const PlanParams& P, int e, int n, int a) {      // MODE_ITER / VALUE terminal policy sample
+  if (P.rng_state) return rng_pick(rng_normal4(P.rng_state, 2u * P.rng_iter + 1u, rng_group_pi(P, e, n, a >> 2)), a & 3);
+  return __ldcs(&P.noise_pi[(static_cast<size_t>(e) * P.N + n) * P.A + a]);
+}
+
 // action a_t of sample n of env e at CEM time (tdmpc2.py:168-181)
 __device__ __forceinline__ float sample_action(const PlanParams& P, int e, int t, int n, int a, int task) {
   float v;
@@ -333,7 +355,7 @@ __device__ __forceinline__ float sample_action(const PlanParams& P, int e, int t
     v = P.pi_actions[((static_cast<size_t>(e) * P.H + t) * P.P + n) * P.A + a];
   } else {
     const size_t sa = (static_cast<size_t>(e) * P.H + t) * P.A + a;
-    const float r = __ldcs(&P.noise_r[((static_cast<size_t>(e) * P.H + t) * (P.N - P.P) + (n - P.P)) * P.A + a]);
+    const float r = noise_r_at(P, e, t, n, a);
     v = __fadd_rn(P.mean[sa], __fmul_rn(P.std[sa], r));       // mean + std * r, two roundings like eager torch
     v = fminf(fmaxf(v, -1.f), 1.f);
   }
@@ -751,7 +773,8 @@ __device__ __forceinline__ void rows_head(const PlanParams& P, Ctx& c, const Lay
       const int e = rm.env < 0 ? 0 : rm.env, idx = rm.env < 0 ? 0 : rm.idx;
       const int task = P.task ? P.task[e] : 0;
       for (int a = c.lane; a < P.A; a += 32) {
-        const float eps = __ldcs(&ea.eps_base[(static_cast<size_t>(e) * ea.eps_rows + idx) * P.A + a]);
+        const float eps = ea.eps_base ? __ldcs(&ea.eps_base[(static_cast<size_t>(e) * ea.eps_rows + idx) * P.A + a])
+                                      : noise_pi_at(P, e, idx, a);        // eps_base == nullptr: in-kernel noise (ITER)
         const float act = pi_action(P, myrow[a], myrow[P.Apad + a], eps, task, a);
         const size_t o = static_cast<size_t>(r) * P.KpadX + P.L + P.T + a;
         split_store(xhi + o, xlo + o, act);
@@ -1312,7 +1335,7 @@ __device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, cons
     const int task = P.task ? P.task[e] : 0;
     __half* xhi = plane_ptr(P, c.slot, BUF_X, 0) + static_cast<size_t>(et.row) * P.KpadX + P.L + P.T;
     __half* xlo = plane_ptr(P, c.slot, BUF_X, 1) + static_cast<size_t>(et.row) * P.KpadX + P.L + P.T;
-    const float* eps = ea.eps_base + (static_cast<size_t>(e) * ea.eps_rows + idx) * P.A;
+    const float* eps = ea.eps_base ? ea.eps_base + (static_cast<size_t>(e) * ea.eps_rows + idx) * P.A : nullptr;   // nullptr: in-kernel noise
     const int a_begin = wide_pi ? 16 * et.grp : 0;
     const int a_end = wide_pi ? min(P.A, a_begin + 16) : P.A;
     for (int a0 = a_begin; a0 < a_end; a0 += 16) {
@@ -1339,7 +1362,7 @@ __device__ __forceinline__ void epi_head_fused(const PlanParams& P, Ctx& c, cons
           if (a < a_end) {
             const float mu = fmaf(__uint_as_float(vm[i + u]), inv_scale, sb[a]);
             const float ls = fmaf(__uint_as_float(vs[i + u]), inv_scale, sb[P.Apad + a]);
-            act2[u] = pi_action(P, mu, ls, __ldcs(&eps[a]), task, a);
+            act2[u] = pi_action(P, mu, ls, eps ? __ldcs(&eps[a]) : noise_pi_at(P, e, idx, a), task, a);
             if (!vec) split_store(xhi + a, xlo + a, act2[u]);
             if (ea.act_out && rm.env >= 0)
               ea.act_out[((static_cast<size_t>(e) * P.H + ea.t_out) * P.P + idx) * P.A + a] = act2[u];
@@ -2056,7 +2079,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
         split_store(xhi + static_cast<size_t>(r) * P.KpadX + col, xlo + static_cast<size_t>(r) * P.KpadX + col, x);
       }
     }
-    if (P.mode == MODE_ITER && !P.actions_explicit && threadIdx.x <= P.H) {
+    if (P.mode == MODE_ITER && !P.actions_explicit && !P.rng_state && threadIdx.x <= P.H) {
       // This tile's slabs of the (HBM-resident, read-once) noise tensors are contiguous: ask for them now, so that the
       // per-step action pass and the terminal policy sample find them in L2 instead of paying DRAM latency.
       const int n0 = (tile % P.tiles_per_env) * kTileM, n1 = min(n0 + kTileM, P.N);
@@ -2142,9 +2165,15 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
                   const int n = min(n0 + r, P.N - 1);
                   const float* src = (n < P.P) ? pa + static_cast<size_t>(n) * P.A : nz + static_cast<size_t>(n - P.P) * P.A;
                   float x[8];
+                  if (n >= P.P && P.rng_state) {                               // in-kernel noise: two groups of four
+                    const float4 g0 = rng_normal4(P.rng_state, 2u * P.rng_iter, rng_group_r(P, env_tile, t, n, g8 >> 2));
+                    const float4 g1 = rng_normal4(P.rng_state, 2u * P.rng_iter, rng_group_r(P, env_tile, t, n, (g8 >> 2) + 1));
+                    x[0] = g0.x; x[1] = g0.y; x[2] = g0.z; x[3] = g0.w; x[4] = g1.x; x[5] = g1.y; x[6] = g1.z; x[7] = g1.w;
+                  } else {
 #pragma unroll
-                  for (int u = 0; u < 8; ++u)                                  // noise is one-shot: evict-first
-                    x[u] = (g8 + u < P.A) ? (n < P.P ? src[g8 + u] : __ldcs(src + g8 + u)) : 0.f;
+                    for (int u = 0; u < 8; ++u)                                // noise is one-shot: evict-first
+                      x[u] = (g8 + u < P.A) ? (n < P.P ? src[g8 + u] : __ldcs(src + g8 + u)) : 0.f;
+                  }
                   uint32_t hw[4], lw[4];
 #pragma unroll
                   for (int u = 0; u < 8; u += 2) {
@@ -2172,7 +2201,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
                   float v;
                   if (n < P.P) v = pa[static_cast<size_t>(n) * P.A + a];
                   else {
-                    v = __fadd_rn(sm_mean[a], __fmul_rn(sm_std[a], __ldcs(&nz[static_cast<size_t>(n - P.P) * P.A + a])));   // one-shot: evict-first
+                    v = __fadd_rn(sm_mean[a], __fmul_rn(sm_std[a], noise_r_at(P, env_tile, t, n, a)));   // one-shot: evict-first
                     v = fminf(fmaxf(v, -1.f), 1.f);
                   }
                   v *= sm_mask[a];
@@ -2210,7 +2239,7 @@ __global__ void __launch_bounds__(kThreads, 1) plan_kernel(const __grid_constant
             ea.eps_base = P.noise_prior + static_cast<size_t>(t) * P.P * P.A; ea.eps_rows = P.H * P.P;
             ea.act_out = P.pi_actions; ea.t_out = t;
           } else {                             // eps = noise_pi[e, n, :]
-            ea.eps_base = P.noise_pi; ea.eps_rows = P.N;
+            ea.eps_base = P.rng_state ? nullptr : P.noise_pi; ea.eps_rows = P.N;
           }
         } else if (EPISODIC && mlp == 5) {     // termination(z_{t+1})  (world_model.py:132-141), input [z | emb]
           ea.kind = EPI_TERM;

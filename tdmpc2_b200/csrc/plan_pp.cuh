@@ -132,7 +132,12 @@ __device__ __forceinline__ void pp_write_actions(const PlanParams& P, PPCtx& c, 
       const float* src = (n < P.P) ? pa + static_cast<size_t>(n) * P.A : nz + static_cast<size_t>(n - P.P) * P.A;
       float x[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) x[u] = (g8 + u < P.A) ? (n < P.P ? src[g8 + u] : __ldcs(src + g8 + u)) : 0.f;
+      for (int u = 0; u < 8; ++u) x[u] = (g8 + u < P.A) ? (n < P.P ? src[g8 + u] : (P.rng_state ? 0.f : __ldcs(src + g8 + u))) : 0.f;
+      if (n >= P.P && P.rng_state) {                                 // in-kernel noise (rng.cuh): two groups of four
+        const float4 g0 = rng_normal4(P.rng_state, 2u * P.rng_iter, rng_group_r(P, env, t, n, g8 >> 2));
+        const float4 g1 = rng_normal4(P.rng_state, 2u * P.rng_iter, rng_group_r(P, env, t, n, (g8 >> 2) + 1));
+        x[0] = g0.x; x[1] = g0.y; x[2] = g0.z; x[3] = g0.w; x[4] = g1.x; x[5] = g1.y; x[6] = g1.z; x[7] = g1.w;
+      }
       uint32_t hw[4], lw[4];
 #pragma unroll
       for (int u = 0; u < 8; u += 2) {
@@ -161,7 +166,7 @@ __device__ __forceinline__ void pp_write_actions(const PlanParams& P, PPCtx& c, 
     float v;
     if (n < P.P) v = pa[static_cast<size_t>(n) * P.A + a];
     else {
-      v = __fadd_rn(sm_mean[a], __fmul_rn(sm_std[a], nz[static_cast<size_t>(n - P.P) * P.A + a]));
+      v = __fadd_rn(sm_mean[a], __fmul_rn(sm_std[a], noise_r_at(P, env, t, n, a)));
       v = fminf(fmaxf(v, -1.f), 1.f);
     }
     v *= sm_mask[a];
@@ -382,7 +387,8 @@ __device__ __forceinline__ void pp_epi_pi(const PlanParams& P, PPCtx& c, const P
         const int a = a0 + i + u;
         act2[u] = 0.f;
         if (a < P.A) {
-          act2[u] = pi_action(P, xr[pp_pi_idx(et.row, a)], xr[pp_pi_idx(et.row, P.Apad + a)], eps[a], task, a);
+          act2[u] = pi_action(P, xr[pp_pi_idx(et.row, a)], xr[pp_pi_idx(et.row, P.Apad + a)],
+                              P.rng_state ? noise_pi_at(P, env, n, a) : eps[a], task, a);
           if (!vec) split_store(xhi + a, xlo + a, act2[u]);
         }
       }
@@ -627,7 +633,7 @@ __global__ void __launch_bounds__(kPPThreads, 1) plan_pp_kernel(const __grid_con
         prog[tid] = st;
       }
       for (int r = tid; r < kTileM; r += kEpiThreads) { c.G[r] = 0.f; c.q1[r] = 0.f; }
-      if (tid <= P.H) {
+      if (tid <= P.H && !P.rng_state) {
         // this tile's slabs of the read-once noise tensors: ask for them now (L2) instead of paying DRAM latency per step
         const int n0 = (tile % P.tiles_per_env) * kTileM, n1 = n0 + kTileM;
         if (tid < P.H) {

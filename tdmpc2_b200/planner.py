@@ -68,6 +68,13 @@ def alloc_noise(cfg: Config, num_envs: int, device, eval_mode: bool = False) -> 
     H, N, P, A, I, K = (cfg.horizon, cfg.num_samples, cfg.num_pi_trajs, cfg.action_dim,
                         cfg.iterations, cfg.num_elites)
     E = num_envs
+    if cfg.get("rng", "torch") == "philox":      # declared non-parity mode: r / pi are generated inside the kernels
+        nz = Noise(torch.empty(E, H, P, A, device=device, dtype=torch.float32), None, None,
+                   torch.empty(I, E, 2, device=device, dtype=torch.int32), torch.empty(E, K, device=device, dtype=torch.float32),
+                   None if eval_mode else torch.empty(E, A, device=device, dtype=torch.float32))
+        if cfg.get("obs", "state") == "rgb":
+            nz.shift = torch.empty(E, 2, device=device, dtype=torch.float32)
+        return nz
     shapes = [(E, H, P, A), (I, E, H, N - P, A), (I, E, N, A)] + ([] if eval_mode else [(E, A)])
     sizes = [int(torch.Size(sh).numel()) for sh in shapes]
     pad = lambda n: (n + 63) // 64 * 64                     # keep every view 256-byte aligned
@@ -104,6 +111,13 @@ def draw_noise(cfg: Config, num_envs: int, device, eval_mode: bool = False,
     nz = out if out is not None else alloc_noise(cfg, E, device, eval_mode)
     if nz.shift is not None:      # ShiftAug inside encode(): the first draw of a reference _plan on pixels (layers.py:55)
         nz.shift.copy_(torch.randint(0, 7, (E, 2), device=device, dtype=torch.float32, generator=g))
+    if nz.r is None:                       # in-kernel noise: only the small host-side draws remain
+        nz.prior.normal_(generator=g)
+        if nz.final is not None:
+            nz.final.normal_(generator=g)
+        nz.qidx.copy_(torch.rand(I, E, cfg.num_q, **kw).argsort(dim=-1)[..., :2])
+        nz.expo.exponential_(generator=g)
+        return nz
     if reference_order and E == 1:
         for t in range(H if P > 0 else 0):
             nz.prior[0, t] = torch.randn(P, A, **kw)
@@ -211,6 +225,13 @@ class Planner:
         # arithmetic: 3 = fp32-parity (default); 1 = the declared NON-PARITY fast mode (see include/tdmpc2_b200.h)
         self.passes = int(os.environ.get("TDMPC2_B200_PASSES", cfg.get("passes", 3) or 3))
         _cabi.check(self.lib.tdmpc2_planner_set_passes(self.h, self.passes))
+        # noise source: "torch" (default; the reference's draws, parity) or "philox" = the declared NON-PARITY throughput mode
+        # (the two large noise tensors are generated inside the kernels: include/tdmpc2_b200.h, tdmpc2_plan_iter_rng)
+        self.philox = cfg.get("rng", "torch") == "philox"
+        self.rng_state = None
+        if self.philox:
+            seed = int(cfg.get("rng_seed", torch.initial_seed())) & ((1 << 63) - 1)
+            self.rng_state = torch.tensor([seed, 0], dtype=torch.int64, device=self.device)   # {seed, plan counter}
         self._keep = []       # tensors referenced by in-flight async calls
         self.weights_version = None
         self._graphs = {}     # eval_mode -> captured launch chain + its static buffers
@@ -335,6 +356,11 @@ class Planner:
             _cabi.check(self.lib.tdmpc2_plan_iter(self.h, _ptr(noise_r), _ptr(noise_pi), _ptr(qidx),
                                                   _ptr(values_out), _ptr(elite_idx_out), self._stream()))
 
+    def iterate_rng(self, iteration: int, qidx, values_out=None, elite_idx_out=None) -> None:
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.tdmpc2_plan_iter_rng(self.h, _ptr(self.rng_state), int(iteration), _ptr(qidx),
+                                                      _ptr(values_out), _ptr(elite_idx_out), self._stream()))
+
     def epilogue(self, expo, noise_final, action_out, prev_mean_out, pick_out=None) -> None:
         with torch.cuda.device(self.device):
             _cabi.check(self.lib.tdmpc2_plan_epilogue(self.h, _ptr(expo), _ptr(noise_final), _ptr(action_out),
@@ -364,13 +390,19 @@ class Planner:
             st = self.get_state()
             tr["z"], tr["pi_actions"] = st["z"], st["pi_actions"]
         for it in range(cfg.iterations):
-            nr, npi, qi = noise.r[it], noise.pi[it], noise.qidx[it]          # contiguous slabs of the [I, E, ...] tensors
+            qi = noise.qidx[it]
+            nr, npi = (None, None) if self.philox else (noise.r[it], noise.pi[it])   # contiguous slabs of the [I, E, ...] tensors
             if tr is not None:
                 v, ei = torch.empty(E, cfg.num_samples, device=dev), torch.empty(E, cfg.num_elites, device=dev, dtype=torch.int64)
-                self.iterate(nr, npi, qi, v, ei)
+                if self.philox:
+                    self.iterate_rng(it, qi, v, ei)
+                else:
+                    self.iterate(nr, npi, qi, v, ei)
                 tr["values"][:, it], tr["elite_idx"][:, it] = v, ei
                 st = self.get_state()
                 tr["iter_mean"].append(st["mean"]); tr["iter_std"].append(st["std"])
+            elif self.philox:
+                self.iterate_rng(it, qi)
             else:
                 self.iterate(nr, npi, qi)
         if tr is not None:
@@ -386,7 +418,9 @@ class Planner:
         for t in noise.tensors():
             if not t.is_contiguous():
                 raise ValueError("noise tensors must be contiguous (iteration-major: see planner.Noise)")
-        if noise.r.shape[:2] != (cfg.iterations, E) or noise.pi.shape[:2] != (cfg.iterations, E):
+        if self.philox:
+            self.rng_state[1] += 1                          # a fresh noise stream per plan()
+        elif noise.r.shape[:2] != (cfg.iterations, E) or noise.pi.shape[:2] != (cfg.iterations, E):
             raise ValueError("noise.r / noise.pi must be [iterations, num_envs, ...] (Noise.from_env_major converts)")
         action = torch.empty(E, cfg.action_dim, device=dev, dtype=torch.float32)
         new_mean = torch.empty(E, cfg.horizon, cfg.action_dim, device=dev, dtype=torch.float32)
@@ -416,6 +450,8 @@ class Planner:
         if st["task"] is not None:
             st["task"].copy_(task, non_blocking=True)
         draw_noise(cfg, E, dev, eval_mode=eval_mode, generator=generator, out=st["noise"])
+        if self.philox:
+            self.rng_state[1] += 1                          # device-side counter: the graph's kernels read it
         st["graph"].replay()
         self._graph_launches += st["launches"]
         return st["action"].clone(), st["new_mean"].clone()
