@@ -48,6 +48,15 @@ CASES = {
     # cfg.obs == 'rgb': layers.conv encoder with ShiftAug inside encode() (layers.py:36-71,136-150)
     "tiny_rgb": ("tiny-rgb", {}, 14, True, 1.0,
                  [(True, False, None, 400), (False, False, None, 401), (False, True, None, 402)]),
+    # branch / knob coverage of _plan on the test-sized model: no policy-prior trajectories (tdmpc2.py:149 skipped),
+    # a one-step horizon (no warm-start shift at :169), and non-default planner knobs with a ragged sample count
+    "tiny_nopi": ("tiny", {"num_pi_trajs": 0}, 15, True, 1.0,
+                  [(True, False, None, 500), (False, False, None, 501), (False, True, None, 502)]),
+    "tiny_h1": ("tiny", {"horizon": 1}, 16, True, 1.0,
+                [(True, False, None, 510), (False, False, None, 511), (False, True, None, 512)]),
+    "tiny_knobs": ("tiny", {"num_samples": 200, "num_elites": 7, "num_pi_trajs": 5, "temperature": 2.0, "min_std": 0.1,
+                            "max_std": 1.5, "num_q": 5, "iterations": 4, "num_bins": 51, "vmin": -5, "vmax": 5}, 17, True, 1.0,
+                   [(True, False, None, 520), (False, False, None, 521), (False, True, None, 522)]),
 }
 
 
