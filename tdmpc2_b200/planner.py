@@ -235,6 +235,8 @@ class Planner:
         self._keep = []       # tensors referenced by in-flight async calls
         self.weights_version = None
         self._graphs = {}     # eval_mode -> captured launch chain + its static buffers
+        self._e1_noise = {}   # eval_mode -> static noise buffers of plan_interleaved
+        self._draw_stream = None
         self._graph_launches = 0
 
     def __del__(self):
@@ -455,6 +457,55 @@ class Planner:
         st["graph"].replay()
         self._graph_launches += st["launches"]
         return st["action"].clone(), st["new_mean"].clone()
+
+    def plan_interleaved(self, obs, task, t0, prev_mean, eval_mode: bool = False,
+                         generator: Optional[torch.Generator] = None):
+        """plan() of ONE environment in the reference's draw order (draw_noise, reference_order) with the draws off the
+        critical path.  A reference-order call makes 2 + H + 3 I small generator launches (0.6 ms of host time for
+        I = 8, and as many tiny kernels): ahead of a graph replay they delay the kernels by that much.  Here the host
+        issues each iteration's draws on a side stream right before that iteration's launch; the kernels (0.5 ms each
+        at E = 1) are far slower than the host, so the side stream runs an iteration ahead and the main stream sees
+        back-to-back planner kernels.  Same generator consumption (the Philox offset advances at call time, whatever the
+        stream), same kernels, same results as draw_noise() + plan()."""
+        cfg, dev = self.cfg, self.device
+        if self.E != 1 or self.philox:
+            raise ValueError("plan_interleaved is the one-environment, torch-noise path")
+        H, N, P, A, I = cfg.horizon, cfg.num_samples, cfg.num_pi_trajs, cfg.action_dim, cfg.iterations
+        key = bool(eval_mode)
+        nz = self._e1_noise.get(key)
+        if nz is None:
+            nz = self._e1_noise[key] = alloc_noise(cfg, 1, dev, eval_mode)
+        if self._draw_stream is None:
+            self._draw_stream = torch.cuda.Stream(device=dev)
+        main, side = torch.cuda.current_stream(dev), self._draw_stream
+        kw = dict(device=dev, dtype=torch.float32, generator=generator)
+        action = torch.empty(1, A, device=dev, dtype=torch.float32)
+        new_mean = torch.empty(1, H, A, device=dev, dtype=torch.float32)
+        side.wait_stream(main)                        # earlier readers of the static noise buffers are done
+        with torch.cuda.stream(side):
+            if nz.shift is not None:                                                  # layers.py:55
+                nz.shift.copy_(torch.randint(0, 7, (1, 2), device=dev, dtype=torch.float32, generator=generator))
+            for t in range(H if P > 0 else 0):                                        # tdmpc2.py:153
+                nz.prior[0, t] = torch.randn(P, A, **kw)
+            main.wait_event(side.record_event())
+        if self.rgb:
+            self.prologue_latent(self.encode_pixels(obs, nz.shift), task, t0, prev_mean, nz.prior)
+        else:
+            self.prologue(obs, task, t0, prev_mean, nz.prior)
+        for it in range(I):
+            with torch.cuda.stream(side):
+                nz.r[it, 0] = torch.randn(H, N - P, A, **kw)                          # tdmpc2.py:175
+                nz.pi[it, 0] = torch.randn(N, A, **kw)                                # world_model.py:166 via tdmpc2.py:134
+                nz.qidx[it, 0] = torch.randperm(cfg.num_q, device=dev, generator=generator)[:2].to(torch.int32)
+                main.wait_event(side.record_event())
+            self.iterate(nz.r[it], nz.pi[it], nz.qidx[it])
+        with torch.cuda.stream(side):
+            nz.expo.exponential_(generator=generator)                                 # math.py:44 gumbel_softmax_sample
+            if not eval_mode:
+                nz.final[0] = torch.randn(A, **kw)                                    # tdmpc2.py:203
+            main.wait_event(side.record_event())
+        self.epilogue(nz.expo, nz.final, action, new_mean)
+        return action, new_mean
 
     def _capture(self, eval_mode: bool):
         cfg, E, dev = self.cfg, self.E, self.device

@@ -12,6 +12,7 @@ independent environments in one call; E == 1 (1-D obs) is the reference API.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Sequence, Union
 
 import torch
@@ -42,6 +43,8 @@ class TDMPC2(torch.nn.Module):
         self._weights_dirty = True
         self.generator: Optional[torch.Generator] = None     # None -> torch's default CUDA generator, like the reference
         self._use_graph = bool(cfg.get("cuda_graph", True))   # replay the launch chain as one CUDA graph (cfg.compile's role)
+        # one environment: interleave the reference-order noise draws with the launches instead (TDMPC2_B200_E1_GRAPH=1: A/B knob)
+        self._e1_interleaved = bool(cfg.get("e1_interleaved", True)) and os.environ.get("TDMPC2_B200_E1_GRAPH", "0") in ("", "0")
 
     # ------------------------------------------------------------------ planner plumbing
     @property
@@ -156,8 +159,14 @@ class TDMPC2(torch.nn.Module):
             # steady state: replay the captured prologue -> I x iter -> epilogue chain (tdmpc2.py:45-55 replays a
             # `reduce-overhead` graph); noise is drawn into the graph's static buffers
             try:
-                action, new_mean = self.planner.plan_graphed(obs, taskv, t0v, prev, eval_mode=eval_mode,
-                                                             generator=self.generator)
+                if E == 1 and self._e1_interleaved and not self.planner.philox:
+                    # one environment draws in the reference's order (29 small launches for I = 8): issue each draw right
+                    # before its consumer instead of all of them ahead of a graph replay (planner.plan_interleaved)
+                    action, new_mean = self.planner.plan_interleaved(obs, taskv, t0v, prev, eval_mode=eval_mode,
+                                                                     generator=self.generator)
+                else:
+                    action, new_mean = self.planner.plan_graphed(obs, taskv, t0v, prev, eval_mode=eval_mode,
+                                                                 generator=self.generator)
             except RuntimeError as e:                      # capture unsupported here: keep the eager launch chain
                 import warnings
                 warnings.warn(f"CUDA-graph capture of the plan chain failed ({e}); launching eagerly")

@@ -170,3 +170,38 @@ def test_shared_latent_fold_only_reorders_the_sum(wl, engine, monkeypatch):
         vals[fold] = tr["values"][:, 0].cpu()          # first iteration: identical inputs on both sides
     d = (vals["1"] - vals["0"]).abs().max().item()
     assert 0.0 < d < 2e-5, d                           # > 0: the fold really ran
+
+
+@pytest.mark.parametrize("wl", ["tiny", "tiny-mt", "tiny-rgb"])
+def test_one_environment_paths_agree_bit_for_bit(wl):
+    """One environment per act() (the reference's call shape) has three host paths: draws interleaved with the launches
+    (default), all draws then one CUDA-graph replay, all draws then eager launches.  Same generator, same kernels: the
+    actions and the carried _prev_mean must be identical, call after call (t0, warm start, eval_mode)."""
+    from tdmpc2_b200.tdmpc2 import TDMPC2
+    sd = synth_state_dict(workload(wl, num_envs=1), seed=26, perturb=True)
+    g = torch.Generator().manual_seed(12)
+    base = workload(wl, num_envs=1)
+    obs = [torch.randint(0, 256, tuple(base.obs_shape["rgb"]), generator=g).float() if base.get("obs", "state") == "rgb"
+           else torch.randn(base.obs_shape["state"][0], generator=g) for _ in range(4)]
+    task = 2 if base.multitask else None
+    outs = {}
+    for name, over in (("interleaved", {}), ("graph", dict(e1_interleaved=False)), ("eager", dict(cuda_graph=False))):
+        agent = TDMPC2(workload(wl, num_envs=1, **over), device="cuda:0")
+        agent.load(sd)
+        agent.generator = torch.Generator(device="cuda:0").manual_seed(77)
+        if name == "graph":                      # capture (which draws from the default generator) before the seeded stream starts
+            agent.act(obs[0], t0=True, task=task); agent.act(obs[0], t0=True, eval_mode=True, task=task)
+            agent.generator = torch.Generator(device="cuda:0").manual_seed(77)
+            agent._prev_mean.zero_()
+        seq = []
+        for i, (t0, ev) in enumerate([(True, False), (False, False), (False, True), (False, False)]):
+            a = agent.act(obs[i], t0=t0, eval_mode=ev, task=task)
+            seq.append((a.clone(), agent._prev_mean.cpu().clone()))
+        outs[name] = seq
+        if name == "interleaved":
+            assert agent.planner._e1_noise and not agent.planner._graphs
+        if name == "graph":
+            assert agent.planner._graphs and not agent.planner._e1_noise
+    for other in ("graph", "eager"):
+        for i, ((a, m), (b, n)) in enumerate(zip(outs["interleaved"], outs[other])):
+            assert torch.equal(a, b) and torch.equal(m, n), f"{wl}: call {i} differs between interleaved and {other}"
