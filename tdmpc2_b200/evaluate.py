@@ -9,6 +9,11 @@ tasks at the same time.  The statistics are the reference's: mean episode reward
 and for multi-task models the normalised score of `evaluate.py:91,96` (success * 100 for `mw-*` tasks, reward / 10
 otherwise, averaged over tasks).
 
+Several GPUs: one process per GPU, each with its own agent and its own E environment instances.  Episodes are independent
+units, so rank g of G takes every G-th episode of the queue and runs the same loop with NO collective in it; the
+per-episode records are exchanged once at the end (`all_gather_object`, a few floats per episode) and every rank returns
+the same merged statistics.
+
 Environments are the reference's wrappers as `envs.make_env` returns them (`reset(task_idx=...)` -> obs tensor,
 `step(action)` -> (obs, reward, done, info), `envs/wrappers/tensor.py`, `multitask.py`); nothing here imports them.
 Video capture and the hydra entry point are not part of the planning path and are not provided.
@@ -20,6 +25,7 @@ from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Sequence
 
 import torch
+import torch.distributed as dist
 
 
 @dataclass
@@ -52,11 +58,13 @@ class _Slot:
 
 
 @torch.no_grad()
-def evaluate(agent, envs: Sequence[Any], eval_episodes: int, eval_mode: bool = False, verbose: bool = False) -> Dict[str, Any]:
+def evaluate(agent, envs: Sequence[Any], eval_episodes: int, eval_mode: bool = False, verbose: bool = False,
+             group: Optional["dist.ProcessGroup"] = None) -> Dict[str, Any]:
     """Evaluate `agent` (a `tdmpc2_b200.TDMPC2` built with `cfg.num_envs == len(envs)`) for `eval_episodes` episodes per
     task.  `eval_mode` is passed to `act()`; the reference's script leaves it at its default (False: the planner adds its
-    final Gaussian noise, tdmpc2.py:203).  Returns {"tasks": {name: TaskResult}, "normalized_score": float | None,
-    "env_steps": int, "act_calls": int}."""
+    final Gaussian noise, tdmpc2.py:203).  Under torch.distributed every rank passes its own agent and environments and
+    gets the merged result.  Returns {"tasks": {name: TaskResult}, "normalized_score": float | None, "env_steps": int,
+    "act_calls": int} (env_steps summed over ranks, act_calls the maximum over ranks)."""
     cfg = agent.cfg
     E = len(envs)
     if E < 1 or eval_episodes < 1:                                            # evaluate.py:42
@@ -66,7 +74,11 @@ def evaluate(agent, envs: Sequence[Any], eval_episodes: int, eval_mode: bool = F
     multitask = bool(cfg.multitask)
     names = list(cfg.tasks) if multitask else [cfg.task]                      # evaluate.py:70
     results = {name: TaskResult(name) for name in names}
-    queue = deque((ti if multitask else None, ep) for ti in range(len(names)) for ep in range(eval_episodes))
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    items = [(ti if multitask else None, ep) for ti in range(len(names)) for ep in range(eval_episodes)]
+    queue = deque(items[rank::world])                                         # episodes are independent: no exchange in the loop
+    records: List[tuple] = []                                                 # (task position, episode, reward, success, length)
     slots = [_Slot() for _ in range(E)]
     obs: List[Optional[torch.Tensor]] = [None] * E
 
@@ -81,7 +93,7 @@ def evaluate(agent, envs: Sequence[Any], eval_episodes: int, eval_mode: bool = F
 
     for i in range(E):
         start(i)
-    filler = next(o for o in obs if o is not None)
+    filler = next((o for o in obs if o is not None), None)
     env_steps = act_calls = 0
     while any(s.active for s in slots):
         batch = torch.stack([o if o is not None else torch.zeros_like(filler) for o in obs])
@@ -99,11 +111,19 @@ def evaluate(agent, envs: Sequence[Any], eval_episodes: int, eval_mode: bool = F
             s.t += 1
             env_steps += 1
             if bool(done):
-                r = results[names[s.task_idx or 0]]
-                r.episode_rewards.append(s.ep_reward)                         # evaluate.py:86-87
-                r.episode_successes.append(float(info.get("success", 0.0)))
-                r.episode_lengths.append(s.t)
+                records.append((s.task_idx or 0, s.episode, s.ep_reward, float(info.get("success", 0.0)), s.t))
                 start(i)
+    if world > 1:                                                             # the one exchange: per-episode records
+        parts: List[Any] = [None] * world
+        dist.all_gather_object(parts, (records, env_steps, act_calls), group=group)
+        records = [r for p in parts for r in p[0]]
+        env_steps, act_calls = sum(p[1] for p in parts), max(p[2] for p in parts)
+    for ti, ep, rew, suc, length in sorted(records, key=lambda r: (r[0], r[1])):
+        r = results[names[ti]]
+        r.episode_rewards.append(rew)                                         # evaluate.py:86-87
+        r.episode_successes.append(suc)
+        r.episode_lengths.append(length)
+    verbose = verbose and rank == 0
     for name in names:
         if verbose:
             print(f"  {name:<22}\tR: {results[name].reward:.01f}  \tS: {results[name].success:.02f}")

@@ -122,3 +122,46 @@ def test_argument_checks():
         evaluate(ScriptedAgent(cfg, 2), [ScriptedEnv()], 1)                 # agent built for another batch size
     with pytest.raises(ValueError):
         evaluate(ScriptedAgent(cfg, 1), [ScriptedEnv()], 0)                 # evaluate.py:42
+
+
+# ------------------------------------------------------------------------------------------------ two ranks over gloo
+def _eval_worker(rank, world, port, q):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cfg = SimpleNamespace(multitask=True, task="x", tasks=["walker-run", "mw-door-open", "cheetah-run"], action_dim=4)
+        ScriptedEnv.counters.clear()
+        agent = ScriptedAgent(cfg, 2)
+        out = evaluate(agent, [ScriptedEnv(), ScriptedEnv()], 5)
+        q.put((rank, {n: (r.episode_rewards, r.episode_successes, r.episode_lengths) for n, r in out["tasks"].items()},
+               out["normalized_score"], out["env_steps"], out["act_calls"], agent.calls))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_split_the_episode_queue_and_merge_once():
+    """world_size 2 over gloo: every rank runs its own two environments on every second episode of the queue, no
+    collective in the loop, one all_gather_object at the end; both ranks return the same merged statistics, with
+    eval_episodes episodes per task."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_eval_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(2)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, t0_, s0, steps0, calls0, own0), (_, t1_, s1, steps1, calls1, own1) = res
+    assert t0_ == t1_ and s0 == s1 and steps0 == steps1 and calls0 == calls1
+    for name, (rew, suc, lens) in t0_.items():
+        assert len(rew) == len(suc) == len(lens) == 5
+    assert steps0 == sum(sum(v[2]) for v in t0_.values())
+    assert calls0 == max(own0, own1) and own0 + own1 < steps0          # each rank batched its own two environments
