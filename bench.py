@@ -368,8 +368,10 @@ def gpu_baselines(wl, cfg, dev, budget_s=40.0):
 
 
 def act_latency_e1(wl, sd, dev, args, calls=20):
-    """The reference's own call shape (evaluate.py:80): ONE environment per act(), CPU observation in, CPU action out,
-    CUDA-graph replay of the launch chain.  Median wall-clock ms per call (perf_counter around act(); it ends with .cpu())."""
+    """The reference's own call shape (evaluate.py:80): ONE environment per act(), CPU observation in, CPU action out; the
+    launch chain runs with the reference-order noise draws on a side stream between the launches (Planner.plan_interleaved;
+    --no-graph: all draws first, then eager launches).  Median wall-clock ms per call (perf_counter around act(); it ends
+    with .cpu())."""
     from tdmpc2_b200.tdmpc2 import TDMPC2
     cfg1 = bench_cfg(wl, 1)
     cfg1.cuda_graph = not args.no_graph
